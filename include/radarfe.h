@@ -1,0 +1,195 @@
+/*
+ * radarfe.h — C ABI of libradarfe.so: the B200 (sm_100a) radar-odometry front end.
+ *
+ * This is the drop-in boundary for the per-frame hot path of Samleo8/RadarSLAMPy
+ * ("RAW-ROAM").  The reference has no FFI of its own (it is pure Python over
+ * OpenCV / SciPy / networkx); each entry point below therefore replaces one Python
+ * call site of the reference, cited as file:line relative to the reference root.
+ * The Python modules in radarslampy_b200/ keep the reference's names and signatures
+ * and call these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every function returns RF_OK (0) or a
+ *     negative rf_status; rf_last_error() gives the message for the last failure.
+ *   - the caller owns every host buffer (C-contiguous, sizes passed explicitly); the
+ *     library never keeps a host pointer after the call returns.
+ *   - device memory, the CUDA stream and all workspaces are owned by the rf_handle.
+ *   - a handle is single-threaded; different handles may be used from different threads.
+ *   - entry points are synchronous on return unless their name ends in _async.
+ *   - there is NO CPU fallback: without a CUDA device rf_create fails with RF_E_CUDA.
+ */
+#ifndef RADARFE_H
+#define RADARFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RADARFE_VERSION 100 /* 0.1.0 */
+#if defined(__GNUC__)
+#define RF_API __attribute__((visibility("default")))
+#else
+#define RF_API
+#endif
+
+typedef enum rf_status {
+    RF_OK = 0,
+    RF_E_BADARG = -1,     /* null pointer, negative size, shape mismatch                  */
+    RF_E_CAPACITY = -2,   /* input exceeds a maximum fixed at rf_create (see rf_config)   */
+    RF_E_CUDA = -3,       /* CUDA runtime / driver error, or no sm_100 device             */
+    RF_E_WORKLIMIT = -4,  /* clique search exceeded rf_config.clique_node_limit           */
+    RF_E_NOMEM = -5
+} rf_status;
+
+/* Constants of the reference, as one POD.  rf_default_config() fills the reference's
+ * values; parity tests run with the defaults. */
+typedef struct rf_config {
+    int32_t azimuths;          /* 400   rows of an Oxford scan            parseData.py:39-43  */
+    int32_t raw_width;         /* 3779  bytes per row: 11 metadata + 3768 bins                */
+    int32_t meta_bytes;        /* 11                                                          */
+    int32_t range_bins;        /* 2025  int(87.5 / 0.0432)                parseData.py:49-51  */
+    int32_t downsample;        /* 2     => R = range_bins / 2, image 2R x 2R   parseData.py:119-125 */
+    int32_t max_features;      /* capacity per frame pair (K)                                  */
+    int32_t max_pairs;         /* capacity of one rf_batch                                     */
+    int32_t max_frames;        /* frames resident in one rf_batch                              */
+    int32_t klt_win;           /* 15    getTransformKLT.py:343                                 */
+    int32_t klt_max_level;     /* 3     getTransformKLT.py:77-84                               */
+    int32_t klt_max_iters;     /* 10                                                           */
+    float   klt_eps;           /* 0.03                                                         */
+    float   klt_min_eig;       /* 1e-4  cv2 default minEigThreshold                            */
+    float   klt_err_thr;       /* 10    ERR_THRESHOLD getTransformKLT.py:84,365                */
+    double  dist_thr_px;       /* 0.5 / 0.0864 = 5.787037037037036  outlierRejection.py:10-11  */
+    double  cart_res_m;        /* 0.0864 m per pixel                parseData.py:10-13         */
+    double  mds_period;        /* 0.25 s  (1 / RADAR_SCAN_FREQUENCY) motionDistortion.py:36    */
+    double  mds_sigma_p[2];    /* (4, 4)                             RawROAMSystem.py:135-139  */
+    double  mds_sigma_v[3];    /* (1, 1, (5 deg)^2)                                            */
+    int64_t clique_node_limit; /* per-pair bound on search-tree descents (RF_E_WORKLIMIT)      */
+    int32_t write_cart_f32;    /* batch path: also materialise the f32 Cartesian image         */
+    int32_t reserved;
+} rf_config;
+
+typedef struct rf_handle rf_handle; /* stream + workspaces + geometry tables            */
+typedef struct rf_frame rf_frame;   /* one device-resident scan: f32 cart + u8 pyramid   */
+typedef struct rf_batch rf_batch;   /* device-resident batch of independent frame pairs  */
+
+/* Result of one frame pair (what Tracker.track + Tracker.getTransform + the MDS solve
+ * return for it).  `src = R * target + h`, h in metres (getTransformKLT.py:129-162,
+ * Tracker.py:108-127). */
+typedef struct rf_pair_result {
+    double R[4];      /* row-major 2x2                                                       */
+    double h[2];      /* metres                                                              */
+    double mds_x[6];  /* [vx, vy, vtheta, Tx, Ty, Ttheta]   motionDistortion.py:295-325      */
+    int32_t n_features;  /* K handed in                                                      */
+    int32_t n_good;      /* after KLT status & (err < thr)      getTransformKLT.py:364-376   */
+    int32_t n_inliers;   /* clique size                          outlierRejection.py:71-78   */
+    int32_t mds_iters;
+    int32_t status;      /* RF_OK or RF_E_WORKLIMIT for this pair                            */
+    int32_t clique_nodes; /* search-tree descents spent                                      */
+} rf_pair_result;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+RF_API void rf_default_config(rf_config* cfg);
+RF_API int rf_create(const rf_config* cfg, int device, void* cuda_stream_or_null, rf_handle** out);
+RF_API void rf_destroy(rf_handle* h);
+RF_API const char* rf_last_error(const rf_handle* h_or_null);
+RF_API int rf_version(void);
+RF_API int rf_cart_size(const rf_handle* h);          /* 2R */
+RF_API void* rf_stream(const rf_handle* h);           /* cudaStream_t the kernels run on */
+/* CUDA-event timing on the handle's stream (bench.py uses it: torch events do not see
+ * this stream).  rf_timer_stop_ms synchronises and returns elapsed milliseconds. */
+RF_API int rf_timer_start(rf_handle* h);
+RF_API int rf_timer_stop_ms(rf_handle* h, float* ms);
+/* number of kernels launched by this handle since creation (bench.py: gpu_launches) */
+RF_API int64_t rf_launch_count(const rf_handle* h);
+
+/* ---- a1  parseData.extractDataFromRadarImage            parseData.py:17-53 ------- */
+/* raw u8 [A, raw_width] -> polar f32 [A, range_bins] (= u8 / 255.f, IEEE division),
+ * timestamps i64 [A], azimuths f32 [A] (radians), valid u8 [A]. Any output may be NULL. */
+RF_API int rf_extract_polar(rf_handle* h, const uint8_t* raw, float* polar, int64_t* timestamps,
+                     float* azimuths, uint8_t* valid);
+
+/* ---- frames ---------------------------------------------------------------------- */
+RF_API int rf_frame_create(rf_handle* h, rf_frame** out);
+RF_API void rf_frame_destroy(rf_handle* h, rf_frame* f);
+
+/* ---- a2+a3  parseData.convertPolarImageToCartesian       parseData.py:100-135 -----
+ *             (img*255).astype(uint8) + cv2 pyramid         getTransformKLT.py:356-360
+ * Exactly one of raw (u8 [A, raw_width]) / polar (f32 [A, range_bins], values k/255)
+ * is non-NULL.  Fills `frame` (f32 cart, u8 image, pyramid levels 1..klt_max_level) and,
+ * if cart_out != NULL, copies the f32 image [2R, 2R] to the host. */
+RF_API int rf_polar_to_cart(rf_handle* h, const uint8_t* raw, const float* polar, rf_frame* frame,
+                     float* cart_out);
+/* Build a frame from a caller-supplied f32 Cartesian image [n, n], n == 2R (the path
+ * getTrackedPointsKLT takes when handed plain NumPy images). */
+RF_API int rf_frame_from_cart(rf_handle* h, const float* cart, int n, rf_frame* frame);
+/* what: 0 = f32 cart [2R,2R]; 1+l = u8 pyramid level l.  *rows/*cols receive the shape. */
+RF_API int rf_frame_download(rf_handle* h, const rf_frame* f, int what, void* out, int* rows, int* cols);
+
+/* ---- a4+a5  cv2.calcOpticalFlowPyrLK + err gating        getTransformKLT.py:359-376 */
+/* pts [K,2] (x,y) -> next [K,2], status u8 [K] (cv2 status & (err < klt_err_thr) when
+ * apply_err_gate != 0), err f32 [K]. */
+RF_API int rf_klt(rf_handle* h, const rf_frame* prev, const rf_frame* next, const float* pts, int K,
+           int apply_err_gate, float* next_xy, uint8_t* status, float* err);
+
+/* ---- a6  outlierRejection.rejectOutliers                 outlierRejection.py:16-95 */
+/* mask u8 [K] = membership in the first largest maximal clique in networkx order. */
+RF_API int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, int K,
+                       uint8_t* mask, int* n_inliers, int* nodes_or_null);
+/* adjacency only (K x K bytes), for tests                   outlierRejection.py:49-58 */
+RF_API int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K,
+                             uint8_t* adj);
+
+/* ---- a7  getTransformKLT.calculateTransformSVD           getTransformKLT.py:129-162 */
+/* src = R * tgt + h (pixel units; Tracker.getTransform scales h by cart_res_m). */
+RF_API int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, double R[4], double hvec[2]);
+
+/* ---- a8  MotionDistortionSolver.optimize_library         motionDistortion.py:80-325 */
+RF_API int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const double* p_jt, int N,
+                 const double T_wj[9], double x_out[6], int* iters, double* cost);
+/* static MotionDistortionSolver.undistort                  motionDistortion.py:127-153 */
+RF_API int rf_mds_undistort(rf_handle* h, const double v[3], const double* pts_xy, int N, double period,
+                     double* out_xy);
+
+/* ---- a9  ANMS.ssc                                        ANMS.py:5-102 ------------- */
+/* kp [n,3] f64 (row, col, sigma) in caller order -> sel_idx [<= n] in selection order. */
+RF_API int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double tol, int cols, int rows,
+           int32_t* sel_idx, int* m);
+
+/* ---- a10 detector (response + 3x3 NMS + threshold)       getFeatures.py:22-53 ------ */
+/* mode 0: min-eigenvalue structure tensor (Sobel 3x3, 3x3 box), cv2.cornerMinEigenVal
+ * semantics.  Candidates are returned sorted by (response desc, index asc):
+ * out [cap,3] f64 (row, col, response).  *n receives the total candidate count. */
+RF_API int rf_detect(rf_handle* h, const rf_frame* f, int mode, float threshold, double* out, int cap, int* n);
+/* response map only (f32 [2R,2R]) — used by the parity tests */
+RF_API int rf_corner_response(rf_handle* h, const rf_frame* f, int mode, float* resp);
+
+/* ---- a12 getPointCloud.getPointCloudPolarInd             getPointCloud.py:11-54 ---- */
+/* polar f32 [A, W] -> out [cap,2] i64 (azimuth, range), azimuth-major order. */
+RF_API int rf_polar_peaks(rf_handle* h, const float* polar, int A, int W, int64_t* out, int64_t cap, int64_t* n);
+
+/* ---- a11 fused pair / batch: Tracker.track + getTransform (+ MDS)  Tracker.py:35-127 */
+RF_API int rf_batch_create(rf_handle* h, rf_batch** out);
+RF_API void rf_batch_destroy(rf_handle* h, rf_batch* b);
+/* Host -> device staging.  raw: [n_frames, A, raw_width] u8; pair_idx: [n_pairs,2]
+ * (prev frame, next frame) indices into raw; feats: [n_pairs, max_features, 2] f32 with
+ * feat_counts[n_pairs]; prev_pose: [n_pairs,3] (x,y,theta) or NULL for identity. */
+RF_API int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
+                    int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose);
+/* Device-only: every stage for every pair, no host synchronisation before return. */
+RF_API int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds);
+RF_API int rf_sync(rf_handle* h);
+/* Device -> host: results [n_pairs]; next_xy [n_pairs,max_features,2] and status
+ * [n_pairs,max_features] may be NULL. */
+RF_API int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status);
+/* upload + run + download in one call (what Tracker.track/getTransform amount to). */
+RF_API int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
+                   int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose,
+                   int with_mds, rf_pair_result* results, float* next_xy, uint8_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADARFE_H */

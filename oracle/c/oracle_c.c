@@ -441,8 +441,9 @@ typedef struct { pyset subg, cand, ext; } frame;
  *   yields_buf (optional): first `yields_cap` ints of the concatenated yields,
  *           each as [size, v0, v1, ...] — used to pin the ORDER against live networkx.
  * Returns clique size. */
-ORC_API int orc_first_max_clique(const uint8_t* adjm, int K, int* out_clique, long* n_yields,
-                                 int* yields_buf, long yields_cap, long* yields_len) {
+static int first_max_clique_impl(const uint8_t* adjm, int K, int* out_clique, long* n_yields,
+                                 int* yields_buf, long yields_cap, long* yields_len, int prune, long* n_descents) {
+    long nd = 0;
     if (n_yields) *n_yields = 0; if (yields_len) *yields_len = 0;
     if (K == 0) return 0;
     pyset* adj = (pyset*)malloc(sizeof(pyset) * K);
@@ -469,7 +470,10 @@ ORC_API int orc_first_max_clique(const uint8_t* adjm, int K, int* out_clique, lo
                 ps_free(&subg_q);
             } else {
                 pyset cand_q; ps_and(&cand_q, &cand, &adj[q]);
-                if (cand_q.used) {
+                /* order-safe bound: a child that cannot yield a clique LARGER than the best
+                 * so far can never replace it (strict '>' at outlierRejection.py:73). */
+                if (cand_q.used && !(prune && qn + cand_q.used <= best)) {
+                    nd++;
                     stack[sp].subg = subg; stack[sp].cand = cand; stack[sp].ext = ext; sp++;
                     Q[qn++] = -1;
                     subg = subg_q; cand = cand_q;
@@ -487,7 +491,21 @@ ORC_API int orc_first_max_clique(const uint8_t* adjm, int K, int* out_clique, lo
     for (int v = 0; v < K; ++v) ps_free(&adj[v]);
     free(adj); free(Q); free(stack);
     if (n_yields) *n_yields = ny; if (yields_len) *yields_len = yl;
+    if (n_descents) *n_descents = nd;
     return best;
+}
+
+ORC_API int orc_first_max_clique(const uint8_t* adjm, int K, int* out_clique, long* n_yields,
+                                 int* yields_buf, long yields_cap, long* yields_len) {
+    return first_max_clique_impl(adjm, K, out_clique, n_yields, yields_buf, yields_cap, yields_len, 0, 0);
+}
+
+/* Same traversal with the order-safe running-best bound; returns the identical clique
+ * (tests pin this against the unpruned enumeration) and reports how many child levels
+ * were actually descended. */
+ORC_API int orc_first_max_clique_pruned(const uint8_t* adjm, int K, int* out_clique, long* n_descents) {
+    long ny, yl;
+    return first_max_clique_impl(adjm, K, out_clique, &ny, 0, 0, &yl, 1, n_descents);
 }
 
 /* ------------------------------------------------------------------------------------

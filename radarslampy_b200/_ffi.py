@@ -1,0 +1,329 @@
+"""ctypes binding of libradarfe.so (include/radarfe.h).  The ONLY module that touches the
+shared library; every drop-in module goes through `RadarFE`.
+
+There is no CPU fallback: if the library is missing, or no sm_100 GPU is visible,
+construction raises."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libradarfe.so")
+
+RF_OK, RF_E_BADARG, RF_E_CAPACITY, RF_E_CUDA, RF_E_WORKLIMIT, RF_E_NOMEM = 0, -1, -2, -3, -4, -5
+
+
+class RfConfig(C.Structure):
+    _fields_ = [
+        ("azimuths", C.c_int32), ("raw_width", C.c_int32), ("meta_bytes", C.c_int32), ("range_bins", C.c_int32),
+        ("downsample", C.c_int32), ("max_features", C.c_int32), ("max_pairs", C.c_int32), ("max_frames", C.c_int32),
+        ("klt_win", C.c_int32), ("klt_max_level", C.c_int32), ("klt_max_iters", C.c_int32),
+        ("klt_eps", C.c_float), ("klt_min_eig", C.c_float), ("klt_err_thr", C.c_float),
+        ("dist_thr_px", C.c_double), ("cart_res_m", C.c_double), ("mds_period", C.c_double),
+        ("mds_sigma_p", C.c_double * 2), ("mds_sigma_v", C.c_double * 3),
+        ("clique_node_limit", C.c_int64), ("write_cart_f32", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class RfPairResult(C.Structure):
+    _fields_ = [
+        ("R", C.c_double * 4), ("h", C.c_double * 2), ("mds_x", C.c_double * 6),
+        ("n_features", C.c_int32), ("n_good", C.c_int32), ("n_inliers", C.c_int32), ("mds_iters", C.c_int32),
+        ("status", C.c_int32), ("clique_nodes", C.c_int32),
+    ]
+
+
+PAIR_RESULT_DTYPE = np.dtype([
+    ("R", np.float64, (4,)), ("h", np.float64, (2,)), ("mds_x", np.float64, (6,)),
+    ("n_features", np.int32), ("n_good", np.int32), ("n_inliers", np.int32), ("mds_iters", np.int32),
+    ("status", np.int32), ("clique_nodes", np.int32)], align=True)
+assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(RfPairResult)
+
+# every symbol include/radarfe.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "rf_default_config", "rf_create", "rf_destroy", "rf_last_error", "rf_version", "rf_cart_size", "rf_stream",
+    "rf_timer_start", "rf_timer_stop_ms", "rf_launch_count", "rf_extract_polar", "rf_frame_create",
+    "rf_frame_destroy", "rf_polar_to_cart", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
+    "rf_reject_outliers", "rf_consistency_adjacency", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
+    "rf_detect", "rf_corner_response", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
+    "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """dlopen libradarfe.so (built by radarslampy_b200._build); raises if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: build it with `python -m radarslampy_b200._build` "
+                    "(this package has no CPU fallback)")
+            L = C.CDLL(LIB_PATH)
+            L.rf_last_error.restype = C.c_char_p
+            L.rf_last_error.argtypes = [C.c_void_p]
+            L.rf_stream.restype = C.c_void_p
+            L.rf_stream.argtypes = [C.c_void_p]
+            L.rf_launch_count.restype = C.c_int64
+            L.rf_launch_count.argtypes = [C.c_void_p]
+            L.rf_destroy.restype = None
+            L.rf_destroy.argtypes = [C.c_void_p]
+            L.rf_frame_destroy.restype = None
+            L.rf_frame_destroy.argtypes = [C.c_void_p, C.c_void_p]
+            L.rf_batch_destroy.restype = None
+            L.rf_batch_destroy.argtypes = [C.c_void_p, C.c_void_p]
+            L.rf_default_config.restype = None
+            _lib = L
+    return _lib
+
+
+def default_config() -> RfConfig:
+    cfg = RfConfig()
+    load_library().rf_default_config(C.byref(cfg))
+    return cfg
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Frame:
+    """Device-resident scan (f32 Cartesian image + u8 LK pyramid)."""
+
+    def __init__(self, fe):
+        self.fe = fe
+        p = C.c_void_p()
+        fe._check(fe.lib.rf_frame_create(fe.h, C.byref(p)))
+        self.p = p
+
+    def close(self):
+        if self.p and self.fe.h:
+            self.fe.lib.rf_frame_destroy(self.fe.h, self.p)
+        self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def download(self, what=0):
+        fe = self.fe
+        r, c = C.c_int(0), C.c_int(0)
+        fe._check(fe.lib.rf_frame_download(fe.h, self.p, what, None, C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.float32 if what == 0 else np.uint8)
+        fe._check(fe.lib.rf_frame_download(fe.h, self.p, what, _ptr(out), C.byref(r), C.byref(c)))
+        return out
+
+
+class RadarFE:
+    """One rf_handle: a CUDA stream, the geometry table and the workspaces on one GPU."""
+
+    def __init__(self, cfg: RfConfig = None, device: int = 0, stream: int = None):
+        self.lib = load_library()
+        self.cfg = cfg if cfg is not None else default_config()
+        h = C.c_void_p()
+        rc = self.lib.rf_create(C.byref(self.cfg), int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != RF_OK:
+            msg = self.lib.rf_last_error(None)
+            raise RuntimeError(f"rf_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+        self.device = device
+        self.n = self.lib.rf_cart_size(self.h)
+
+    # -- plumbing ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == RF_OK:
+            return
+        msg = self.lib.rf_last_error(self.h)
+        msg = msg.decode() if msg else ""
+        if rc in (RF_E_BADARG, RF_E_CAPACITY):
+            raise ValueError(f"libradarfe ({rc}): {msg}")
+        raise RuntimeError(f"libradarfe ({rc}): {msg}")
+
+    def launch_count(self) -> int:
+        return int(self.lib.rf_launch_count(self.h))
+
+    def timer_start(self):
+        self._check(self.lib.rf_timer_start(self.h))
+
+    def timer_stop_ms(self) -> float:
+        ms = C.c_float(0)
+        self._check(self.lib.rf_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self.lib.rf_sync(self.h))
+
+    def new_frame(self) -> Frame:
+        return Frame(self)
+
+    # -- a1 ---------------------------------------------------------------------
+    def extract_polar(self, raw):
+        raw = _c(raw, np.uint8)
+        A, W = self.cfg.azimuths, self.cfg.range_bins
+        if raw.shape != (A, self.cfg.raw_width):
+            raise ValueError(f"raw scan must be {(A, self.cfg.raw_width)}, got {raw.shape}")
+        polar = np.empty((A, W), np.float32)
+        ts = np.empty((A, 1), np.int64)
+        az = np.empty((A, 1), np.float32)
+        valid = np.empty((A, 1), np.uint8)
+        self._check(self.lib.rf_extract_polar(self.h, _ptr(raw), _ptr(polar), _ptr(ts), _ptr(az), _ptr(valid)))
+        return polar, ts, az, valid.astype(bool)
+
+    # -- a2 / a3 ----------------------------------------------------------------
+    def polar_to_cart(self, raw=None, polar=None, frame: Frame = None, want_host=True):
+        frame = frame or self.new_frame()
+        out = np.empty((self.n, self.n), np.float32) if want_host else None
+        if raw is not None:
+            raw = _c(raw, np.uint8)
+            if raw.shape != (self.cfg.azimuths, self.cfg.raw_width):
+                raise ValueError("raw scan has the wrong shape")
+            self._check(self.lib.rf_polar_to_cart(self.h, _ptr(raw), None, frame.p, _ptr(out)))
+        else:
+            polar = _c(polar, np.float32)
+            if polar.shape != (self.cfg.azimuths, self.cfg.range_bins):
+                raise ValueError(f"polar image must be {(self.cfg.azimuths, self.cfg.range_bins)}, got {polar.shape}")
+            self._check(self.lib.rf_polar_to_cart(self.h, None, _ptr(polar), frame.p, _ptr(out)))
+        return frame, out
+
+    def frame_from_cart(self, cart, frame: Frame = None):
+        cart = _c(cart, np.float32)
+        if cart.ndim != 2 or cart.shape[0] != cart.shape[1]:
+            raise ValueError("Cartesian image must be square")
+        frame = frame or self.new_frame()
+        self._check(self.lib.rf_frame_from_cart(self.h, _ptr(cart), cart.shape[0], frame.p))
+        return frame
+
+    # -- a4 / a5 ----------------------------------------------------------------
+    def klt(self, prev: Frame, nxt: Frame, pts, apply_err_gate=True):
+        pts = _c(pts, np.float32).reshape(-1, 2)
+        K = pts.shape[0]
+        out = np.zeros((K, 2), np.float32)
+        st = np.zeros((K, 1), np.uint8)
+        err = np.zeros((K, 1), np.float32)
+        if K:
+            self._check(self.lib.rf_klt(self.h, prev.p, nxt.p, _ptr(pts), K, int(apply_err_gate), _ptr(out), _ptr(st),
+                                        _ptr(err)))
+        return out, st, err
+
+    # -- a6 ---------------------------------------------------------------------
+    def reject_outliers(self, prev_xy, new_xy):
+        a = _c(prev_xy, np.float32).reshape(-1, 2)
+        b = _c(new_xy, np.float32).reshape(-1, 2)
+        if a.shape != b.shape:
+            raise ValueError("Coordinates should be the same shape")
+        K = a.shape[0]
+        mask = np.zeros(K, np.uint8)
+        n_in, nodes = C.c_int(0), C.c_int(0)
+        if K:
+            self._check(self.lib.rf_reject_outliers(self.h, _ptr(a), _ptr(b), K, _ptr(mask), C.byref(n_in), C.byref(nodes)))
+        return mask.astype(bool), n_in.value, nodes.value
+
+    def consistency_adjacency(self, prev_xy, new_xy):
+        a = _c(prev_xy, np.float32).reshape(-1, 2)
+        b = _c(new_xy, np.float32).reshape(-1, 2)
+        K = a.shape[0]
+        adj = np.zeros((K, K), np.uint8)
+        self._check(self.lib.rf_consistency_adjacency(self.h, _ptr(a), _ptr(b), K, _ptr(adj)))
+        return adj
+
+    # -- a7 ---------------------------------------------------------------------
+    def kabsch(self, src_xy, tgt_xy):
+        s = _c(src_xy, np.float32).reshape(-1, 2)
+        t = _c(tgt_xy, np.float32).reshape(-1, 2)
+        if s.shape != t.shape:
+            raise ValueError("point sets must have the same shape")
+        R = np.zeros((2, 2), np.float64)
+        h = np.zeros((2, 1), np.float64)
+        self._check(self.lib.rf_kabsch(self.h, _ptr(s), _ptr(t), s.shape[0], _ptr(R), _ptr(h)))
+        return R, h
+
+    # -- a8 ---------------------------------------------------------------------
+    def mds_solve(self, T_wj0, p_w, p_jt, T_wj):
+        T0 = _c(T_wj0, np.float64).reshape(3, 3)
+        T1 = _c(T_wj, np.float64).reshape(3, 3)
+        pw = _c(np.asarray(p_w)[:, :2], np.float64)
+        pj = _c(np.asarray(p_jt)[:, :2], np.float64)
+        if pw.shape != pj.shape:
+            raise ValueError("p_w and p_jt must have the same shape")
+        x = np.zeros(6, np.float64)
+        it = C.c_int(0)
+        cost = C.c_double(0)
+        self._check(self.lib.rf_mds_solve(self.h, _ptr(T0), _ptr(pw), _ptr(pj), pw.shape[0], _ptr(T1), _ptr(x),
+                                          C.byref(it), C.byref(cost)))
+        return x, it.value, cost.value
+
+    def mds_undistort(self, v, pts_xy, period):
+        v = _c(v, np.float64).reshape(3)
+        p = _c(np.asarray(pts_xy)[:, :2], np.float64)
+        out = np.zeros_like(p)
+        if p.shape[0]:
+            self._check(self.lib.rf_mds_undistort(self.h, _ptr(v), _ptr(p), p.shape[0], C.c_double(period), _ptr(out)))
+        return out
+
+    # -- a9 ---------------------------------------------------------------------
+    def ssc(self, keypoints, num_ret_points, tolerance, cols, rows):
+        kp = _c(keypoints, np.float64).reshape(-1, 3)
+        n = kp.shape[0]
+        sel = np.zeros(max(n, 1), np.int32)
+        m = C.c_int(0)
+        self._check(self.lib.rf_ssc(self.h, _ptr(kp), n, int(num_ret_points), C.c_double(tolerance), int(cols), int(rows),
+                                    _ptr(sel), C.byref(m)))
+        return sel[:m.value].copy()
+
+    # -- a10 --------------------------------------------------------------------
+    def detect(self, frame: Frame, threshold, cap=65536, mode=0):
+        out = np.zeros((cap, 3), np.float64)
+        n = C.c_int(0)
+        self._check(self.lib.rf_detect(self.h, frame.p, mode, C.c_float(threshold), _ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy(), n.value
+
+    def corner_response(self, frame: Frame, mode=0):
+        out = np.zeros((self.n, self.n), np.float32)
+        self._check(self.lib.rf_corner_response(self.h, frame.p, mode, _ptr(out)))
+        return out
+
+    # -- a12 --------------------------------------------------------------------
+    def polar_peaks(self, polar):
+        polar = _c(polar, np.float32)
+        A, W = polar.shape
+        cap = A * (W // 2 + 1)
+        out = np.zeros((cap, 2), np.int64)
+        n = C.c_int64(0)
+        self._check(self.lib.rf_polar_peaks(self.h, _ptr(polar), A, W, _ptr(out), C.c_int64(cap), C.byref(n)))
+        return out[:n.value].copy()
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device: int = 0) -> RadarFE:
+    """Process-wide engine used by the drop-in modules (one per device)."""
+    with _default_lock:
+        fe = _default.get(device)
+        if fe is None:
+            fe = RadarFE(device=device)
+            _default[device] = fe
+        return fe

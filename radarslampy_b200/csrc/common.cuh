@@ -1,0 +1,94 @@
+// common.cuh — handle layout, error plumbing and small device helpers shared by every
+// translation unit of libradarfe.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/radarfe.h"
+
+#define RF_MAX_LEVELS 4  // pyramid levels 0..3 (klt_max_level <= 3)
+
+// A set of `count` device-resident frames with uniform strides (count == 1 for rf_frame).
+struct FrameSet {
+    float* cart;                   // [count][n][n] f32 (null when the batch path elides it)
+    size_t cart_stride;            // elements between frames
+    uint8_t* lvl[RF_MAX_LEVELS];   // u8 pyramid levels, tightly packed rows
+    size_t lvl_stride[RF_MAX_LEVELS];  // bytes between frames
+    int w[RF_MAX_LEVELS], h[RF_MAX_LEVELS];
+    int n_levels;
+    int count;
+};
+struct rf_frame {
+    FrameSet fs;
+};
+
+struct rf_handle {
+    rf_config cfg;
+    int device;
+    cudaStream_t stream;
+    bool owns_stream;
+    int n;          // cartesian size 2R
+    int R;
+    int sm_count;
+    // geometry table: packed fixed-point sample coordinates of cv2.warpPolar's inverse map
+    uint32_t* map;  // [n][n]  (sx | sy << 17), sx = round(32*rho), sy = round(32*(phi+1))
+    // staging
+    uint8_t* d_raw;      // one raw scan
+    float* d_polar;      // one f32 polar image
+    uint8_t* d_polar_u8; // [A][range_bins] u8 recovered from an f32 polar
+    void* d_scratch; size_t scratch_bytes;    // generic device scratch (grown on demand)
+    void* h_pinned; size_t pinned_bytes;      // generic pinned host staging
+    cudaEvent_t ev0, ev1;
+    int64_t launches;
+    std::string err;
+};
+
+extern thread_local std::string g_rf_err;  // for failures without a handle
+
+int rf_fail(rf_handle* h, int code, const char* fmt, ...);
+int rf_ensure_scratch(rf_handle* h, size_t bytes);
+int rf_ensure_pinned(rf_handle* h, size_t bytes);
+
+#define RF_CUDA(h, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return rf_fail((h), RF_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                           __FILE__, __LINE__);                                                  \
+    } while (0)
+
+#define RF_CHECK_LAUNCH(h)                                                                       \
+    do {                                                                                         \
+        (h)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess)                                                                   \
+            return rf_fail((h), RF_E_CUDA, "kernel launch failed: %s (%s:%d)",                   \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+    } while (0)
+
+// ---- device helpers ---------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int p, int len) {
+    // cv::BORDER_REFLECT_101 for |overshoot| < len (always true here: borders <= 16 px, len > 15)
+    if (p < 0) p = -p;
+    if (p >= len) p = 2 * len - 2 - p;
+    return p;
+}
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }  // ties-to-even, like cvRound
+__device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
+
+// ---- per-stage launchers (defined in the k_*.cu files) ------------------------------
+int rf_frameset_alloc(rf_handle* h, FrameSet* fs, int count, bool with_f32);
+void rf_frameset_free(FrameSet* fs);
+int rf_launch_build_map(rf_handle* h);
+// src: `n_frames` scans, frame i at d_src + i*src_frame_stride (elements), row pitch and first
+// power column given; tap type u8 (raw scan) or f32 (caller polar image)
+int rf_launch_polar2cart_u8(rf_handle* h, const uint8_t* d_src, size_t src_frame_stride, int row_pitch,
+                            int col0, const FrameSet& dst, int first, int n_frames, bool write_f32);
+int rf_launch_polar2cart_f32(rf_handle* h, const float* d_src, int row_pitch, const FrameSet& dst);
+int rf_launch_cart_to_u8(rf_handle* h, const FrameSet& fs);
+int rf_launch_pyramid(rf_handle* h, const FrameSet& fs, int first, int n_frames);
+int rf_launch_extract(rf_handle* h, const uint8_t* d_raw, float* d_polar);

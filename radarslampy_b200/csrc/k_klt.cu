@@ -1,0 +1,273 @@
+// k_klt.cu — pyramidal Lucas-Kanade tracking with OpenCV's fixed-point semantics.
+//
+// Replaces cv2.calcOpticalFlowPyrLK(winSize=(15,15), maxLevel=3, criteria=(EPS|COUNT,10,0.03))
+// at getTransformKLT.py:359-360 and the err gating at getTransformKLT.py:364-365.
+// Restated algorithm: oracle/c/oracle_c.c::lk_level (SURVEY.md Spec S-a4).
+//
+// Mapping: ONE WARP tracks ONE feature through all pyramid levels.  Per level the warp
+//   1. stages the 18x18 u8 neighbourhood of the previous image in shared memory
+//      (REFLECT_101 padding exactly like cv's padded pyramid),
+//   2. evaluates the Scharr derivative on the fly for the 16x16 positions the window can
+//      touch (cv computes a whole-image derivative; outside the image it is 0),
+//   3. builds the Q5 image patch and Q0 derivative patches of the 15x15 window in
+//      REGISTERS (8 window pixels per lane) and reduces the 2x2 normal matrix,
+//   4. iterates: stages the 16x16 u8 window of the next image, forms the mismatch vector
+//      with exact integer products, reduces with REDUX (split hi/lo 16 bits, exact),
+//      and solves the 2x2 system in f32.
+// All integer sums are exact; cv2 accumulates the same products in f32, so positions agree
+// to ~5e-4 px (tolerance in north_star: 0.02 px) and status/err gating is identical.
+#include "common.cuh"
+
+#define KLT_WARPS 4
+#define KLT_WIN 15
+#define KLT_NPIX 225
+#define KLT_PER_LANE 8
+
+struct KltArgs {
+    FrameSet prev, next;
+    const int32_t* pair_idx;  // [P][2] frame indices (prev set, next set) or nullptr -> (0,0)
+    const float* pts;         // [P][Kmax][2]
+    const int32_t* counts;    // [P] or nullptr -> Kmax
+    int Kmax, P;
+    float* next_xy;           // [P][Kmax][2]
+    uint8_t* status;          // [P][Kmax]
+    float* err;               // [P][Kmax]
+    int max_iters;
+    double eps2;
+    float min_eig, err_thr;
+    int gate;
+};
+
+struct WarpSmem {
+    uint8_t I[18][20];   // previous-image neighbourhood, origin (ip.x-1, ip.y-1)
+    short2 D[16][16];    // Scharr (dx, dy) at (ip.x + c, ip.y + r)
+    uint8_t J[16][16];   // next-image window, origin (in.x, in.y)
+};
+
+// exact warp sum of int32 values whose total may exceed 32 bits
+__device__ __forceinline__ long long warp_sum_exact(int v) {
+    int lo = v & 0xFFFF, hi = v >> 16;  // v == (hi << 16) + lo, lo in [0, 65535]
+    int slo = __reduce_add_sync(0xffffffffu, lo);
+    int shi = __reduce_add_sync(0xffffffffu, hi);
+    return ((long long)shi << 16) + (long long)slo;
+}
+
+__device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
+    const float ia = __fsub_rn(1.f, a), ib = __fsub_rn(1.f, b);
+    w00 = cv_round(__fmul_rn(__fmul_rn(ia, ib), 16384.f));
+    w01 = cv_round(__fmul_rn(__fmul_rn(a, ib), 16384.f));
+    w10 = cv_round(__fmul_rn(__fmul_rn(ia, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+__device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ J, int w, int h, int ox, int oy, int lane) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = lane + 32 * k, r = idx >> 4, c = idx & 15;
+        s.J[r][c] = __ldg(J + (size_t)reflect101(oy + r, h) * w + reflect101(ox + c, w));
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int j_sample(const WarpSmem& s, int y, int x, int w00, int w01, int w10, int w11) {
+    const int v = s.J[y][x] * w00 + s.J[y][x + 1] * w01 + s.J[y + 1][x] * w10 + s.J[y + 1][x + 1] * w11;
+    return (v + (1 << 8)) >> 9;
+}
+
+__global__ void __launch_bounds__(KLT_WARPS * 32) k_klt(const KltArgs a) {
+    __shared__ WarpSmem smem[KLT_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * KLT_WARPS + wib;
+    const int pair = (int)(gw / a.Kmax), k = (int)(gw - (long long)pair * a.Kmax);
+    if (pair >= a.P) return;
+    const int count = a.counts ? a.counts[pair] : a.Kmax;
+    if (k >= count) return;
+    WarpSmem& s = smem[wib];
+    const int fprev = a.pair_idx ? a.pair_idx[2 * pair] : 0;
+    const int fnext = a.pair_idx ? a.pair_idx[2 * pair + 1] : 0;
+    const size_t o = (size_t)pair * a.Kmax + k;
+    const float ptx = a.pts[2 * o], pty = a.pts[2 * o + 1];
+    const float half = 7.0f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+
+    float nx = 0.f, ny = 0.f;  // nextPts[ptidx]
+    int status = 1;
+    float err = 0.f;
+    const int top = a.prev.n_levels - 1;
+
+    // per-lane window pixels (idx = lane + 32*j < 225)
+    int wy[KLT_PER_LANE], wx[KLT_PER_LANE];
+#pragma unroll
+    for (int j = 0; j < KLT_PER_LANE; ++j) {
+        const int idx = lane + 32 * j;
+        wy[j] = idx / KLT_WIN; wx[j] = idx - wy[j] * KLT_WIN;
+    }
+
+    for (int l = top; l >= 0; --l) {
+        const int w = a.prev.w[l], h = a.prev.h[l];
+        const uint8_t* __restrict__ I = a.prev.lvl[l] + (size_t)fprev * a.prev.lvl_stride[l];
+        const uint8_t* __restrict__ J = a.next.lvl[l] + (size_t)fnext * a.next.lvl_stride[l];
+        const float sc = 1.f / (float)(1 << l);
+        float px = __fmul_rn(ptx, sc), py = __fmul_rn(pty, sc);
+        if (l == top) { nx = px; ny = py; }
+        else { nx = __fmul_rn(nx, 2.f); ny = __fmul_rn(ny, 2.f); }
+        px = __fsub_rn(px, half); py = __fsub_rn(py, half);
+        const int ipx = cv_floor(px), ipy = cv_floor(py);
+        if (ipx < -KLT_WIN || ipx >= w || ipy < -KLT_WIN || ipy >= h) {
+            if (l == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        q14_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        __syncwarp();
+        // 1. 18x18 neighbourhood (324 bytes)
+        for (int idx = lane; idx < 18 * 18; idx += 32) {
+            const int r = idx / 18, c = idx - r * 18;
+            s.I[r][c] = __ldg(I + (size_t)reflect101(ipy - 1 + r, h) * w + reflect101(ipx - 1 + c, w));
+        }
+        __syncwarp();
+        // 2. Scharr at the 16x16 positions (cv::calcSharrDeriv; zero outside the image)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int idx = lane + 32 * j, r = idx >> 4, c = idx & 15;
+            const int X = ipx + c, Y = ipy + r;
+            int gx = 0, gy = 0;
+            if (X >= 0 && X < w && Y >= 0 && Y < h) {
+                const int p00 = s.I[r][c], p01 = s.I[r][c + 1], p02 = s.I[r][c + 2];
+                const int p10 = s.I[r + 1][c], p12 = s.I[r + 1][c + 2];
+                const int p20 = s.I[r + 2][c], p21 = s.I[r + 2][c + 1], p22 = s.I[r + 2][c + 2];
+                gx = (3 * p02 + 10 * p12 + 3 * p22) - (3 * p00 + 10 * p10 + 3 * p20);
+                gy = (3 * p20 + 10 * p21 + 3 * p22) - (3 * p00 + 10 * p01 + 3 * p02);
+            }
+            s.D[r][c] = make_short2((short)gx, (short)gy);
+        }
+        __syncwarp();
+        // 3. window patches in registers + normal matrix
+        int Iw[KLT_PER_LANE], Ix[KLT_PER_LANE], Iy[KLT_PER_LANE];
+        int a11 = 0, a12 = 0, a22 = 0;
+#pragma unroll
+        for (int j = 0; j < KLT_PER_LANE; ++j) {
+            Iw[j] = Ix[j] = Iy[j] = 0;
+            if (lane + 32 * j < KLT_NPIX) {
+                const int y = wy[j], x = wx[j];
+                const int iv = s.I[y + 1][x + 1] * w00 + s.I[y + 1][x + 2] * w01 + s.I[y + 2][x + 1] * w10 +
+                               s.I[y + 2][x + 2] * w11;
+                const short2 d00 = s.D[y][x], d01 = s.D[y][x + 1], d10 = s.D[y + 1][x], d11 = s.D[y + 1][x + 1];
+                const int ixv = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
+                const int iyv = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
+                Iw[j] = (iv + (1 << 8)) >> 9;
+                Ix[j] = ixv; Iy[j] = iyv;
+                a11 += ixv * ixv; a12 += ixv * iyv; a22 += iyv * iyv;
+            }
+        }
+        const float A11 = __fmul_rn((float)warp_sum_exact(a11), FLT_SCALE);
+        const float A12 = __fmul_rn((float)warp_sum_exact(a12), FLT_SCALE);
+        const float A22 = __fmul_rn((float)warp_sum_exact(a22), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dif = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * KLT_NPIX));
+        if (minEig < a.min_eig || D < 1.1920928955078125e-07f) {
+            if (l == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        float qx = __fsub_rn(nx, half), qy = __fsub_rn(ny, half);  // nextPt -= halfWin
+        float pdx = 0.f, pdy = 0.f;
+        // 4. iterations
+        for (int it = 0; it < a.max_iters; ++it) {
+            const int inx = cv_floor(qx), iny = cv_floor(qy);
+            if (inx < -KLT_WIN || inx >= w || iny < -KLT_WIN || iny >= h) {
+                if (l == 0) status = 0;
+                break;
+            }
+            q14_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
+            __syncwarp();
+            load_J(s, J, w, h, inx, iny, lane);
+            int b1 = 0, b2 = 0;
+#pragma unroll
+            for (int j = 0; j < KLT_PER_LANE; ++j) {
+                if (lane + 32 * j < KLT_NPIX) {
+                    const int diff = j_sample(s, wy[j], wx[j], w00, w01, w10, w11) - Iw[j];
+                    b1 += diff * Ix[j]; b2 += diff * Iy[j];
+                }
+            }
+            const float B1 = __fmul_rn((float)warp_sum_exact(b1), FLT_SCALE);
+            const float B2 = __fmul_rn((float)warp_sum_exact(b2), FLT_SCALE);
+            const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, B2), __fmul_rn(A22, B1)), D);
+            const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, B1), __fmul_rn(A11, B2)), D);
+            qx = __fadd_rn(qx, ddx); qy = __fadd_rn(qy, ddy);
+            nx = __fadd_rn(qx, half); ny = __fadd_rn(qy, half);
+            if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= a.eps2) break;
+            if (it > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 && fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
+                nx = __fsub_rn(nx, __fmul_rn(ddx, 0.5f)); ny = __fsub_rn(ny, __fmul_rn(ddy, 0.5f));
+                break;
+            }
+            pdx = ddx; pdy = ddy;
+        }
+        // 5. residual of the final position (level 0 only)
+        if (status && l == 0) {
+            const float ex = __fsub_rn(nx, half), ey = __fsub_rn(ny, half);
+            const int iex = cv_floor(ex), iey = cv_floor(ey);
+            if (iex < -KLT_WIN || iex >= w || iey < -KLT_WIN || iey >= h) {
+                status = 0;
+            } else {
+                q14_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
+                __syncwarp();
+                load_J(s, J, w, h, iex, iey, lane);
+                int e = 0;
+#pragma unroll
+                for (int j = 0; j < KLT_PER_LANE; ++j)
+                    if (lane + 32 * j < KLT_NPIX) e += abs(j_sample(s, wy[j], wx[j], w00, w01, w10, w11) - Iw[j]);
+                err = __fdiv_rn((float)warp_sum_exact(e), (float)(32 * KLT_NPIX));
+            }
+        }
+    }
+    if (lane == 0) {
+        a.next_xy[2 * o] = nx; a.next_xy[2 * o + 1] = ny;
+        // getTransformKLT.py:365  status &= (err < ERR_THRESHOLD)
+        if (a.gate && !(err < a.err_thr)) status = 0;
+        a.status[o] = (uint8_t)status;
+        a.err[o] = err;
+    }
+}
+
+int rf_launch_klt(rf_handle* h, const FrameSet& prev, const FrameSet& next, const int32_t* d_pair_idx, const float* d_pts,
+                  const int32_t* d_counts, int Kmax, int P, float* d_next, uint8_t* d_status, float* d_err, int gate) {
+    KltArgs a;
+    a.prev = prev; a.next = next; a.pair_idx = d_pair_idx; a.pts = d_pts; a.counts = d_counts;
+    a.Kmax = Kmax; a.P = P; a.next_xy = d_next; a.status = d_status; a.err = d_err;
+    int mc = h->cfg.klt_max_iters; mc = mc < 0 ? 0 : (mc > 100 ? 100 : mc);  // cv clamps the criteria
+    double eps = h->cfg.klt_eps; eps = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
+    a.max_iters = mc; a.eps2 = eps * eps;
+    a.min_eig = h->cfg.klt_min_eig; a.err_thr = h->cfg.klt_err_thr; a.gate = gate;
+    long long warps = (long long)P * Kmax;
+    if (warps == 0) return RF_OK;
+    unsigned blocks = (unsigned)((warps + KLT_WARPS - 1) / KLT_WARPS);
+    k_klt<<<blocks, KLT_WARPS * 32, 0, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+extern "C" int rf_klt(rf_handle* h, const rf_frame* prev, const rf_frame* next, const float* pts, int K,
+                      int apply_err_gate, float* next_xy, uint8_t* status, float* err) {
+    if (!h || !prev || !next || !pts || !next_xy || !status || !err || K < 0)
+        return rf_fail(h, RF_E_BADARG, "rf_klt: null argument");
+    if (K == 0) return RF_OK;
+    size_t bp = (size_t)K * 2 * sizeof(float), bs = (size_t)K, be = (size_t)K * sizeof(float);
+    size_t off_next = (bp + 255) & ~(size_t)255, off_err = off_next + ((bp + 255) & ~(size_t)255);
+    size_t off_st = off_err + ((be + 255) & ~(size_t)255), total = off_st + ((bs + 255) & ~(size_t)255);
+    int rc = rf_ensure_scratch(h, total);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    RF_CUDA(h, cudaMemcpyAsync(base, pts, bp, cudaMemcpyHostToDevice, h->stream));
+    rc = rf_launch_klt(h, prev->fs, next->fs, nullptr, (const float*)base, nullptr, K, 1, (float*)(base + off_next),
+                       (uint8_t*)(base + off_st), (float*)(base + off_err), apply_err_gate);
+    if (rc) return rc;
+    RF_CUDA(h, cudaMemcpyAsync(next_xy, base + off_next, bp, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(err, base + off_err, be, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(status, base + off_st, bs, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
