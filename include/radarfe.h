@@ -142,6 +142,13 @@ RF_API int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* n
 RF_API int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K,
                              uint8_t* adj);
 
+/* Test hook: the clique search alone on a caller-supplied adjacency matrix (K x K bytes,
+ * diagonal ignored).  prune == 0 enumerates EVERY maximal clique in networkx order and
+ * returns their count plus an order-sensitive FNV-1a hash over (size, members...) of each
+ * yield, so tests can pin the enumeration ORDER against the oracle.  mask_out: K int32. */
+RF_API int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, int32_t* mask_out, int* size,
+                     int64_t* n_yields, uint64_t* order_hash, int64_t* nodes);
+
 /* ---- a7  getTransformKLT.calculateTransformSVD           getTransformKLT.py:129-162 */
 /* src = R * tgt + h (pixel units; Tracker.getTransform scales h by cart_res_m). */
 RF_API int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, double R[4], double hvec[2]);

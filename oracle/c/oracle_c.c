@@ -441,9 +441,18 @@ typedef struct { pyset subg, cand, ext; } frame;
  *   yields_buf (optional): first `yields_cap` ints of the concatenated yields,
  *           each as [size, v0, v1, ...] — used to pin the ORDER against live networkx.
  * Returns clique size. */
+static unsigned long long g_order_hash;
+static unsigned long long fnv_mix(unsigned long long h, int v) {
+    for (int b = 0; b < 4; ++b) { h ^= (unsigned long long)((v >> (8 * b)) & 0xFF); h *= 1099511628211ULL; }
+    return h;
+}
+/* order-sensitive FNV-1a hash over (size, members...) of every yield of the last enumeration */
+ORC_API unsigned long long orc_last_order_hash(void) { return g_order_hash; }
+
 static int first_max_clique_impl(const uint8_t* adjm, int K, int* out_clique, long* n_yields,
                                  int* yields_buf, long yields_cap, long* yields_len, int prune, long* n_descents) {
     long nd = 0;
+    g_order_hash = 14695981039346656037ULL;
     if (n_yields) *n_yields = 0; if (yields_len) *yields_len = 0;
     if (K == 0) return 0;
     pyset* adj = (pyset*)malloc(sizeof(pyset) * K);
@@ -465,6 +474,7 @@ static int first_max_clique_impl(const uint8_t* adjm, int K, int* out_clique, lo
             pyset subg_q; ps_and(&subg_q, &subg, &adj[q]);
             if (!subg_q.used) {
                 ny++;
+                g_order_hash = fnv_mix(g_order_hash, qn); for (int i = 0; i < qn; ++i) g_order_hash = fnv_mix(g_order_hash, Q[i]);
                 if (yields_buf && yl + qn + 1 <= yields_cap) { yields_buf[yl++] = qn; for (int i = 0; i < qn; ++i) yields_buf[yl++] = Q[i]; }
                 if (qn > best) { best = qn; memcpy(out_clique, Q, sizeof(int) * qn); }
                 ps_free(&subg_q);

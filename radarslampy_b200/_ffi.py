@@ -46,7 +46,7 @@ SYMBOLS = [
     "rf_default_config", "rf_create", "rf_destroy", "rf_last_error", "rf_version", "rf_cart_size", "rf_stream",
     "rf_timer_start", "rf_timer_stop_ms", "rf_launch_count", "rf_extract_polar", "rf_frame_create",
     "rf_frame_destroy", "rf_polar_to_cart", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
-    "rf_reject_outliers", "rf_consistency_adjacency", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
+    "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
     "rf_detect", "rf_corner_response", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch",
 ]
@@ -247,6 +247,16 @@ class RadarFE:
         adj = np.zeros((K, K), np.uint8)
         self._check(self.lib.rf_consistency_adjacency(self.h, _ptr(a), _ptr(b), K, _ptr(adj)))
         return adj
+
+    def clique_search(self, adj, prune=True):
+        """Test hook: (mask, size, n_yields, order_hash, nodes) for a K x K adjacency matrix."""
+        adj = _c(adj, np.uint8)
+        K = adj.shape[0]
+        mask = np.zeros(max(K, 1), np.int32)
+        size, ny, hs, nodes = C.c_int(0), C.c_int64(0), C.c_uint64(0), C.c_int64(0)
+        self._check(self.lib.rf_clique_search(self.h, _ptr(adj), K, int(prune), _ptr(mask), C.byref(size), C.byref(ny),
+                                              C.byref(hs), C.byref(nodes)))
+        return mask[:K].astype(bool), size.value, ny.value, hs.value, nodes.value
 
     # -- a7 ---------------------------------------------------------------------
     def kabsch(self, src_xy, tgt_xy):

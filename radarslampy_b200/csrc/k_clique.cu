@@ -1,0 +1,709 @@
+// k_clique.cu — distance-consistency graph + the reference's "first largest maximal clique".
+//
+// Replaces outlierRejection.rejectOutliers (outlierRejection.py:16-95):
+//   cdist / |d_prev - d_new| <= thr adjacency (:49-58)          -> k_adjacency (fp64, no FMA)
+//   nx.find_cliques + "first strictly larger clique" (:63-78)   -> k_clique
+//
+// Parity contract.  Maximum cliques tie on real data and the reference keeps the first one
+// networkx yields, so the kernel reproduces networkx 3.6's pivoting Bron–Kerbosch *in the
+// iteration order of CPython 3.12 sets* (restated in oracle/c/oracle_c.c).
+// A set of small ints is a hash table whose slot of key k is k & mask (+ probing); when the
+// table is at least as large as the node count every key sits in its own slot, i.e. the set
+// iterates in ascending order and is fully described by a BITSET.  Only sets whose table is
+// smaller than K need their slot layout emulated (an explicit int16 table of <= Kpad/2 slots).
+// Each set is therefore { bitset | mask, fill, used, finger | small table }.
+//
+// Mapping: one warp per frame pair.  Bitset algebra, popcounts, ordered compaction and the
+// pivot arg-max run across the 32 lanes; the collision-order emulation of small tables is
+// inherently sequential and is done by lane 0.  The current search frame lives in shared
+// memory; parents are pushed to a per-pair stack in global memory.
+// Search-tree children that cannot beat the best clique so far are skipped (order-safe: the
+// parent's state does not depend on whether a child was descended).
+#include "common.cuh"
+
+#define EMPTY_SLOT (-1)
+#define DUMMY_SLOT (-2)
+
+struct CliqueGeom {
+    int Kpad;    // padded capacity (multiple of 32, power of two)
+    int NW;      // 32-bit words per bitset
+    int TABN;    // int16 slots in an explicit table (Kpad / 2)
+    int SW;      // 32-bit words per set = NW + 4 + TABN / 2
+    int SEQCAP;  // max degree of a node whose adjacency set has a table smaller than Kpad
+};
+
+__host__ __device__ inline int growth_size(int n) {
+    // table size of a set grown by n successive adds from empty (CPython set_add_entry:
+    // resize to used*4 when fill*5 >= mask*3)
+    return n <= 4 ? 8 : n <= 18 ? 32 : n <= 76 ? 128 : n <= 306 ? 512 : n <= 1228 ? 2048 : 8192;
+}
+
+struct SetRef {
+    uint32_t* w;  // base
+    int NW;
+    __device__ uint32_t* bits() const { return w; }
+    __device__ int& mask() const { return ((int*)(w + NW))[0]; }
+    __device__ int& fill() const { return ((int*)(w + NW))[1]; }
+    __device__ int& used() const { return ((int*)(w + NW))[2]; }
+    __device__ int& finger() const { return ((int*)(w + NW))[3]; }
+    __device__ int16_t* tab() const { return (int16_t*)(w + NW + 4); }
+};
+
+// ---- sequential emulation helpers (lane 0 only) -------------------------------------
+__device__ void tab_insert_clean(int16_t* t, int mask, int key) {
+    unsigned perturb = (unsigned)key;
+    unsigned i = (unsigned)key & mask;
+    for (;;) {
+        if (t[i] == EMPTY_SLOT) { t[i] = (int16_t)key; return; }
+        if (i + 9 <= (unsigned)mask) {
+            for (int j = 1; j <= 9; ++j)
+                if (t[i + j] == EMPTY_SLOT) { t[i + j] = (int16_t)key; return; }
+        }
+        perturb >>= 5;
+        i = (i * 5 + 1 + perturb) & mask;
+    }
+}
+
+// Build the explicit table of a FRESH set from an insertion sequence (no dummies, no
+// duplicates): successive adds with CPython's growth rule.  `tmp` is scratch of >= n keys.
+__device__ void tab_build_by_adds(int16_t* t, const int16_t* seq, int n, int16_t* tmp) {
+    int mask = 7, fill = 0;
+    for (int i = 0; i < 8; ++i) t[i] = EMPTY_SLOT;
+    for (int s = 0; s < n; ++s) {
+        tab_insert_clean(t, mask, seq[s]);
+        ++fill;
+        if (fill * 5 >= mask * 3) {
+            int newsize = 8;
+            while (newsize <= fill * 4) newsize <<= 1;
+            int m = 0;
+            for (int i = 0; i <= mask; ++i) if (t[i] >= 0) tmp[m++] = t[i];
+            for (int i = 0; i < newsize; ++i) t[i] = EMPTY_SLOT;
+            mask = newsize - 1;
+            for (int i = 0; i < m; ++i) tab_insert_clean(t, mask, tmp[i]);
+        }
+    }
+}
+
+// ---- warp-cooperative primitives ----------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// ascending keys of (a [& | &~] f) -> out ; returns count
+__device__ int bits_to_seq(const uint32_t* a, const uint32_t* f, bool want_in, int NW, int16_t* out, int lane) {
+    int total = 0;
+    for (int w0 = 0; w0 < NW; w0 += 32) {
+        const int w = w0 + lane;
+        uint32_t v = w < NW ? a[w] : 0u;
+        if (f && w < NW) v = want_in ? (v & f[w]) : (v & ~f[w]);
+        const int c = __popc(v);
+        const int incl = warp_incl_scan(c, lane);
+        int base = total + incl - c;
+        while (v) { const int b = __ffs(v) - 1; out[base++] = (int16_t)(w * 32 + b); v &= v - 1; }
+        total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return total;
+}
+
+// live keys of explicit table in slot order, filtered -> out ; returns count
+__device__ int tab_to_seq(const int16_t* t, int size, const uint32_t* f, bool want_in, int16_t* out, int lane) {
+    int total = 0;
+    for (int i0 = 0; i0 < size; i0 += 32) {
+        const int i = i0 + lane;
+        const int k = i < size ? t[i] : -1;
+        bool ok = k >= 0;
+        if (ok && f) ok = (((f[k >> 5] >> (k & 31)) & 1u) != 0) == want_in;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) out[total + __popc(m & ((1u << lane) - 1))] = (int16_t)k;
+        total += __popc(m);
+    }
+    return total;
+}
+
+// ordered live keys of a set (optionally filtered by bitset f)
+__device__ int set_to_seq(const SetRef& s, int K, const uint32_t* f, bool want_in, int16_t* out, int lane) {
+    const int size = s.mask() + 1;
+    if (size >= K) return bits_to_seq(s.bits(), f, want_in, s.NW, out, lane);
+    return tab_to_seq(s.tab(), size, f, want_in, out, lane);
+}
+
+__device__ int bits_count2(const uint32_t* a, const uint32_t* b, bool and_not, int NW, int lane) {
+    int c = 0;
+    for (int w = lane; w < NW; w += 32) c += __popc(and_not ? (a[w] & ~b[w]) : (a[w] & b[w]));
+    return __reduce_add_sync(0xffffffffu, c);
+}
+
+// dst = fresh set holding (a op b) where the insertion order is given by `seq` when the
+// table is small; bits are always a op b.
+__device__ void fresh_from(const SetRef& dst, const uint32_t* a, const uint32_t* b, bool and_not, int n, int K,
+                           const int16_t* seq, int16_t* tmp, int lane) {
+    for (int w = lane; w < dst.NW; w += 32) dst.bits()[w] = and_not ? (a[w] & ~b[w]) : (a[w] & b[w]);
+    const int size = growth_size(n);
+    if (lane == 0) {
+        dst.mask() = size - 1; dst.fill() = n; dst.used() = n; dst.finger() = 0;
+        if (size < K) tab_build_by_adds(dst.tab(), seq, n, tmp);
+    }
+    __syncwarp();
+}
+
+struct CliqueArgs {
+    CliqueGeom g;
+    int P;
+    const int32_t* counts;     // [P] node count of each problem
+    int Kmax;                  // row capacity of the per-problem arrays (== g.Kpad)
+    const uint32_t* adjbits;   // [P][Kpad][NW]
+    int16_t* adjseq;           // [P][Kpad][SEQCAP] slot-ordered neighbours of small-table nodes
+    int16_t* deg;              // [P][Kpad]
+    uint32_t* stack;           // [P][Kpad + 1][3 * SW]
+    int prune;
+    long long node_limit;
+    // outputs
+    uint8_t* mask;             // [P][Kpad]
+    int32_t* n_inliers;        // [P]
+    int32_t* nodes;            // [P] pops performed
+    int32_t* status;           // [P]
+    long long* n_yields;       // [P] (may be null)
+    unsigned long long* order_hash;  // [P] (may be null) FNV-1a over (size, members...) of every yield
+};
+
+__device__ __forceinline__ unsigned long long fnv_mix(unsigned long long hsh, int v) {
+    for (int b = 0; b < 4; ++b) { hsh ^= (unsigned long long)((v >> (8 * b)) & 0xFF); hsh *= 1099511628211ULL; }
+    return hsh;
+}
+
+// dst = a & adj[q]   (CPython set_intersection: iterate the smaller operand; on a tie iterate adj[q])
+__device__ int set_and_adj(const SetRef& dst, const SetRef& a, int q, int K, const uint32_t* adjq, int degq,
+                           const int16_t* adjseq_q, int16_t* seq, int16_t* tmp, int lane) {
+    const int n = bits_count2(a.bits(), adjq, false, a.NW, lane);
+    if (n == 0) { if (lane == 0) dst.used() = 0; __syncwarp(); return 0; }
+    if (growth_size(n) < K) {
+        int m;
+        if (degq <= a.used()) {
+            if (growth_size(degq) >= K) m = bits_to_seq(adjq, a.bits(), true, a.NW, seq, lane);
+            else {
+                // neighbours of q in adj[q]'s slot order, keep those in a
+                m = 0;
+                for (int i0 = 0; i0 < degq; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int k = i < degq ? adjseq_q[i] : -1;
+                    const bool ok = k >= 0 && ((a.bits()[k >> 5] >> (k & 31)) & 1u);
+                    const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                    if (ok) seq[m + __popc(bm & ((1u << lane) - 1))] = (int16_t)k;
+                    m += __popc(bm);
+                }
+            }
+        } else {
+            m = set_to_seq(a, K, adjq, true, seq, lane);
+        }
+        __syncwarp();
+    }
+    fresh_from(dst, a.bits(), adjq, false, n, K, seq, tmp, lane);
+    return n;
+}
+
+// dst = a - adj[u]   (CPython set_difference, both branches)
+__device__ void set_sub_adj(const SetRef& dst, const SetRef& a, int K, const uint32_t* adju, int degu, int16_t* seq,
+                            int16_t* tmp, int lane) {
+    const int NW = a.NW;
+    if ((a.used() >> 2) > degu) {
+        // set_copy_and_difference: copy a (one up-front resize to used*2), then discard
+        const int a_used = a.used(), a_fill = a.fill(), a_mask = a.mask();
+        int newmask = 7;
+        if (a_used * 5 >= 7 * 3) { int ns = 8; while (ns <= a_used * 2) ns <<= 1; newmask = ns - 1; }
+        const bool explicit_tab = (newmask + 1) < K;
+        int m = 0;
+        if (explicit_tab) {
+            if (newmask == a_mask && a_fill == a_used) {   // slot-for-slot copy
+                for (int i = lane; i <= newmask; i += 32) dst.tab()[i] = a.tab()[i];
+            } else {
+                m = set_to_seq(a, K, nullptr, true, seq, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    int16_t* t = dst.tab();
+                    for (int i = 0; i <= newmask; ++i) t[i] = EMPTY_SLOT;
+                    for (int i = 0; i < m; ++i) tab_insert_clean(t, newmask, seq[i]);
+                }
+            }
+            __syncwarp();
+        }
+        const int removed = bits_count2(a.bits(), adju, false, NW, lane);
+        if (explicit_tab) {
+            for (int i = lane; i <= newmask; i += 32) {
+                const int k = dst.tab()[i];
+                if (k >= 0 && ((adju[k >> 5] >> (k & 31)) & 1u)) dst.tab()[i] = DUMMY_SLOT;
+            }
+        }
+        for (int w = lane; w < NW; w += 32) dst.bits()[w] = a.bits()[w] & ~adju[w];
+        __syncwarp();
+        int fill = a_used, used = a_used - removed, mask = newmask;
+        if ((fill - used) > mask / 4) {   // "more than 1/4 dummies": rebuild at used*4
+            int ns = 8; while (ns <= used * 4) ns <<= 1;
+            if (explicit_tab) {
+                m = tab_to_seq(dst.tab(), mask + 1, nullptr, true, seq, lane);
+                __syncwarp();
+                if (ns < K) {
+                    if (lane == 0) {
+                        int16_t* t = dst.tab();
+                        for (int i = 0; i < ns; ++i) t[i] = EMPTY_SLOT;
+                        for (int i = 0; i < m; ++i) tab_insert_clean(t, ns - 1, seq[i]);
+                    }
+                }
+            } else if (ns < K) {
+                m = bits_to_seq(dst.bits(), nullptr, true, NW, seq, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    int16_t* t = dst.tab();
+                    for (int i = 0; i < ns; ++i) t[i] = EMPTY_SLOT;
+                    for (int i = 0; i < m; ++i) tab_insert_clean(t, ns - 1, seq[i]);
+                }
+            }
+            mask = ns - 1; fill = used;
+        }
+        if (lane == 0) { dst.mask() = mask; dst.fill() = fill; dst.used() = used; dst.finger() = 0; }
+        __syncwarp();
+        return;
+    }
+    const int n = bits_count2(a.bits(), adju, true, NW, lane);
+    if (n > 0 && growth_size(n) < K) { set_to_seq(a, K, adju, false, seq, lane); __syncwarp(); }
+    fresh_from(dst, a.bits(), adju, true, n, K, seq, tmp, lane);
+}
+
+// ext.pop(): first live slot at or after finger (wrapping)
+__device__ int set_pop(const SetRef& s, int K, int lane) {
+    const int mask = s.mask(), size = mask + 1;
+    const int start = s.finger() & mask;
+    int found = -1, slot = -1;
+    if (size >= K) {
+        // identity layout: slot == key.  next set bit >= start, else lowest set bit
+        const int NW = s.NW;
+        for (int pass = 0; pass < 2 && found < 0; ++pass) {
+            const int from = pass == 0 ? start : 0;
+            for (int w0 = (from >> 5); w0 < NW && found < 0; w0 += 32) {
+                const int w = w0 + lane;
+                uint32_t v = w < NW ? s.bits()[w] : 0u;
+                if (w == (from >> 5)) v &= ~0u << (from & 31);
+                const unsigned bm = __ballot_sync(0xffffffffu, v != 0u);
+                if (bm) {
+                    const int src = __ffs(bm) - 1;
+                    const uint32_t vv = __shfl_sync(0xffffffffu, v, src);
+                    found = (w0 + src) * 32 + (__ffs(vv) - 1);
+                }
+            }
+        }
+        slot = found;
+    } else {
+        const int16_t* t = s.tab();
+        for (int pass = 0; pass < 2 && found < 0; ++pass) {
+            const int from = pass == 0 ? start : 0;
+            for (int i0 = from & ~31; i0 < size && found < 0; i0 += 32) {
+                const int i = i0 + lane;
+                const int k = (i < size && i >= from) ? t[i] : -1;
+                const unsigned bm = __ballot_sync(0xffffffffu, k >= 0);
+                if (bm) {
+                    const int src = __ffs(bm) - 1;
+                    found = __shfl_sync(0xffffffffu, k, src);
+                    slot = i0 + src;
+                }
+            }
+        }
+        if (lane == 0) s.tab()[slot] = DUMMY_SLOT;
+    }
+    if (lane == 0) {
+        s.bits()[found >> 5] &= ~(1u << (found & 31));
+        s.used() -= 1;
+        s.finger() = slot + 1;
+    }
+    __syncwarp();
+    return found;
+}
+
+// cand.remove(q)
+__device__ void set_remove(const SetRef& s, int K, int q, int lane) {
+    const int size = s.mask() + 1;
+    if (size < K) {
+        int16_t* t = s.tab();
+        for (int i = lane; i < size; i += 32) if (t[i] == q) t[i] = DUMMY_SLOT;
+    }
+    if (lane == 0) { s.bits()[q >> 5] &= ~(1u << (q & 31)); s.used() -= 1; }
+    __syncwarp();
+}
+
+__device__ void set_copy_words(uint32_t* dst, const uint32_t* src, int words, int lane) {
+    for (int i = lane; i < words; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
+    extern __shared__ uint32_t sm[];
+    const int lane = threadIdx.x;
+    const int p = blockIdx.x;
+    if (p >= a.P) return;
+    const CliqueGeom g = a.g;
+    const int K = a.counts[p];
+    const int NW = g.NW, SW = g.SW;
+    // shared layout: subg | cand | ext | ch_subg | ch_cand | seq[Kpad] | tmp[Kpad] | Q[Kpad] | bestQ[Kpad]
+    SetRef subg{sm, NW}, cand{sm + SW, NW}, ext{sm + 2 * SW, NW}, chs{sm + 3 * SW, NW}, chc{sm + 4 * SW, NW};
+    int16_t* seq = (int16_t*)(sm + 5 * SW);
+    int16_t* tmp = seq + g.Kpad;
+    int16_t* Q = tmp + g.Kpad;
+    int16_t* bestQ = Q + g.Kpad;
+    const uint32_t* adjbits = a.adjbits + (size_t)p * g.Kpad * NW;
+    int16_t* adjseq = a.adjseq + (size_t)p * g.Kpad * g.SEQCAP;
+    int16_t* deg = a.deg + (size_t)p * g.Kpad;
+    uint32_t* stack = a.stack + (size_t)p * (g.Kpad + 1) * 3 * SW;
+    uint8_t* outmask = a.mask + (size_t)p * g.Kpad;
+
+    for (int i = lane; i < g.Kpad; i += 32) outmask[i] = 0;
+    if (K <= 0) {
+        if (lane == 0) { a.n_inliers[p] = 0; a.nodes[p] = 0; a.status[p] = RF_OK; if (a.n_yields) a.n_yields[p] = 0; if (a.order_hash) a.order_hash[p] = 14695981039346656037ULL; }
+        return;
+    }
+    // ---- degrees and slot orders of small-table adjacency sets ------------------------
+    for (int u = 0; u < K; ++u) {
+        const uint32_t* row = adjbits + (size_t)u * NW;
+        int c = 0;
+        for (int w = lane; w < NW; w += 32) c += __popc(row[w]);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) deg[u] = (int16_t)c;
+        if (c > 0 && growth_size(c) < K) {
+            // adj[u] = {v for v in G[u] if v != u}: ascending adds into a small table
+            const int m = bits_to_seq(row, nullptr, true, NW, seq, lane);
+            __syncwarp();
+            if (lane == 0) tab_build_by_adds(chs.tab(), seq, m, tmp);
+            __syncwarp();
+            tab_to_seq(chs.tab(), growth_size(c), nullptr, true, adjseq + (size_t)u * g.SEQCAP, lane);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    // ---- root: cand = set(G) ; subg = cand.copy() --------------------------------------
+    for (int w = lane; w < NW; w += 32) {
+        const int lo = w * 32;
+        uint32_t v = K >= lo + 32 ? ~0u : (K > lo ? ((1u << (K - lo)) - 1u) : 0u);
+        cand.bits()[w] = v; subg.bits()[w] = v;
+    }
+    if (lane == 0) {
+        const int size = growth_size(K);
+        cand.mask() = size - 1; cand.fill() = K; cand.used() = K; cand.finger() = 0;
+        subg.mask() = size - 1; subg.fill() = K; subg.used() = K; subg.finger() = 0;
+    }
+    __syncwarp();
+    int qn = 1, sp = 0, best = 0;
+    long long pops = 0, ny = 0;
+    unsigned long long hsh = 14695981039346656037ULL;
+    int status = RF_OK;
+
+    auto choose_pivot_and_ext = [&]() {
+        // u = max(subg, key=lambda u: len(cand & adj[u])) — first maximum in subg's iteration order
+        const int m = set_to_seq(subg, K, nullptr, true, seq, lane);
+        __syncwarp();
+        unsigned bestkey = 0;
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            unsigned key = 0;
+            if (i < m) {
+                const uint32_t* row = adjbits + (size_t)seq[i] * NW;
+                int c = 0;
+                for (int w = 0; w < NW; ++w) c += __popc(cand.bits()[w] & row[w]);
+                key = ((unsigned)c << 16) | (unsigned)(0xFFFF - i);
+            }
+            bestkey = max(bestkey, key);
+        }
+        bestkey = __reduce_max_sync(0xffffffffu, bestkey);
+        const int u = seq[0xFFFF - (bestkey & 0xFFFF)];
+        __syncwarp();
+        set_sub_adj(ext, cand, K, adjbits + (size_t)u * NW, deg[u], seq, tmp, lane);
+    };
+    choose_pivot_and_ext();
+
+    for (;;) {
+        if (ext.used() > 0) {
+            if (pops >= a.node_limit) { status = RF_E_WORKLIMIT; break; }
+            ++pops;
+            const int q = set_pop(ext, K, lane);
+            set_remove(cand, K, q, lane);
+            if (lane == 0) Q[qn - 1] = (int16_t)q;
+            const uint32_t* adjq = adjbits + (size_t)q * NW;
+            const int degq = deg[q];
+            const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
+            const int nsub = set_and_adj(chs, subg, q, K, adjq, degq, adjseq_q, seq, tmp, lane);
+            if (nsub == 0) {
+                ++ny;
+                __syncwarp();
+                if (a.order_hash) { hsh = fnv_mix(hsh, qn); for (int i = 0; i < qn; ++i) hsh = fnv_mix(hsh, Q[i]); }
+                if (qn > best) {   // outlierRejection.py:73 strict '>'
+                    best = qn;
+                    for (int i = lane; i < qn; i += 32) bestQ[i] = Q[i];
+                    __syncwarp();
+                }
+            } else {
+                const int ncand = bits_count2(cand.bits(), adjq, false, NW, lane);
+                if (ncand > 0 && !(a.prune && qn + ncand <= best)) {
+                    set_and_adj(chc, cand, q, K, adjq, degq, adjseq_q, seq, tmp, lane);
+                    // push parent frame
+                    uint32_t* fr = stack + (size_t)sp * 3 * SW;
+                    set_copy_words(fr, sm, 3 * SW, lane);
+                    ++sp;
+                    __syncwarp();
+                    if (lane == 0) Q[qn] = -1;
+                    ++qn;
+                    set_copy_words(subg.w, chs.w, SW, lane);
+                    set_copy_words(cand.w, chc.w, SW, lane);
+                    __syncwarp();
+                    choose_pivot_and_ext();
+                }
+            }
+        } else {
+            --qn;
+            if (sp == 0) break;
+            --sp;
+            const uint32_t* fr = stack + (size_t)sp * 3 * SW;
+            __syncwarp();
+            set_copy_words(sm, fr, 3 * SW, lane);
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < best; i += 32) outmask[bestQ[i]] = 1;
+    if (lane == 0) {
+        a.n_inliers[p] = best;
+        a.nodes[p] = (int32_t)(pops > 0x7fffffff ? 0x7fffffff : pops);
+        a.status[p] = status;
+        if (a.n_yields) a.n_yields[p] = ny;
+        if (a.order_hash) a.order_hash[p] = hsh;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// adjacency: scipy cdist 'euclidean' on f32 inputs upcast to f64, |d_prev - d_new| <= thr.
+// One block per problem; thread t owns (row i, word w) pairs.  Self-loops are dropped
+// (networkx: adj[u] = {v for v in G[u] if v != u}).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_adjacency(const float* __restrict__ prev, const float* __restrict__ nw, const int32_t* __restrict__ counts, int Kstride,
+            int Kpad, int NW, double thr, uint32_t* __restrict__ adjbits, uint8_t* __restrict__ adj_bytes) {
+    const int p = blockIdx.x;
+    const int K = counts[p];
+    const float* a = prev + (size_t)p * Kstride * 2;
+    const float* b = nw + (size_t)p * Kstride * 2;
+    uint32_t* out = adjbits + (size_t)p * Kpad * NW;
+    for (int t = threadIdx.x; t < Kpad * NW; t += blockDim.x) {
+        const int i = t / NW, w = t - i * NW;
+        uint32_t bitsv = 0;
+        if (i < K) {
+            const double ax = (double)a[2 * i], ay = (double)a[2 * i + 1];
+            const double bx = (double)b[2 * i], by = (double)b[2 * i + 1];
+            for (int bb = 0; bb < 32; ++bb) {
+                const int j = w * 32 + bb;
+                if (j >= K) break;
+                const double d1x = __dsub_rn(ax, (double)a[2 * j]), d1y = __dsub_rn(ay, (double)a[2 * j + 1]);
+                const double d2x = __dsub_rn(bx, (double)b[2 * j]), d2y = __dsub_rn(by, (double)b[2 * j + 1]);
+                const double s1 = __dadd_rn(__dmul_rn(d1x, d1x), __dmul_rn(d1y, d1y));
+                const double s2 = __dadd_rn(__dmul_rn(d2x, d2x), __dmul_rn(d2y, d2y));
+                const double dd = fabs(__dsub_rn(__dsqrt_rn(s1), __dsqrt_rn(s2)));
+                const bool e = dd <= thr;
+                if (adj_bytes) adj_bytes[((size_t)p * K + i) * K + j] = e;   // includes the diagonal, like the reference matrix
+                if (e && j != i) bitsv |= 1u << bb;
+            }
+        }
+        out[t] = bitsv;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bytes_to_bits(const uint8_t* __restrict__ adj, int K, int Kpad, int NW, uint32_t* __restrict__ out) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < Kpad * NW; t += gridDim.x * blockDim.x) {
+        const int i = t / NW, w = t - i * NW;
+        uint32_t v = 0;
+        if (i < K)
+            for (int bb = 0; bb < 32; ++bb) {
+                const int j = w * 32 + bb;
+                if (j < K && j != i && adj[(size_t)i * K + j]) v |= 1u << bb;
+            }
+        out[t] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+struct CliqueWorkspace {
+    CliqueGeom g;
+    int P;
+    uint32_t* adjbits; int16_t* adjseq; int16_t* deg; uint32_t* stack;
+    uint8_t* mask; int32_t *n_inliers, *nodes, *status; long long* n_yields; unsigned long long* hash;
+};
+
+static CliqueGeom make_geom(int Kmax) {
+    CliqueGeom g;
+    int kp = 64; while (kp < Kmax) kp <<= 1;
+    g.Kpad = kp; g.NW = kp / 32; g.TABN = kp / 2; g.SW = g.NW + 4 + g.TABN / 2;
+    g.SEQCAP = kp <= 512 ? 76 : (kp <= 2048 ? 306 : 1228);
+    if (g.SEQCAP > kp) g.SEQCAP = kp;
+    return g;
+}
+
+size_t rf_clique_workspace_bytes(int Kmax, int P) {
+    CliqueGeom g = make_geom(Kmax);
+    size_t per = (size_t)g.Kpad * g.NW * 4 + (size_t)g.Kpad * g.SEQCAP * 2 + (size_t)g.Kpad * 2 +
+                 (size_t)(g.Kpad + 1) * 3 * g.SW * 4 + (size_t)g.Kpad + 64;
+    return per * P + 4096;
+}
+
+// carve a workspace out of `base` (device memory of rf_clique_workspace_bytes)
+static CliqueWorkspace carve(void* base, int Kmax, int P) {
+    CliqueWorkspace ws; ws.g = make_geom(Kmax); ws.P = P;
+    const CliqueGeom& g = ws.g;
+    char* p = (char*)base;
+    auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
+    ws.stack = (uint32_t*)take((size_t)P * (g.Kpad + 1) * 3 * g.SW * 4);
+    ws.adjbits = (uint32_t*)take((size_t)P * g.Kpad * g.NW * 4);
+    ws.adjseq = (int16_t*)take((size_t)P * g.Kpad * g.SEQCAP * 2);
+    ws.deg = (int16_t*)take((size_t)P * g.Kpad * 2);
+    ws.mask = (uint8_t*)take((size_t)P * g.Kpad);
+    ws.n_inliers = (int32_t*)take((size_t)P * 4);
+    ws.nodes = (int32_t*)take((size_t)P * 4);
+    ws.status = (int32_t*)take((size_t)P * 4);
+    ws.n_yields = (long long*)take((size_t)P * 8);
+    ws.hash = (unsigned long long*)take((size_t)P * 8);
+    return ws;
+}
+
+size_t rf_clique_ws_total(int Kmax, int P) {
+    CliqueGeom g = make_geom(Kmax);
+    auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    return r((size_t)P * (g.Kpad + 1) * 3 * g.SW * 4) + r((size_t)P * g.Kpad * g.NW * 4) + r((size_t)P * g.Kpad * g.SEQCAP * 2) +
+           r((size_t)P * g.Kpad * 2) + r((size_t)P * g.Kpad) + 3 * r((size_t)P * 4) + 2 * r((size_t)P * 8);
+}
+
+static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t* d_counts, int prune, bool debug) {
+    CliqueArgs a;
+    a.g = ws.g; a.P = ws.P; a.counts = d_counts; a.Kmax = ws.g.Kpad; a.adjbits = ws.adjbits; a.adjseq = ws.adjseq;
+    a.deg = ws.deg; a.stack = ws.stack; a.prune = prune; a.node_limit = h->cfg.clique_node_limit;
+    a.mask = ws.mask; a.n_inliers = ws.n_inliers; a.nodes = ws.nodes; a.status = ws.status;
+    a.n_yields = debug ? ws.n_yields : nullptr; a.order_hash = debug ? ws.hash : nullptr;
+    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)4 * ws.g.Kpad * 2;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_clique, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rf_fail(h, RF_E_CUDA, "clique smem %zu: %s", smem, cudaGetErrorString(e));
+    }
+    k_clique<<<ws.P, 32, smem, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+// Batched device entry used by the fused pair/batch path.  d_prev/d_new: [P][Kstride][2]
+// compacted good correspondences, d_counts[P].  `ws_base` must hold rf_clique_ws_total().
+int rf_launch_reject(rf_handle* h, void* ws_base, const float* d_prev, const float* d_new, const int32_t* d_counts,
+                     int Kstride, int P, uint8_t** d_mask_out, int* mask_stride, int32_t** d_ninl, int32_t** d_nodes,
+                     int32_t** d_status) {
+    CliqueWorkspace ws = carve(ws_base, Kstride, P);
+    k_adjacency<<<P, 256, 0, h->stream>>>(d_prev, d_new, d_counts, Kstride, ws.g.Kpad, ws.g.NW, h->cfg.dist_thr_px,
+                                          ws.adjbits, nullptr);
+    RF_CHECK_LAUNCH(h);
+    int rc = launch_clique(h, ws, d_counts, 1, false);
+    if (rc) return rc;
+    *d_mask_out = ws.mask; *mask_stride = ws.g.Kpad; *d_ninl = ws.n_inliers; *d_nodes = ws.nodes; *d_status = ws.status;
+    return RF_OK;
+}
+
+extern "C" {
+
+int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* adj) {
+    if (!h || !prev_xy || !new_xy || !adj || K < 0) return rf_fail(h, RF_E_BADARG, "rf_consistency_adjacency: bad argument");
+    if (K == 0) return RF_OK;
+    CliqueGeom g = make_geom(K);
+    size_t bp = ((size_t)K * 8 + 255) & ~(size_t)255;
+    size_t total = 2 * bp + 256 + (size_t)g.Kpad * g.NW * 4 + (size_t)K * K;
+    int rc = rf_ensure_scratch(h, total);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    float* dp = (float*)base; float* dn = (float*)(base + bp);
+    int32_t* dc = (int32_t*)(base + 2 * bp);
+    uint32_t* bits = (uint32_t*)(base + 2 * bp + 256);
+    uint8_t* bytes = (uint8_t*)(bits + (size_t)g.Kpad * g.NW);
+    RF_CUDA(h, cudaMemcpyAsync(dp, prev_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dn, new_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dc, &K, 4, cudaMemcpyHostToDevice, h->stream));
+    k_adjacency<<<1, 256, 0, h->stream>>>(dp, dn, dc, K, g.Kpad, g.NW, h->cfg.dist_thr_px, bits, bytes);
+    RF_CHECK_LAUNCH(h);
+    RF_CUDA(h, cudaMemcpyAsync(adj, bytes, (size_t)K * K, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* mask, int* n_inliers,
+                       int* nodes) {
+    if (!h || !prev_xy || !new_xy || !mask || K < 0) return rf_fail(h, RF_E_BADARG, "rf_reject_outliers: bad argument");
+    if (n_inliers) *n_inliers = 0;
+    if (nodes) *nodes = 0;
+    if (K == 0) return RF_OK;
+    if (K > 8192) return rf_fail(h, RF_E_CAPACITY, "rf_reject_outliers: K=%d exceeds 8192", K);
+    size_t bp = ((size_t)K * 8 + 255) & ~(size_t)255;
+    size_t wsb = rf_clique_ws_total(K, 1);
+    int rc = rf_ensure_scratch(h, 2 * bp + 256 + wsb);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    float* dp = (float*)base; float* dn = (float*)(base + bp);
+    int32_t* dc = (int32_t*)(base + 2 * bp);
+    RF_CUDA(h, cudaMemcpyAsync(dp, prev_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dn, new_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dc, &K, 4, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* dmask; int stride; int32_t *dn_inl, *dnodes, *dstatus;
+    rc = rf_launch_reject(h, base + 2 * bp + 256, dp, dn, dc, K, 1, &dmask, &stride, &dn_inl, &dnodes, &dstatus);
+    if (rc) return rc;
+    int32_t out[3];
+    RF_CUDA(h, cudaMemcpyAsync(mask, dmask, (size_t)K, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&out[0], dn_inl, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&out[1], dnodes, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&out[2], dstatus, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n_inliers) *n_inliers = out[0];
+    if (nodes) *nodes = out[1];
+    if (out[2] != RF_OK) return rf_fail(h, out[2], "rf_reject_outliers: clique search exceeded %lld nodes (best-so-far mask returned)",
+                                        (long long)h->cfg.clique_node_limit);
+    return RF_OK;
+}
+
+// Test hook: clique search on a caller-supplied adjacency matrix (K x K bytes).
+int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, int32_t* clique_mask_out, int* size,
+                     int64_t* n_yields, uint64_t* order_hash, int64_t* nodes) {
+    if (!h || !adj || K < 0) return rf_fail(h, RF_E_BADARG, "rf_clique_search: bad argument");
+    if (K == 0) { if (size) *size = 0; return RF_OK; }
+    size_t ab = ((size_t)K * K + 255) & ~(size_t)255;
+    size_t wsb = rf_clique_ws_total(K, 1);
+    int rc = rf_ensure_scratch(h, ab + 256 + wsb);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    uint8_t* dadj = (uint8_t*)base;
+    int32_t* dc = (int32_t*)(base + ab);
+    CliqueWorkspace ws = carve(base + ab + 256, K, 1);
+    RF_CUDA(h, cudaMemcpyAsync(dadj, adj, (size_t)K * K, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dc, &K, 4, cudaMemcpyHostToDevice, h->stream));
+    k_bytes_to_bits<<<64, 256, 0, h->stream>>>(dadj, K, ws.g.Kpad, ws.g.NW, ws.adjbits);
+    RF_CHECK_LAUNCH(h);
+    rc = launch_clique(h, ws, dc, prune, true);
+    if (rc) return rc;
+    std::vector<uint8_t> m(K);
+    int32_t o[3]; long long ny; unsigned long long hs;
+    RF_CUDA(h, cudaMemcpyAsync(m.data(), ws.mask, (size_t)K, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&o[0], ws.n_inliers, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&o[1], ws.nodes, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&o[2], ws.status, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&ny, ws.n_yields, 8, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&hs, ws.hash, 8, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (clique_mask_out) for (int i = 0; i < K; ++i) clique_mask_out[i] = m[i];
+    if (size) *size = o[0];
+    if (nodes) *nodes = o[1];
+    if (n_yields) *n_yields = ny;
+    if (order_hash) *order_hash = hs;
+    if (o[2] != RF_OK) return rf_fail(h, o[2], "rf_clique_search: node limit exceeded");
+    return RF_OK;
+}
+
+}  // extern "C"

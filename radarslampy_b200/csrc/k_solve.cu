@@ -1,0 +1,433 @@
+// k_solve.cu — rigid-transform estimate and the motion-distortion nonlinear least squares.
+//
+// Replaces:
+//   getTransformKLT.calculateTransformSVD (getTransformKLT.py:129-162), Tracker.getTransform
+//     (Tracker.py:108-127)                                   -> k_kabsch
+//   MotionDistortionSolver.update_problem / error_vector / optimize_library
+//     (motionDistortion.py:80-205, 295-325; scipy least_squares 'lm')  -> k_mds
+//   MotionDistortionSolver.undistort (motionDistortion.py:127-153)     -> k_undistort
+//
+// One warp per frame pair.  Kabsch: the reference runs in float32 because its inputs are
+// float32 (sequential f32 column means, f32 centring); those two steps are reproduced
+// bit-for-bit, the 2x2 cross-covariance is then accumulated exactly in f64 and the SVD is
+// replaced by the closed-form 2-D optimum theta = atan2(C10 - C01, C00 + C11), which equals
+// U diag(1, det) V^T whenever that is unique.
+// MDS: Levenberg-Marquardt in f64 with an analytic Jacobian derived from the residual the
+// reference defines (its own jacobian() is inconsistent with error() and unused).  The
+// solve converges to the minimiser, which scipy's 'lm' reaches to ~1e-5 m.
+#include <math.h>
+
+#include "common.cuh"
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+struct KabschArgs {
+    const float* src;       // [P][Kstride][2]   x0 (old points)
+    const float* tgt;       // [P][Kstride][2]   x1 (new points)
+    const uint8_t* mask;    // [P][mask_stride] or nullptr (all rows up to counts[p])
+    int mask_stride;
+    const int32_t* counts;  // [P] rows to scan
+    int Kstride, P;
+    double* R;              // [P][4]
+    double* h;              // [P][2]  (pixel units)
+    int32_t* n_used;        // [P]
+};
+
+__global__ void __launch_bounds__(128) k_kabsch(const KabschArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= a.P) return;
+    const int K = a.counts[p];
+    const float* s = a.src + (size_t)p * a.Kstride * 2;
+    const float* t = a.tgt + (size_t)p * a.Kstride * 2;
+    const uint8_t* m = a.mask ? a.mask + (size_t)p * a.mask_stride : nullptr;
+    // np.mean(axis=0) of an (N,2) float32 array: rows are added sequentially in float32
+    float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
+    int n = 0;
+    for (int i = 0; i < K; ++i) {
+        if (m && !m[i]) continue;
+        s0x = __fadd_rn(s0x, s[2 * i]); s0y = __fadd_rn(s0y, s[2 * i + 1]);
+        s1x = __fadd_rn(s1x, t[2 * i]); s1y = __fadd_rn(s1y, t[2 * i + 1]);
+        ++n;
+    }
+    double R00 = 1, R01 = 0, R10 = 0, R11 = 1, hx = 0, hy = 0;
+    if (n > 0) {
+        const float m0x = __fdiv_rn(s0x, (float)n), m0y = __fdiv_rn(s0y, (float)n);
+        const float m1x = __fdiv_rn(s1x, (float)n), m1y = __fdiv_rn(s1y, (float)n);
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+        for (int i = lane; i < K; i += 32) {
+            if (m && !m[i]) continue;
+            const double ax = (double)__fsub_rn(s[2 * i], m0x), ay = (double)__fsub_rn(s[2 * i + 1], m0y);
+            const double bx = (double)__fsub_rn(t[2 * i], m1x), by = (double)__fsub_rn(t[2 * i + 1], m1y);
+            c00 += ax * bx; c01 += ax * by; c10 += ay * bx; c11 += ay * by;   // C = norm_x0^T norm_x1
+        }
+        c00 = warp_sum_d(c00); c01 = warp_sum_d(c01); c10 = warp_sum_d(c10); c11 = warp_sum_d(c11);
+        const double sn = c10 - c01, cs = c00 + c11;
+        const double nr = hypot(sn, cs);
+        double c = 1.0, sgn = 0.0;
+        if (nr > 0.0) { c = cs / nr; sgn = sn / nr; }
+        R00 = c; R01 = -sgn; R10 = sgn; R11 = c;
+        hx = (double)m0x - (R00 * (double)m1x + R01 * (double)m1y);   // h = x0_mean - R x1_mean
+        hy = (double)m0y - (R10 * (double)m1x + R11 * (double)m1y);
+    }
+    if (lane == 0) {
+        double* R = a.R + (size_t)p * 4; double* h = a.h + (size_t)p * 2;
+        R[0] = R00; R[1] = R01; R[2] = R10; R[3] = R11; h[0] = hx; h[1] = hy;
+        if (a.n_used) a.n_used[p] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// motion distortion
+// ------------------------------------------------------------------------------------
+struct MdsArgs {
+    int P;
+    // explicit-problem mode (rf_mds_solve): p_w / p_jt given in metres
+    const double* p_w;      // [P][Nstride][2] or nullptr
+    const double* p_jt;     // [P][Nstride][2] or nullptr
+    const int32_t* counts;  // [P]
+    int Nstride;
+    const double* T_wj0;    // [P][9]
+    const double* T_wj;     // [P][9]  (explicit mode) or nullptr
+    // fused mode: correspondences in pixels + inlier mask + Kabsch result + previous pose
+    const float* px_old; const float* px_new; const uint8_t* mask; int mask_stride; int Kstride;
+    const double* kab_R; const double* kab_h; const double* prev_pose;  // [P][3] or nullptr (identity)
+    double center, res;
+    double period, sig_p0, sig_p1, sig_v0, sig_v1, sig_v2;
+    int max_iters;
+    double* x_out;          // [P][6]
+    int32_t* iters;         // [P]
+    double* cost;           // [P]
+    double* scratch;        // [P][Nstride][5]: pwx, pwy, px, py, dT
+};
+
+__device__ __forceinline__ double wrap_pi(double th) {
+    // utils.normalize_angles: (th + pi) % (2 pi) - pi with Python's floored modulo
+    const double two_pi = 2.0 * M_PI;
+    double r = fmod(th + M_PI, two_pi);
+    if (r < 0) r += two_pi;
+    return r - M_PI;
+}
+
+struct MdsEval { double cost; double g[6]; double H[21]; };
+
+// residual, gradient J^T r and Gauss-Newton matrix J^T J at x (warp-reduced; all lanes get the result)
+__device__ void mds_eval(const double* __restrict__ pts, int N, const double x[6], const double T0inv[6], double th0,
+                         const MdsArgs& a, bool want_deriv, MdsEval& o, int lane) {
+    const double c = cos(x[5]), s = sin(x[5]);
+    const double wp0 = 1.0 / a.sig_p0, wp1 = 1.0 / a.sig_p1;
+    double cost = 0, g[6] = {0, 0, 0, 0, 0, 0}, H[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) H[i] = 0;
+    for (int i = lane; i < N; i += 32) {
+        const double pwx = pts[5 * i], pwy = pts[5 * i + 1], px = pts[5 * i + 2], py = pts[5 * i + 3], dT = pts[5 * i + 4];
+        const double th = x[2] * dT;
+        const double ct = cos(th), st = sin(th);
+        const double qx = ct * px - st * py + x[0] * dT, qy = st * px + ct * py + x[1] * dT;
+        const double dx = pwx - x[3], dy = pwy - x[4];
+        const double mx = c * dx + s * dy, my = -s * dx + c * dy;
+        const double ex = mx - qx, ey = my - qy;
+        const double ux = ex * ex * 0.5 + 1.0, uy = ey * ey * 0.5 + 1.0;
+        const double rx = wp0 * log(ux), ry = wp1 * log(uy);
+        cost += rx * rx + ry * ry;
+        if (want_deriv) {
+            const double kx = wp0 * ex / ux, ky = wp1 * ey / uy;   // d rho / d e
+            // d e / d x
+            const double dqx_dvt = dT * (-st * px - ct * py), dqy_dvt = dT * (ct * px - st * py);
+            double Jx[6] = {-dT, 0.0, -dqx_dvt, -c, -s, my};
+            double Jy[6] = {0.0, -dT, -dqy_dvt, s, -c, -mx};
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { Jx[k] *= kx; Jy[k] *= ky; }
+            int idx = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                g[r] += Jx[r] * rx + Jy[r] * ry;
+#pragma unroll
+                for (int cc = r; cc < 6; ++cc) H[idx++] += Jx[r] * Jx[cc] + Jy[r] * Jy[cc];
+            }
+        }
+    }
+    cost = warp_sum_d(cost);
+    if (want_deriv) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) g[k] = warp_sum_d(g[k]);
+#pragma unroll
+        for (int k = 0; k < 21; ++k) H[k] = warp_sum_d(H[k]);
+    }
+    // velocity-consistency residuals (3 rows), identical on every lane
+    const double tx = x[3] - T0inv[4], ty = x[4] - T0inv[5];                // t - t0
+    const double relx = T0inv[0] * tx + T0inv[1] * ty, rely = T0inv[2] * tx + T0inv[3] * ty;  // R0^T (t - t0)
+    const double relth = atan2(sin(x[5] - th0), cos(x[5] - th0));           // arctan2 of the relative rotation
+    const double wv0 = (double)N / a.sig_v0, wv1 = (double)N / a.sig_v1, wv2 = (double)N / a.sig_v2;
+    const double ip = 1.0 / a.period;
+    const double r0 = wv0 * (x[0] - relx * ip), r1 = wv1 * (x[1] - rely * ip), r2 = wv2 * wrap_pi(x[2] - relth * ip);
+    cost += r0 * r0 + r1 * r1 + r2 * r2;
+    if (want_deriv) {
+        double J0[6] = {wv0, 0, 0, -wv0 * T0inv[0] * ip, -wv0 * T0inv[1] * ip, 0};
+        double J1[6] = {0, wv1, 0, -wv1 * T0inv[2] * ip, -wv1 * T0inv[3] * ip, 0};
+        double J2[6] = {0, 0, wv2, 0, 0, -wv2 * ip};
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            g[r] += J0[r] * r0 + J1[r] * r1 + J2[r] * r2;
+#pragma unroll
+            for (int cc = r; cc < 6; ++cc) H[idx++] += J0[r] * J0[cc] + J1[r] * J1[cc] + J2[r] * J2[cc];
+        }
+    }
+    o.cost = cost;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.g[k] = g[k];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) o.H[k] = H[k];
+}
+
+// solve (H + lam * diag(D)) dx = -g by Cholesky; returns false if not positive definite
+__device__ bool solve6(const double Hu[21], const double D[6], double lam, const double g[6], double dx[6]) {
+    double A[6][6];
+    int idx = 0;
+    for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c) { A[r][c] = Hu[idx]; A[c][r] = Hu[idx]; ++idx; }
+    for (int r = 0; r < 6; ++r) A[r][r] += lam * D[r];
+    double L[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double sum = A[i][j];
+            for (int k = 0; k < j; ++k) sum -= L[i][k] * L[j][k];
+            if (i == j) { if (!(sum > 0.0)) return false; L[i][i] = sqrt(sum); }
+            else L[i][j] = sum / L[j][j];
+        }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double sum = -g[i]; for (int k = 0; k < i; ++k) sum -= L[i][k] * y[k]; y[i] = sum / L[i][i]; }
+    for (int i = 5; i >= 0; --i) { double sum = y[i]; for (int k = i + 1; k < 6; ++k) sum -= L[k][i] * dx[k]; dx[i] = sum / L[i][i]; }
+    return true;
+}
+
+__global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
+    const int lane = threadIdx.x;
+    const int p = blockIdx.x;
+    if (p >= a.P) return;
+    double* pts = a.scratch + (size_t)p * a.Nstride * 5;
+    double T0[9], Tw[9];
+    int N = 0;
+    if (a.p_w) {
+        // explicit problem: motionDistortion.py:80-99
+        N = a.counts[p];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { T0[k] = a.T_wj0[(size_t)p * 9 + k]; Tw[k] = a.T_wj[(size_t)p * 9 + k]; }
+        const double* pw = a.p_w + (size_t)p * a.Nstride * 2;
+        const double* pj = a.p_jt + (size_t)p * a.Nstride * 2;
+        for (int i = lane; i < N; i += 32) {
+            const double x = pj[2 * i], y = pj[2 * i + 1];
+            pts[5 * i] = pw[2 * i]; pts[5 * i + 1] = pw[2 * i + 1]; pts[5 * i + 2] = x; pts[5 * i + 3] = y;
+            pts[5 * i + 4] = a.period * atan2(-y, -x) / (2.0 * M_PI);   // compute_time_deltas :107-124
+        }
+    } else {
+        // fused pair: RawROAMSystem.py:190-209 for a pair whose previous frame is the keyframe
+        //   p_w = prev_pose o ((good_old - centre) * res),  p_jt = (good_new - centre) * res,
+        //   T_wj = prev_pose @ [[R, h * res], [0, 1]]
+        double x0 = 0, y0 = 0, t0 = 0;
+        if (a.prev_pose) { x0 = a.prev_pose[3 * p]; y0 = a.prev_pose[3 * p + 1]; t0 = a.prev_pose[3 * p + 2]; }
+        const double c0 = cos(t0), s0 = sin(t0);
+        T0[0] = c0; T0[1] = -s0; T0[2] = x0; T0[3] = s0; T0[4] = c0; T0[5] = y0; T0[6] = 0; T0[7] = 0; T0[8] = 1;
+        const double* R = a.kab_R + (size_t)p * 4; const double* h = a.kab_h + (size_t)p * 2;
+        const double hx = h[0] * a.res, hy = h[1] * a.res;
+        Tw[0] = c0 * R[0] - s0 * R[2]; Tw[1] = c0 * R[1] - s0 * R[3]; Tw[2] = c0 * hx - s0 * hy + x0;
+        Tw[3] = s0 * R[0] + c0 * R[2]; Tw[4] = s0 * R[1] + c0 * R[3]; Tw[5] = s0 * hx + c0 * hy + y0;
+        Tw[6] = 0; Tw[7] = 0; Tw[8] = 1;
+        const int K = a.counts[p];
+        const float* po = a.px_old + (size_t)p * a.Kstride * 2;
+        const float* pn = a.px_new + (size_t)p * a.Kstride * 2;
+        const uint8_t* m = a.mask + (size_t)p * a.mask_stride;
+        // order-preserving compaction of the inliers
+        for (int i0 = 0; i0 < K; i0 += 32) {
+            const int i = i0 + lane;
+            const bool ok = i < K && m[i];
+            const unsigned bm = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int j = N + __popc(bm & ((1u << lane) - 1));
+                const double ox = ((double)po[2 * i] - a.center) * a.res, oy = ((double)po[2 * i + 1] - a.center) * a.res;
+                const double x = ((double)pn[2 * i] - a.center) * a.res, y = ((double)pn[2 * i + 1] - a.center) * a.res;
+                pts[5 * j] = c0 * ox - s0 * oy + x0; pts[5 * j + 1] = s0 * ox + c0 * oy + y0;
+                pts[5 * j + 2] = x; pts[5 * j + 3] = y;
+                pts[5 * j + 4] = a.period * atan2(-y, -x) / (2.0 * M_PI);
+            }
+            N += __popc(bm);
+        }
+    }
+    __syncwarp();
+    // T_wj0^{-1} = [R0^T, -R0^T t0]; keep R0^T (4) and t0 (2); theta0
+    const double T0inv[6] = {T0[0], T0[3], T0[1], T0[4], T0[2], T0[5]};   // R0^T row-major, then t0
+    const double th0 = atan2(T0[3], T0[0]);
+    // initial guess: v0 = [dx, dy, dtheta](T_wj0^-1 T_wj) / period ; pose from T_wj  (:91, 300-302)
+    double x[6];
+    {
+        const double tx = Tw[2] - T0[2], ty = Tw[5] - T0[5];
+        const double relx = T0inv[0] * tx + T0inv[1] * ty, rely = T0inv[2] * tx + T0inv[3] * ty;
+        // relative rotation = R0^T Rw ; atan2(rel[1,0], rel[0,0])
+        const double r00 = T0[0] * Tw[0] + T0[3] * Tw[3], r10 = T0[1] * Tw[0] + T0[4] * Tw[3];
+        x[0] = relx / a.period; x[1] = rely / a.period; x[2] = atan2(r10, r00) / a.period;
+        x[3] = Tw[2]; x[4] = Tw[5]; x[5] = atan2(Tw[3], Tw[0]);
+    }
+    MdsEval ev;
+    mds_eval(pts, N, x, T0inv, th0, a, true, ev, lane);
+    double lam = 1e-3;
+    int it = 0;
+    for (; it < a.max_iters; ++it) {
+        double D[6];
+        for (int k = 0, idx = 0; k < 6; ++k) { D[k] = fmax(ev.H[idx], 1e-300); idx += 6 - k; }
+        double gmax = 0;
+        for (int k = 0; k < 6; ++k) gmax = fmax(gmax, fabs(ev.g[k]) / sqrt(D[k]));
+        if (gmax < 1e-14 * fmax(1.0, sqrt(ev.cost))) break;
+        bool accepted = false;
+        double stepmax = 0;
+        for (int tries = 0; tries < 40; ++tries) {
+            double dx[6];
+            if (!solve6(ev.H, D, lam, ev.g, dx)) { lam *= 10; continue; }
+            double xn[6];
+            stepmax = 0;
+            for (int k = 0; k < 6; ++k) { xn[k] = x[k] + dx[k]; stepmax = fmax(stepmax, fabs(dx[k]) / (fabs(x[k]) + 1e-6)); }
+            MdsEval en;
+            mds_eval(pts, N, xn, T0inv, th0, a, false, en, lane);
+            if (en.cost <= ev.cost) {
+                const double dec = ev.cost - en.cost;
+                for (int k = 0; k < 6; ++k) x[k] = xn[k];
+                mds_eval(pts, N, x, T0inv, th0, a, true, ev, lane);
+                lam = fmax(lam * 0.2, 1e-15);
+                accepted = true;
+                if (dec <= 1e-17 * fmax(ev.cost, 1e-300) && stepmax < 1e-10) stepmax = 0;  // converged
+                break;
+            }
+            lam *= 10;
+            if (stepmax < 1e-15) break;
+        }
+        if (!accepted || stepmax < 1e-13) { ++it; break; }
+    }
+    if (lane == 0) {
+        for (int k = 0; k < 6; ++k) a.x_out[(size_t)p * 6 + k] = x[k];
+        if (a.iters) a.iters[p] = it;
+        if (a.cost) a.cost[p] = 0.5 * ev.cost;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_undistort(const double* __restrict__ pts, int N, double vx, double vy, double vth, double period, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double x = pts[2 * i], y = pts[2 * i + 1];
+    const double t = period * atan2(-y, -x) / (2.0 * M_PI);
+    const double th = vth * t, c = cos(th), s = sin(th);
+    out[2 * i] = c * x - s * y + vx * t;
+    out[2 * i + 1] = s * x + c * y + vy * t;
+}
+
+// ---- launchers ------------------------------------------------------------------------
+int rf_launch_kabsch(rf_handle* h, const float* d_src, const float* d_tgt, const uint8_t* d_mask, int mask_stride,
+                     const int32_t* d_counts, int Kstride, int P, double* d_R, double* d_h, int32_t* d_nused) {
+    KabschArgs a{d_src, d_tgt, d_mask, mask_stride, d_counts, Kstride, P, d_R, d_h, d_nused};
+    k_kabsch<<<(P + 3) / 4, 128, 0, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+static void fill_mds_cfg(rf_handle* h, MdsArgs& a) {
+    a.period = h->cfg.mds_period;
+    a.sig_p0 = h->cfg.mds_sigma_p[0]; a.sig_p1 = h->cfg.mds_sigma_p[1];
+    a.sig_v0 = h->cfg.mds_sigma_v[0]; a.sig_v1 = h->cfg.mds_sigma_v[1]; a.sig_v2 = h->cfg.mds_sigma_v[2];
+    a.center = (double)h->R; a.res = h->cfg.cart_res_m;
+    a.max_iters = 200;
+}
+
+int rf_launch_mds_fused(rf_handle* h, const float* d_old, const float* d_new, const uint8_t* d_mask, int mask_stride,
+                        const int32_t* d_counts, int Kstride, int P, const double* d_R, const double* d_h,
+                        const double* d_prev_pose, double* d_scratch, double* d_x, int32_t* d_iters) {
+    MdsArgs a; memset(&a, 0, sizeof(a));
+    fill_mds_cfg(h, a);
+    a.P = P; a.counts = d_counts; a.Nstride = Kstride; a.px_old = d_old; a.px_new = d_new; a.mask = d_mask;
+    a.mask_stride = mask_stride; a.Kstride = Kstride; a.kab_R = d_R; a.kab_h = d_h; a.prev_pose = d_prev_pose;
+    a.x_out = d_x; a.iters = d_iters; a.cost = nullptr; a.scratch = d_scratch;
+    k_mds<<<P, 32, 0, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+extern "C" {
+
+int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, double R[4], double hvec[2]) {
+    if (!h || !src_xy || !tgt_xy || !R || !hvec || N < 0) return rf_fail(h, RF_E_BADARG, "rf_kabsch: bad argument");
+    size_t bp = ((size_t)N * 8 + 255) & ~(size_t)255;
+    int rc = rf_ensure_scratch(h, 2 * bp + 1024);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    float* ds = (float*)base; float* dt = (float*)(base + bp);
+    int32_t* dc = (int32_t*)(base + 2 * bp);
+    double* dR = (double*)(base + 2 * bp + 256); double* dh = dR + 4;
+    if (N) {
+        RF_CUDA(h, cudaMemcpyAsync(ds, src_xy, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(dt, tgt_xy, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    RF_CUDA(h, cudaMemcpyAsync(dc, &N, 4, cudaMemcpyHostToDevice, h->stream));
+    rc = rf_launch_kabsch(h, ds, dt, nullptr, 0, dc, N > 0 ? N : 1, 1, dR, dh, nullptr);
+    if (rc) return rc;
+    double out[6];
+    RF_CUDA(h, cudaMemcpyAsync(out, dR, 48, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(R, out, 32); memcpy(hvec, out + 4, 16);
+    return RF_OK;
+}
+
+int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const double* p_jt, int N, const double T_wj[9],
+                 double x_out[6], int* iters, double* cost) {
+    if (!h || !T_wj0 || !T_wj || !x_out || N < 0 || (N > 0 && (!p_w || !p_jt)))
+        return rf_fail(h, RF_E_BADARG, "rf_mds_solve: bad argument");
+    const int Ns = N > 0 ? N : 1;
+    size_t bp = ((size_t)Ns * 16 + 255) & ~(size_t)255, bs = ((size_t)Ns * 40 + 255) & ~(size_t)255;
+    int rc = rf_ensure_scratch(h, 2 * bp + bs + 1024);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    double* dpw = (double*)base; double* dpj = (double*)(base + bp); double* dsc = (double*)(base + 2 * bp);
+    char* tail = base + 2 * bp + bs;
+    double* dT0 = (double*)tail; double* dTw = dT0 + 9; double* dx = dTw + 9; double* dcost = dx + 6;
+    int32_t* dc = (int32_t*)(dcost + 1); int32_t* dit = dc + 1;
+    if (N) {
+        RF_CUDA(h, cudaMemcpyAsync(dpw, p_w, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(dpj, p_jt, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+    RF_CUDA(h, cudaMemcpyAsync(dT0, T_wj0, 72, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dTw, T_wj, 72, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dc, &N, 4, cudaMemcpyHostToDevice, h->stream));
+    MdsArgs a; memset(&a, 0, sizeof(a));
+    fill_mds_cfg(h, a);
+    a.P = 1; a.p_w = dpw; a.p_jt = dpj; a.counts = dc; a.Nstride = Ns; a.T_wj0 = dT0; a.T_wj = dTw;
+    a.x_out = dx; a.iters = dit; a.cost = dcost; a.scratch = dsc;
+    k_mds<<<1, 32, 0, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
+    double xo[7]; int32_t ito;
+    RF_CUDA(h, cudaMemcpyAsync(xo, dx, 56, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(&ito, dit, 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(x_out, xo, 48);
+    if (cost) *cost = xo[6];
+    if (iters) *iters = ito;
+    return RF_OK;
+}
+
+int rf_mds_undistort(rf_handle* h, const double v[3], const double* pts_xy, int N, double period, double* out_xy) {
+    if (!h || !v || N < 0 || (N > 0 && (!pts_xy || !out_xy))) return rf_fail(h, RF_E_BADARG, "rf_mds_undistort: bad argument");
+    if (N == 0) return RF_OK;
+    size_t bp = ((size_t)N * 16 + 255) & ~(size_t)255;
+    int rc = rf_ensure_scratch(h, 2 * bp);
+    if (rc) return rc;
+    double* din = (double*)h->d_scratch; double* dout = (double*)((char*)h->d_scratch + bp);
+    RF_CUDA(h, cudaMemcpyAsync(din, pts_xy, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
+    k_undistort<<<(N + 255) / 256, 256, 0, h->stream>>>(din, N, v[0], v[1], v[2], period, dout);
+    RF_CHECK_LAUNCH(h);
+    RF_CUDA(h, cudaMemcpyAsync(out_xy, dout, (size_t)N * 16, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+}  // extern "C"

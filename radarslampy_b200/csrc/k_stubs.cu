@@ -2,11 +2,6 @@
 #include "common.cuh"
 #define NI(h) rf_fail((h), RF_E_BADARG, "%s: not implemented yet", __func__)
 extern "C" {
-int rf_reject_outliers(rf_handle* h, const float*, const float*, int, uint8_t*, int*, int*) { return NI(h); }
-int rf_consistency_adjacency(rf_handle* h, const float*, const float*, int, uint8_t*) { return NI(h); }
-int rf_kabsch(rf_handle* h, const float*, const float*, int, double*, double*) { return NI(h); }
-int rf_mds_solve(rf_handle* h, const double*, const double*, const double*, int, const double*, double*, int*, double*) { return NI(h); }
-int rf_mds_undistort(rf_handle* h, const double*, const double*, int, double, double*) { return NI(h); }
 int rf_ssc(rf_handle* h, const double*, int, int, double, int, int, int32_t*, int*) { return NI(h); }
 int rf_detect(rf_handle* h, const rf_frame*, int, float, double*, int, int*) { return NI(h); }
 int rf_corner_response(rf_handle* h, const rf_frame*, int, float*) { return NI(h); }
