@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — radar frames/s polar->pose on B200 (BASELINE.json metric) for the fused front end.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]; configs[2] with --mds 1): a seeded synthetic Oxford-shaped
+sequence (400 azimuths x 3768 range bins uint8 + 11 metadata bytes, 0.0438 m/bin) of
+--frames scans per GPU.  One step = one pass of the hot path over that batch: scan decode +
+polar->Cartesian + u8 pyramid for every frame, then pyramidal LK, distance-consistency clique
+rejection, Kabsch (and the motion-distortion solve) for every consecutive pair -> one pose per
+pair.  `value` = poses/s with the scans resident in HBM; `e2e` = the same through the C ABI with
+host buffers (pinned H2D of every scan + D2H of the poses inside the timed region).
+Multi-GPU: every rank owns an independent sequence (weak scaling, no data-path collective);
+the poses are gathered to rank 0 over NCCL once per step.
+
+--impl reference times the reference's own CPU path (the third-party calls the reference
+makes: cv2.warpPolar, cv2.calcOpticalFlowPyrLK, scipy cdist, networkx find_cliques, numpy SVD,
+scipy least_squares — oracle/ref_pipeline.py) on the host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_BYTES = 126e6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="scans per GPU per step")
+    ap.add_argument("--features", type=int, default=200)
+    ap.add_argument("--res", type=float, default=0.0438, help="range resolution m/bin (BASELINE: 0.0438; reference: 0.0432)")
+    ap.add_argument("--mds", type=int, default=0, help="1 = motion-distortion solve enabled (configs[2])")
+    ap.add_argument("--write-f32", type=int, default=0, help="also materialise the f32 Cartesian image per frame")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args, rank):
+    """Seeded synthetic sequence for this rank: raw scans, pairs, features, ground-truth poses."""
+    from radarslampy_b200 import synthetic as S
+    rb = int(87.5 / args.res)
+    world = S.World(seed=1234 + rank)
+    raw, poses = S.make_sequence(args.frames, res_m=args.res, world=world, first=0)
+    kmax = max(64, (args.features + 63) // 64 * 64)
+    pair_idx, feats, counts = S.sequence_pairs(args.frames, world, poses, args.res, rb, k=args.features, max_features=kmax)
+    return rb, kmax, raw, poses, pair_idx, feats, counts
+
+
+def stage_bytes(cfgd, S_frames, P, K_total, write_f32, levels):
+    """ALGORITHMIC bytes per launch group: every input read once, every mandated output
+    written once."""
+    A, W, n = cfgd["azimuths"], cfgd["range_bins"], cfgd["n"]
+    lv = [(n, n)]
+    for _ in range(1, levels):
+        lv.append(((lv[-1][0] + 1) // 2, (lv[-1][1] + 1) // 2))
+    px = [a * b for a, b in lv]
+    b = {}
+    b["polar2cart"] = S_frames * (A * W + px[0] + (4 * px[0] if write_f32 else 0))
+    b["pyramid"] = S_frames * sum(px[l - 1] + px[l] for l in range(1, levels))
+    # one track: per level an 18x18 previous-image patch + at least one 16x16 next-image window, + the err pass
+    b["klt"] = K_total * (levels * (324 + 256) + 256) + K_total * (8 + 8 + 1 + 4)
+    b["compact"] = K_total * (8 + 8 + 1) + K_total * (8 + 8 + 4)
+    b["reject"] = K_total * 16 + K_total
+    b["kabsch"] = K_total * 17 + P * 48
+    b["mds"] = K_total * 17 + P * (48 + 24 + 48)
+    b["finish"] = K_total * 6 + P * 120
+    return b
+
+
+# ---------------------------------------------------------------------------------------
+def cpu_pairs_worker(job):
+    """One contiguous chunk of pairs through the reference's library calls (frames converted once)."""
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import ref_pipeline as P
+    raw, feats, counts, poses, res_m, with_mds = job
+    carts = [P.polar_to_cart(P.extract_polar(r, res_m)) for r in raw]
+    out = []
+    for p in range(len(raw) - 1):
+        o = P.track_pair(None, None, feats[p, :counts[p]], prev_pose=poses[p], with_mds=with_mds, range_res_m=res_m,
+                         carts=(carts[p], carts[p + 1]))
+        out.append((o["h"], o["R"], o["n_inliers"]))
+    return out
+
+
+def cpu_reference_rate(args, raw, feats, counts, poses, n_pairs, repeats=1):
+    """poses/s of the CPU path over `n_pairs` consecutive pairs, all host cores (one process per core,
+    OpenCV single-threaded inside each)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_pairs = max(1, min(n_pairs, len(raw) - 1))
+    workers = min(cores, n_pairs)
+    per = -(-n_pairs // workers)
+    jobs = []
+    for w in range(workers):
+        a, bnd = w * per, min(n_pairs, (w + 1) * per)
+        if a >= bnd:
+            break
+        jobs.append((raw[a:bnd + 1], feats[a:bnd], counts[a:bnd], poses[a:bnd], args.res, bool(args.mds)))
+    best = None
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(jobs)) as pool:
+        pool.map(cpu_pairs_worker, [(j[0][:2], j[1][:1], j[2][:1], j[3][:1], j[4], j[5]) for j in jobs])   # warm imports
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(cpu_pairs_worker, jobs)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_pairs / best, len(jobs), n_pairs, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    rb, kmax, raw, poses, pair_idx, feats, counts = workload(args, 0)
+    cores = os.cpu_count() or 1
+    n_pairs = args.cpu_pairs or min(args.frames - 1, 2 * cores)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, workers, n_used, dt = cpu_reference_rate(args, raw, feats, counts, poses, n_pairs)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    value = n_used / t
+    sample = (f"{n_used} consecutive pairs of the {args.frames}-frame synthetic sequence per step, split over {workers} worker "
+              f"processes (cv2 single-threaded in each), frames converted once per worker")
+    line = {
+        "impl": "reference", "metric": "radar frames/sec polar->pose", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+        "config": workload_config(args, rb, kmax),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, rb, kmax):
+    return {"workload": f"synthetic Oxford-shaped sequence, {args.frames} scans/GPU/step (400x3768 u8 + 11 metadata bytes, "
+                        f"{args.res} m/bin -> {rb} used bins, {2 * (rb // 2)}^2 Cartesian), {args.features} features/pair given, "
+                        f"KLT 15x15 x 4 levels, clique rejection, Kabsch" + (", motion-distortion LM" if args.mds else ""),
+            "frames_per_step_per_gpu": args.frames, "pairs_per_step_per_gpu": args.frames - 1, "features_per_pair": args.features,
+            "range_res_m": args.res, "mds": bool(args.mds), "write_cart_f32": bool(args.write_f32),
+            "l2": "inputs larger than L2: each step streams >= 1.3 GB of scans + pyramids per GPU (L2 = 126 MB)"}
+
+
+# ---------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    rb, kmax, raw_np, poses, pair_idx, feats, counts = workload(args, rank)
+    cpu_line = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        # timed BEFORE the CUDA context exists (fork-safe), on a bounded sample of the same workload
+        cores = os.cpu_count() or 1
+        n_pairs = args.cpu_pairs or min(args.frames - 1, 2 * cores)
+        rate, workers, n_used, dt = cpu_reference_rate(args, raw_np, feats, counts, poses, n_pairs, repeats=2)
+        cpu_line = {"value": rate, "unit": "frames/s", "cores": workers, "kind": "port",
+                    "sample": f"first {n_used} pairs of the same sequence through oracle/ref_pipeline.py (the reference's own "
+                              f"cv2/scipy/networkx/numpy calls), {workers} processes, best of 2 ({dt:.2f} s)"}
+
+    import torch
+    import torch.distributed as dist
+    from radarslampy_b200 import _ffi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    S, P = args.frames, args.frames - 1
+    cfg = _ffi.default_config()
+    cfg.range_bins = rb
+    cfg.cart_res_m = 2 * args.res
+    cfg.dist_thr_px = 0.5 / (2 * args.res)
+    cfg.max_frames, cfg.max_pairs, cfg.max_features = S, max(P, 1), kmax
+    cfg.write_cart_f32 = args.write_f32
+    stream = torch.cuda.Stream()
+    fe = _ffi.RadarFE(cfg, device=local_rank, stream=stream.cuda_stream)
+    batch = fe.new_batch()
+    # pinned host staging (what a caller streaming scans from disk would fill)
+    raw = _ffi.pinned_empty(raw_np.shape, np.uint8); raw[...] = raw_np
+    feats_p = _ffi.pinned_empty(feats.shape, np.float32); feats_p[...] = feats
+    outs = batch.alloc_outputs(pinned=True)
+    prev_pose = poses[:-1].copy()
+    gather_buf = None
+    res_dev = torch.zeros((P, 15), dtype=torch.float64, device="cuda") if world > 1 else None
+    if world > 1:
+        gather_buf = [torch.zeros_like(res_dev) for _ in range(world)] if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_poses(res_host):
+        """trajectory concatenation: poses of every rank to rank 0 over NCCL"""
+        if world == 1:
+            return
+        flat = np.concatenate([res_host["R"], res_host["h"], res_host["mds_x"], res_host["n_good"][:, None],
+                               res_host["n_inliers"][:, None], res_host["status"][:, None]], axis=1)
+        res_dev.copy_(torch.from_numpy(flat), non_blocking=True)
+        dist.gather(res_dev, gather_buf, dst=0)
+
+    # ---- device-resident arm: scans already in HBM ------------------------------------------
+    batch.upload(raw, pair_idx, feats_p, counts, prev_pose=prev_pose)
+    batch.set_profiling(True)
+    for _ in range(args.warmup):
+        batch.run_async(with_mds=bool(args.mds))
+    fe.sync()
+    batch.stage_times()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    n0 = fe.launch_count()
+    fe.timer_start()
+    for _ in range(args.steps):
+        batch.run_async(with_mds=bool(args.mds))
+    ms = fe.timer_stop_ms()
+    launches = fe.launch_count() - n0
+    barrier()
+    stage_ms, runs = batch.stage_times()
+    res, nxt, corr = batch.download(outs)
+    fe.sync()
+    gather_poses(res)
+    barrier()
+
+    # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ------
+    batch.set_profiling(False)
+    for _ in range(args.warmup):
+        batch.upload(raw, pair_idx, feats_p, counts, prev_pose=prev_pose, sync=False)
+        batch.run_async(with_mds=bool(args.mds))
+        r2 = batch.download(outs, sync=False, want_tracks=False)
+        fe.sync()
+    barrier()
+    t0 = time.perf_counter()
+    fe.timer_start()
+    for _ in range(args.steps):
+        batch.upload(raw, pair_idx, feats_p, counts, prev_pose=prev_pose, sync=False)
+        batch.run_async(with_mds=bool(args.mds))
+        r2 = batch.download(outs, sync=False, want_tracks=False)
+        fe.sync()                                   # the caller reads the poses of this step
+        gather_poses(r2[0])
+    ms_e2e = fe.timer_stop_ms()                   # CUDA events on the handle's stream (every step ends in a sync)
+    barrier()
+    if world > 1:                                 # the NCCL gather runs on torch's stream: bound it by the host clock
+        ms_e2e = max(ms_e2e, (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop()
+
+    # ---- reduce over ranks (max time) ---------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K_total = int(counts.sum())
+    cfgd = {"azimuths": cfg.azimuths, "range_bins": rb, "n": fe.n}
+    sb = stage_bytes(cfgd, S, P, K_total, bool(args.write_f32), 4)
+    peak, peak_src = peaks()
+    stages = {}
+    for name, tot in stage_ms.items():
+        per = tot / max(runs, 1)
+        stages[name] = {"ms": per, "alg_bytes": sb[name], "gbs": (sb[name] / (per * 1e-3) / 1e9) if per > 0 else None}
+    dom = max(stages, key=lambda k: stages[k]["ms"])
+    achieved = stages[dom]["gbs"] or 0.0
+    value = world * P * args.steps / (ms * 1e-3)
+    e2e = world * P * args.steps / (ms_e2e * 1e-3)
+    h2d = S * cfg.azimuths * (cfg.meta_bytes + rb) + P * (8 + kmax * 8 + 4 + 24)
+    d2h = P * 120
+    line = {
+        "metric": "radar frames/sec polar->pose", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/f32/f64", "data": "synthetic", "config": workload_config(args, rb, kmax),
+        "klt_tracks_per_s": world * K_total * args.steps / (ms * 1e-3),
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": sb[dom], "ms_per_launch": stages[dom]["ms"]},
+        "stages": stages,
+        "clocks": clocks,
+        "pose_check": {"median_dtheta_rad": float(np.median(np.arctan2(res["R"][:, 2], res["R"][:, 0]))),
+                       "expected_dtheta_rad": 0.025, "median_inliers": float(np.median(res["n_inliers"])),
+                       "worklimit_pairs": int((res["status"] != 0).sum())},
+    }
+    if cpu_line is not None:
+        line["cpu_baseline"] = cpu_line
+    print(json.dumps(line), flush=True)
+    batch.close()
+    fe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

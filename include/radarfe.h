@@ -185,12 +185,33 @@ RF_API void rf_batch_destroy(rf_handle* h, rf_batch* b);
  * feat_counts[n_pairs]; prev_pose: [n_pairs,3] (x,y,theta) or NULL for identity. */
 RF_API int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
                     int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose);
+/* Same without the trailing synchronisation: the host buffers must stay valid (and should
+ * be pinned, see rf_host_alloc) until rf_sync returns. */
+RF_API int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
+                          int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose);
 /* Device-only: every stage for every pair, no host synchronisation before return. */
 RF_API int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds);
 RF_API int rf_sync(rf_handle* h);
 /* Device -> host: results [n_pairs]; next_xy [n_pairs,max_features,2] and status
  * [n_pairs,max_features] may be NULL. */
 RF_API int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status);
+RF_API int rf_batch_download_async(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status);
+/* KLT-stage outputs of the last run: status [n_pairs,max_features] = cv2 status & (err < thr)
+ * (getTransformKLT.py:365) before the clique fix-up, and err. Either may be NULL. */
+RF_API int rf_batch_klt_status(rf_handle* h, rf_batch* b, uint8_t* klt_status, float* err);
+/* One frame of the batch back to the host (what: 0 = f32 cart, needs write_cart_f32;
+ * 1+l = u8 pyramid level l). */
+RF_API int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, int what, void* out, int* rows, int* cols);
+/* Per-stage CUDA-event timing on the handle's stream.  While enabled, every
+ * rf_batch_run_async records events at its stage boundaries (ring of 64 runs);
+ * rf_batch_stage_times synchronises, sums the elapsed ms of the runs recorded since the last
+ * call into ms_sum[8] = {polar->cart, pyramid, klt, compact, reject, kabsch, mds, finish}
+ * and resets the ring. */
+RF_API int rf_batch_set_profiling(rf_handle* h, rf_batch* b, int on);
+RF_API int rf_batch_stage_times(rf_handle* h, rf_batch* b, float* ms_sum, int cap, int* n_runs);
+/* Pinned (page-locked) host memory for the *_async entry points. */
+RF_API int rf_host_alloc(size_t bytes, void** out);
+RF_API void rf_host_free(void* p);
 /* upload + run + download in one call (what Tracker.track/getTransform amount to). */
 RF_API int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
                    int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose,

@@ -48,8 +48,11 @@ SYMBOLS = [
     "rf_frame_destroy", "rf_polar_to_cart", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
     "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
     "rf_detect", "rf_corner_response", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
-    "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch",
+    "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
+    "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
+    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free",
 ]
+STAGES = ("polar2cart", "pyramid", "klt", "compact", "reject", "kabsch", "mds", "finish")
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -78,6 +81,9 @@ def load_library():
             L.rf_batch_destroy.restype = None
             L.rf_batch_destroy.argtypes = [C.c_void_p, C.c_void_p]
             L.rf_default_config.restype = None
+            L.rf_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+            L.rf_host_free.restype = None
+            L.rf_host_free.argtypes = [C.c_void_p]
             _lib = L
     return _lib
 
@@ -94,6 +100,140 @@ def _ptr(a):
 
 def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+class _PinnedOwner:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.rf_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """NumPy array in page-locked host memory (for the *_async batch calls)."""
+    import weakref
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    rc = lib.rf_host_alloc(C.c_size_t(max(nbytes, 1)), C.byref(p))
+    if rc != RF_OK:
+        msg = lib.rf_last_error(None)
+        raise MemoryError(f"rf_host_alloc failed ({rc}): {msg.decode() if msg else ''}")
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    owner = _PinnedOwner(lib, p)
+    weakref.finalize(buf, lambda o=owner: o.__del__())
+    return arr
+
+
+class Batch:
+    """Device-resident batch of independent frame pairs (rf_batch)."""
+
+    def __init__(self, fe):
+        self.fe = fe
+        p = C.c_void_p()
+        fe._check(fe.lib.rf_batch_create(fe.h, C.byref(p)))
+        self.p = p
+        self.n_pairs = 0
+        self._keep = None
+
+    def close(self):
+        if self.p and self.fe.h:
+            self.fe.lib.rf_batch_destroy(self.fe.h, self.p)
+        self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _marshal(self, raw, pair_idx, feats, counts, prev_pose):
+        fe = self.fe
+        cfg = fe.cfg
+        raw = np.ascontiguousarray(raw, np.uint8)
+        if raw.ndim != 3 or raw.shape[1:] != (cfg.azimuths, cfg.raw_width):
+            raise ValueError(f"raw scans must be [n_frames, {cfg.azimuths}, {cfg.raw_width}] uint8, got {raw.shape}")
+        pair_idx = np.ascontiguousarray(pair_idx, np.int32).reshape(-1, 2)
+        P = pair_idx.shape[0]
+        feats = np.ascontiguousarray(feats, np.float32)
+        if feats.shape != (P, cfg.max_features, 2):
+            raise ValueError(f"feats must be [n_pairs, max_features={cfg.max_features}, 2] float32, got {feats.shape}")
+        counts = np.ascontiguousarray(counts, np.int32).reshape(-1)
+        if counts.shape[0] != P:
+            raise ValueError("feat_counts must have one entry per pair")
+        if prev_pose is not None:
+            prev_pose = np.ascontiguousarray(prev_pose, np.float64).reshape(P, 3)
+        return raw, pair_idx, feats, counts, prev_pose
+
+    def upload(self, raw, pair_idx, feats, counts, prev_pose=None, sync=True):
+        fe = self.fe
+        raw, pair_idx, feats, counts, prev_pose = self._marshal(raw, pair_idx, feats, counts, prev_pose)
+        fn = fe.lib.rf_batch_upload if sync else fe.lib.rf_batch_upload_async
+        fe._check(fn(fe.h, self.p, _ptr(raw), raw.shape[0], _ptr(pair_idx), pair_idx.shape[0], _ptr(feats), _ptr(counts),
+                     _ptr(prev_pose)))
+        self.n_pairs = pair_idx.shape[0]
+        self._keep = (raw, pair_idx, feats, counts, prev_pose)   # async: keep host buffers alive
+
+    def run_async(self, with_mds=False):
+        self.fe._check(self.fe.lib.rf_batch_run_async(self.fe.h, self.p, int(with_mds)))
+
+    def alloc_outputs(self, pinned=False):
+        P, K = self.fe.cfg.max_pairs, self.fe.cfg.max_features
+        mk = pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dt))
+        return mk((P,), PAIR_RESULT_DTYPE), mk((P, K, 2), np.float32), mk((P, K), np.uint8)
+
+    def download(self, out=None, sync=True, want_tracks=True):
+        fe = self.fe
+        P = self.n_pairs
+        res, nxt, st = out if out is not None else self.alloc_outputs()
+        fn = fe.lib.rf_batch_download if sync else fe.lib.rf_batch_download_async
+        fe._check(fn(fe.h, self.p, _ptr(res), _ptr(nxt) if want_tracks else None, _ptr(st) if want_tracks else None))
+        return res[:P], nxt[:P], st[:P]
+
+    def klt_status(self):
+        fe = self.fe
+        P, K = self.n_pairs, fe.cfg.max_features
+        st = np.zeros((max(P, 1), K), np.uint8)
+        err = np.zeros((max(P, 1), K), np.float32)
+        fe._check(fe.lib.rf_batch_klt_status(fe.h, self.p, _ptr(st), _ptr(err)))
+        return st[:P], err[:P]
+
+    def frame(self, idx, what=1):
+        fe = self.fe
+        r, c = C.c_int(0), C.c_int(0)
+        fe._check(fe.lib.rf_batch_frame_download(fe.h, self.p, idx, what, None, C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.float32 if what == 0 else np.uint8)
+        fe._check(fe.lib.rf_batch_frame_download(fe.h, self.p, idx, what, _ptr(out), C.byref(r), C.byref(c)))
+        return out
+
+    def set_profiling(self, on=True):
+        self.fe._check(self.fe.lib.rf_batch_set_profiling(self.fe.h, self.p, int(on)))
+
+    def stage_times(self):
+        """({stage: total ms}, n_runs) over the runs recorded since the last call."""
+        ms = (C.c_float * 8)()
+        n = C.c_int(0)
+        self.fe._check(self.fe.lib.rf_batch_stage_times(self.fe.h, self.p, ms, 8, C.byref(n)))
+        return dict(zip(STAGES, [float(v) for v in ms])), n.value
+
+    def track(self, raw, pair_idx, feats, counts, prev_pose=None, with_mds=False):
+        """upload + run + download (rf_track_batch)."""
+        fe = self.fe
+        raw, pair_idx, feats, counts, prev_pose = self._marshal(raw, pair_idx, feats, counts, prev_pose)
+        P = pair_idx.shape[0]
+        res, nxt, st = self.alloc_outputs()
+        fe._check(fe.lib.rf_track_batch(fe.h, self.p, _ptr(raw), raw.shape[0], _ptr(pair_idx), P, _ptr(feats), _ptr(counts),
+                                        _ptr(prev_pose), int(with_mds), _ptr(res), _ptr(nxt), _ptr(st)))
+        self.n_pairs = P
+        return res[:P], nxt[:P], st[:P]
 
 
 class Frame:
@@ -177,6 +317,9 @@ class RadarFE:
 
     def new_frame(self) -> Frame:
         return Frame(self)
+
+    def new_batch(self) -> Batch:
+        return Batch(self)
 
     # -- a1 ---------------------------------------------------------------------
     def extract_polar(self, raw):

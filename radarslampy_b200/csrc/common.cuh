@@ -92,3 +92,18 @@ int rf_launch_polar2cart_f32(rf_handle* h, const float* d_src, int row_pitch, co
 int rf_launch_cart_to_u8(rf_handle* h, const FrameSet& fs);
 int rf_launch_pyramid(rf_handle* h, const FrameSet& fs, int first, int n_frames);
 int rf_launch_extract(rf_handle* h, const uint8_t* d_raw, float* d_polar);
+
+// k_klt.cu
+int rf_launch_klt(rf_handle* h, const FrameSet& prev, const FrameSet& next, const int32_t* d_pair_idx, const float* d_pts,
+                  const int32_t* d_counts, int Kmax, int P, float* d_next, uint8_t* d_status, float* d_err, int gate);
+// k_clique.cu
+size_t rf_clique_ws_total(int Kmax, int P);
+int rf_launch_reject(rf_handle* h, void* ws_base, const float* d_prev, const float* d_new, const int32_t* d_counts,
+                     int Kstride, int P, uint8_t** d_mask_out, int* mask_stride, int32_t** d_ninl, int32_t** d_nodes,
+                     int32_t** d_status);
+// k_solve.cu
+int rf_launch_kabsch(rf_handle* h, const float* d_src, const float* d_tgt, const uint8_t* d_mask, int mask_stride,
+                     const int32_t* d_counts, int Kstride, int P, double* d_R, double* d_h, int32_t* d_nused);
+int rf_launch_mds_fused(rf_handle* h, const float* d_old, const float* d_new, const uint8_t* d_mask, int mask_stride,
+                        const int32_t* d_counts, int Kstride, int P, const double* d_R, const double* d_h,
+                        const double* d_prev_pose, double* d_scratch, double* d_x, int32_t* d_iters);

@@ -1,0 +1,357 @@
+// k_batch.cu — the fused per-pair front end over a device-resident batch of independent
+// frame pairs: what Tracker.track + Tracker.getTransform (+ the MotionDistortionSolver call
+// in RawROAMSystem.run) do for one pair, for every pair of the batch, one launch per stage.
+//
+// Replaces (reference file:line):
+//   RawROAMSystem.py:164-165   load + convertPolarImageToCartesian     -> k_polar2cart / k_pyr_down
+//   Tracker.py:75-76           getTrackedPointsKLT                     -> k_klt
+//   getTransformKLT.py:368-376 good/bad split (order-preserving)       -> k_compact_good
+//   Tracker.py:95              rejectOutliers                          -> k_adjacency + k_clique
+//   Tracker.py:103-104         corrStatus[good rows] &= clique mask    -> k_finish_pairs
+//   Tracker.py:108-127         getTransform (Kabsch, h * 0.0864)       -> k_kabsch (+ k_finish_pairs)
+//   RawROAMSystem.py:190-212   T_wj, p_w, MDS.update_problem/optimize  -> k_mds (fused mode)
+//
+// HBM layout of an rf_batch (all sized once at rf_batch_create from rf_config maxima):
+//   raw      [max_frames][A][raw_pitch] u8   only the used columns (11 metadata + range_bins)
+//                                            are uploaded (2-D copy), raw_pitch = 16-byte multiple
+//   frames   FrameSet(count = max_frames): u8 pyramid levels (+ f32 plane if write_cart_f32)
+//   pairs    pair_idx[P][2], feats[P][Kmax][2], counts[P], prev_pose[P][3]
+//   tracks   next[P][Kmax][2], status[P][Kmax], err[P][Kmax]
+//   good     old/new[P][Kmax][2], src_row[P][Kmax], n_good[P]
+//   clique   workspace of k_clique.cu (adjacency bitsets, search stacks, masks)
+//   poses    R[P][4], h[P][2], mds_x[P][6], results[P] (rf_pair_result)
+#include "common.cuh"
+
+#define RF_PROFILE_RING 64
+#define RF_N_STAGES 8   // p2c, pyramid, klt, compact, reject, kabsch, mds, finish
+
+struct rf_batch {
+    int max_frames, max_pairs, Kmax;
+    int raw_pitch, raw_cols;
+    uint8_t* d_raw;
+    FrameSet fs;
+    int32_t* d_pair_idx; float* d_feats; int32_t* d_counts; double* d_prev_pose;
+    float* d_next; uint8_t* d_status; float* d_err;
+    float *d_good_old, *d_good_new; int32_t* d_good_src; int32_t* d_ngood;
+    void* d_clique_ws;
+    double *d_R, *d_h, *d_x; int32_t* d_iters; double* d_mds_scratch;
+    uint8_t* d_corr;             // [P][Kmax] corrStatus after the clique fix-up
+    rf_pair_result* d_results;
+    int n_frames, n_pairs; bool has_pose; bool ran_mds;
+    // per-stage CUDA events of the most recent runs (ring)
+    bool profiling; int prof_head; int prof_count;
+    cudaEvent_t ev[RF_PROFILE_RING][RF_N_STAGES + 1];
+};
+
+// ------------------------------------------------------------------------------------
+// getTransformKLT.py:368-376: good_new = nextPts[status == 1] (order preserved).  One warp
+// per pair.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_compact_good(const float* __restrict__ feats, const float* __restrict__ next, const uint8_t* __restrict__ status,
+               const int32_t* __restrict__ counts, int Kmax, int P, float* __restrict__ good_old,
+               float* __restrict__ good_new, int32_t* __restrict__ good_src, int32_t* __restrict__ n_good) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int K = counts[p];
+    const size_t base = (size_t)p * Kmax;
+    int n = 0;
+    for (int i0 = 0; i0 < K; i0 += 32) {
+        const int i = i0 + lane;
+        const bool ok = i < K && status[base + i];
+        const unsigned bm = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const size_t j = base + n + __popc(bm & ((1u << lane) - 1));
+            reinterpret_cast<float2*>(good_old)[j] = reinterpret_cast<const float2*>(feats)[base + i];
+            reinterpret_cast<float2*>(good_new)[j] = reinterpret_cast<const float2*>(next)[base + i];
+            good_src[j] = i;
+        }
+        n += __popc(bm);
+    }
+    if (lane == 0) n_good[p] = n;
+}
+
+// Assemble rf_pair_result and the caller-facing corrStatus (Tracker.py:98-104).
+__global__ void __launch_bounds__(128)
+k_finish_pairs(int P, int Kmax, const int32_t* __restrict__ counts, const int32_t* __restrict__ n_good,
+               const uint8_t* __restrict__ status, const int32_t* __restrict__ good_src,
+               const uint8_t* __restrict__ cmask, int mask_stride, const int32_t* __restrict__ n_inl,
+               const int32_t* __restrict__ nodes, const int32_t* __restrict__ cstatus, const double* __restrict__ R,
+               const double* __restrict__ hpx, double res, const double* __restrict__ x, const int32_t* __restrict__ iters,
+               int with_mds, uint8_t* __restrict__ corr, rf_pair_result* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const size_t base = (size_t)p * Kmax;
+    const int K = counts[p], ng = n_good[p];
+    for (int i = lane; i < Kmax; i += 32) corr[base + i] = 0;
+    __syncwarp();
+    for (int j = lane; j < ng; j += 32)
+        if (cmask[(size_t)p * mask_stride + j]) corr[base + good_src[base + j]] = 1;
+    if (lane == 0) {
+        rf_pair_result r;
+        for (int k = 0; k < 4; ++k) r.R[k] = R[(size_t)p * 4 + k];
+        r.h[0] = hpx[(size_t)p * 2] * res; r.h[1] = hpx[(size_t)p * 2 + 1] * res;   // Tracker.py:125-126
+        for (int k = 0; k < 6; ++k) r.mds_x[k] = with_mds ? x[(size_t)p * 6 + k] : 0.0;
+        r.n_features = K; r.n_good = ng; r.n_inliers = n_inl[p];
+        r.mds_iters = with_mds ? iters[p] : 0;
+        r.status = cstatus[p]; r.clique_nodes = nodes[p];
+        out[p] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+static void batch_free(rf_batch* b) {
+    if (!b) return;
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(b->d_raw); rf_frameset_free(&b->fs);
+    F(b->d_pair_idx); F(b->d_feats); F(b->d_counts); F(b->d_prev_pose);
+    F(b->d_next); F(b->d_status); F(b->d_err);
+    F(b->d_good_old); F(b->d_good_new); F(b->d_good_src); F(b->d_ngood);
+    F(b->d_clique_ws); F(b->d_R); F(b->d_h); F(b->d_x); F(b->d_iters); F(b->d_mds_scratch);
+    F(b->d_corr); F(b->d_results);
+    for (int i = 0; i < RF_PROFILE_RING; ++i)
+        for (int s = 0; s <= RF_N_STAGES; ++s)
+            if (b->ev[i][s]) cudaEventDestroy(b->ev[i][s]);
+    delete b;
+}
+
+#define RF_BALLOC(ptr, bytes)                                                                       \
+    do {                                                                                            \
+        if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) {                                   \
+            cudaGetLastError(); batch_free(b);                                                      \
+            return rf_fail(h, RF_E_NOMEM, "rf_batch_create: cudaMalloc(%zu) failed", (size_t)(bytes)); \
+        }                                                                                           \
+    } while (0)
+
+extern "C" {
+
+int rf_batch_create(rf_handle* h, rf_batch** out) {
+    if (!h || !out) return rf_fail(h, RF_E_BADARG, "rf_batch_create: null argument");
+    *out = nullptr;
+    const rf_config& c = h->cfg;
+    rf_batch* b = new rf_batch();
+    memset(b, 0, sizeof(*b));
+    b->max_frames = c.max_frames; b->max_pairs = c.max_pairs; b->Kmax = c.max_features;
+    b->raw_cols = c.meta_bytes + c.range_bins;
+    b->raw_pitch = (b->raw_cols + 15) & ~15;
+    const size_t P = b->max_pairs, K = b->Kmax;
+    RF_BALLOC(b->d_raw, (size_t)b->max_frames * c.azimuths * b->raw_pitch);
+    int rc = rf_frameset_alloc(h, &b->fs, b->max_frames, c.write_cart_f32 != 0);
+    if (rc) { batch_free(b); return rc; }
+    RF_BALLOC(b->d_pair_idx, P * 2 * sizeof(int32_t));
+    RF_BALLOC(b->d_feats, P * K * 2 * sizeof(float));
+    RF_BALLOC(b->d_counts, P * sizeof(int32_t));
+    RF_BALLOC(b->d_prev_pose, P * 3 * sizeof(double));
+    RF_BALLOC(b->d_next, P * K * 2 * sizeof(float));
+    RF_BALLOC(b->d_status, P * K);
+    RF_BALLOC(b->d_err, P * K * sizeof(float));
+    RF_BALLOC(b->d_good_old, P * K * 2 * sizeof(float));
+    RF_BALLOC(b->d_good_new, P * K * 2 * sizeof(float));
+    RF_BALLOC(b->d_good_src, P * K * sizeof(int32_t));
+    RF_BALLOC(b->d_ngood, P * sizeof(int32_t));
+    RF_BALLOC(b->d_clique_ws, rf_clique_ws_total((int)K, (int)P));
+    RF_BALLOC(b->d_R, P * 4 * sizeof(double));
+    RF_BALLOC(b->d_h, P * 2 * sizeof(double));
+    RF_BALLOC(b->d_x, P * 6 * sizeof(double));
+    RF_BALLOC(b->d_iters, P * sizeof(int32_t));
+    RF_BALLOC(b->d_mds_scratch, P * K * 5 * sizeof(double));
+    RF_BALLOC(b->d_corr, P * K);
+    RF_BALLOC(b->d_results, P * sizeof(rf_pair_result));
+    *out = b;
+    return RF_OK;
+}
+
+void rf_batch_destroy(rf_handle* h, rf_batch* b) {
+    if (!b) return;
+    if (h) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    batch_free(b);
+}
+
+int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
+                          int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose) {
+    if (!h || !b || n_frames < 0 || n_pairs < 0 || (n_frames > 0 && !raw) ||
+        (n_pairs > 0 && (!pair_idx || !feats || !feat_counts)))
+        return rf_fail(h, RF_E_BADARG, "rf_batch_upload: null argument");
+    if (n_frames > b->max_frames || n_pairs > b->max_pairs)
+        return rf_fail(h, RF_E_CAPACITY, "rf_batch_upload: %d frames / %d pairs exceed the batch capacity (%d / %d)",
+                       n_frames, n_pairs, b->max_frames, b->max_pairs);
+    const rf_config& c = h->cfg;
+    for (int p = 0; p < n_pairs; ++p) {
+        if (feat_counts[p] < 0 || feat_counts[p] > b->Kmax)
+            return rf_fail(h, RF_E_CAPACITY, "rf_batch_upload: pair %d has %d features (max_features = %d)", p,
+                           feat_counts[p], b->Kmax);
+        if (pair_idx[2 * p] < 0 || pair_idx[2 * p] >= n_frames || pair_idx[2 * p + 1] < 0 || pair_idx[2 * p + 1] >= n_frames)
+            return rf_fail(h, RF_E_BADARG, "rf_batch_upload: pair %d references a frame outside [0, %d)", p, n_frames);
+    }
+    if (n_frames)
+        RF_CUDA(h, cudaMemcpy2DAsync(b->d_raw, b->raw_pitch, raw, c.raw_width, b->raw_cols, (size_t)n_frames * c.azimuths,
+                                     cudaMemcpyHostToDevice, h->stream));
+    if (n_pairs) {
+        RF_CUDA(h, cudaMemcpyAsync(b->d_pair_idx, pair_idx, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(b->d_feats, feats, (size_t)n_pairs * b->Kmax * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(b->d_counts, feat_counts, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        if (prev_pose)
+            RF_CUDA(h, cudaMemcpyAsync(b->d_prev_pose, prev_pose, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    b->n_frames = n_frames; b->n_pairs = n_pairs; b->has_pose = prev_pose != nullptr;
+    return RF_OK;
+}
+
+int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx, int n_pairs,
+                    const float* feats, const int32_t* feat_counts, const double* prev_pose) {
+    int rc = rf_batch_upload_async(h, b, raw, n_frames, pair_idx, n_pairs, feats, feat_counts, prev_pose);
+    if (rc) return rc;
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+int rf_batch_set_profiling(rf_handle* h, rf_batch* b, int on) {
+    if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_set_profiling: null argument");
+    if (on && !b->ev[0][0]) {
+        for (int i = 0; i < RF_PROFILE_RING; ++i)
+            for (int s = 0; s <= RF_N_STAGES; ++s) RF_CUDA(h, cudaEventCreate(&b->ev[i][s]));
+    }
+    b->profiling = on != 0; b->prof_head = 0; b->prof_count = 0;
+    return RF_OK;
+}
+
+int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
+    if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_run_async: null argument");
+    const rf_config& c = h->cfg;
+    const int P = b->n_pairs, F = b->n_frames, K = b->Kmax;
+    cudaEvent_t* ev = b->profiling ? b->ev[b->prof_head] : nullptr;
+    int stage = 0;
+    auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], h->stream); ++stage; };
+    int rc;
+    mark();
+    if (F) {
+        rc = rf_launch_polar2cart_u8(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, c.meta_bytes, b->fs, 0, F,
+                                     b->fs.cart != nullptr);
+        if (rc) return rc;
+    }
+    mark();
+    if (F && (rc = rf_launch_pyramid(h, b->fs, 0, F))) return rc;
+    mark();
+    if (P) {
+        if ((rc = rf_launch_klt(h, b->fs, b->fs, b->d_pair_idx, b->d_feats, b->d_counts, K, P, b->d_next, b->d_status,
+                                b->d_err, 1))) return rc;
+        mark();
+        k_compact_good<<<(P + 3) / 4, 128, 0, h->stream>>>(b->d_feats, b->d_next, b->d_status, b->d_counts, K, P,
+                                                           b->d_good_old, b->d_good_new, b->d_good_src, b->d_ngood);
+        RF_CHECK_LAUNCH(h);
+        mark();
+        uint8_t* d_mask; int mask_stride; int32_t *d_ninl, *d_nodes, *d_cstatus;
+        if ((rc = rf_launch_reject(h, b->d_clique_ws, b->d_good_old, b->d_good_new, b->d_ngood, K, P, &d_mask, &mask_stride,
+                                   &d_ninl, &d_nodes, &d_cstatus))) return rc;
+        mark();
+        // Tracker.getTransform(good_old, good_new): src = good_old, target = good_new
+        if ((rc = rf_launch_kabsch(h, b->d_good_old, b->d_good_new, d_mask, mask_stride, b->d_ngood, K, P, b->d_R, b->d_h,
+                                   nullptr))) return rc;
+        mark();
+        if (with_mds) {
+            if ((rc = rf_launch_mds_fused(h, b->d_good_old, b->d_good_new, d_mask, mask_stride, b->d_ngood, K, P, b->d_R,
+                                          b->d_h, b->has_pose ? b->d_prev_pose : nullptr, b->d_mds_scratch, b->d_x,
+                                          b->d_iters))) return rc;
+        }
+        mark();
+        k_finish_pairs<<<(P + 3) / 4, 128, 0, h->stream>>>(P, K, b->d_counts, b->d_ngood, b->d_status, b->d_good_src, d_mask,
+                                                           mask_stride, d_ninl, d_nodes, d_cstatus, b->d_R, b->d_h,
+                                                           c.cart_res_m, b->d_x, b->d_iters, with_mds, b->d_corr,
+                                                           b->d_results);
+        RF_CHECK_LAUNCH(h);
+        mark();
+    } else {
+        while (stage <= RF_N_STAGES) mark();
+    }
+    b->ran_mds = with_mds != 0;
+    if (ev) { b->prof_head = (b->prof_head + 1) % RF_PROFILE_RING; if (b->prof_count < RF_PROFILE_RING) b->prof_count++; }
+    return RF_OK;
+}
+
+int rf_batch_stage_times(rf_handle* h, rf_batch* b, float* ms_sum, int cap, int* n_runs) {
+    if (!h || !b || !ms_sum || cap < RF_N_STAGES) return rf_fail(h, RF_E_BADARG, "rf_batch_stage_times: bad argument");
+    for (int s = 0; s < cap; ++s) ms_sum[s] = 0.f;
+    if (n_runs) *n_runs = b->prof_count;
+    if (!b->profiling) return RF_OK;
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < b->prof_count; ++r) {
+        const int i = (b->prof_head - 1 - r + 2 * RF_PROFILE_RING) % RF_PROFILE_RING;
+        for (int s = 0; s < RF_N_STAGES; ++s) {
+            float ms = 0.f;
+            RF_CUDA(h, cudaEventElapsedTime(&ms, b->ev[i][s], b->ev[i][s + 1]));
+            ms_sum[s] += ms;
+        }
+    }
+    b->prof_count = 0;
+    return RF_OK;
+}
+
+int rf_batch_download_async(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status) {
+    if (!h || !b || (b->n_pairs > 0 && !results)) return rf_fail(h, RF_E_BADARG, "rf_batch_download: null argument");
+    const size_t P = b->n_pairs, K = b->Kmax;
+    if (!P) return RF_OK;
+    RF_CUDA(h, cudaMemcpyAsync(results, b->d_results, P * sizeof(rf_pair_result), cudaMemcpyDeviceToHost, h->stream));
+    if (next_xy) RF_CUDA(h, cudaMemcpyAsync(next_xy, b->d_next, P * K * 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (status) RF_CUDA(h, cudaMemcpyAsync(status, b->d_corr, P * K, cudaMemcpyDeviceToHost, h->stream));
+    return RF_OK;
+}
+
+int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status) {
+    int rc = rf_batch_download_async(h, b, results, next_xy, status);
+    if (rc) return rc;
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+int rf_batch_klt_status(rf_handle* h, rf_batch* b, uint8_t* klt_status, float* err) {
+    if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_klt_status: null argument");
+    const size_t P = b->n_pairs, K = b->Kmax;
+    if (!P) return RF_OK;
+    if (klt_status) RF_CUDA(h, cudaMemcpyAsync(klt_status, b->d_status, P * K, cudaMemcpyDeviceToHost, h->stream));
+    if (err) RF_CUDA(h, cudaMemcpyAsync(err, b->d_err, P * K * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx, int n_pairs,
+                   const float* feats, const int32_t* feat_counts, const double* prev_pose, int with_mds,
+                   rf_pair_result* results, float* next_xy, uint8_t* status) {
+    int rc = rf_batch_upload_async(h, b, raw, n_frames, pair_idx, n_pairs, feats, feat_counts, prev_pose);
+    if (rc) return rc;
+    if ((rc = rf_batch_run_async(h, b, with_mds))) return rc;
+    return rf_batch_download(h, b, results, next_xy, status);
+}
+
+int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, int what, void* out, int* rows, int* cols) {
+    if (!h || !b || frame < 0 || frame >= b->n_frames) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: bad frame");
+    if (what == 0) {
+        if (!b->fs.cart) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: batch was created with write_cart_f32 = 0");
+        if (rows) *rows = h->n;
+        if (cols) *cols = h->n;
+        if (out) RF_CUDA(h, cudaMemcpyAsync(out, b->fs.cart + (size_t)frame * b->fs.cart_stride, (size_t)h->n * h->n * 4,
+                                            cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        const int l = what - 1;
+        if (l < 0 || l >= b->fs.n_levels) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: no pyramid level %d", l);
+        if (rows) *rows = b->fs.h[l];
+        if (cols) *cols = b->fs.w[l];
+        if (out) RF_CUDA(h, cudaMemcpyAsync(out, b->fs.lvl[l] + (size_t)frame * b->fs.lvl_stride[l],
+                                            (size_t)b->fs.w[l] * b->fs.h[l], cudaMemcpyDeviceToHost, h->stream));
+    }
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+// pinned host staging for callers that want asynchronous uploads (NumPy arrays can wrap it)
+int rf_host_alloc(size_t bytes, void** out) {
+    if (!out) return RF_E_BADARG;
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return rf_fail(nullptr, RF_E_NOMEM, "rf_host_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return RF_OK;
+}
+void rf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+"""GPU parity of the fused batch path (rf_track_batch: Tracker.track + getTransform + MDS for
+many independent pairs) against the reference-generated goldens and against the reference's
+own library calls (oracle/ref_pipeline.py) on seeded synthetic Oxford-shaped scans.
+Tolerances (north_star): identical status / clique, tracks <= 0.02 px, pose <= 1e-4 m, 1e-5 rad."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_PX, TOL_M, TOL_RAD = 0.02, 1e-4, 1e-5
+RES = 0.0864
+
+
+def _engine(range_bins=2025, res=0.0432, max_pairs=16, max_frames=16, max_features=256, f32=0):
+    from radarslampy_b200 import _ffi
+    cfg = _ffi.default_config()
+    cfg.range_bins = range_bins
+    cfg.cart_res_m = 2 * res
+    cfg.dist_thr_px = 0.5 / (2 * res)
+    cfg.max_pairs, cfg.max_frames, cfg.max_features = max_pairs, max_frames, max_features
+    cfg.write_cart_f32 = f32
+    return _ffi.RadarFE(cfg)
+
+
+def _pad(feat_list, kmax):
+    feats = np.zeros((len(feat_list), kmax, 2), np.float32)
+    counts = np.zeros(len(feat_list), np.int32)
+    for i, f in enumerate(feat_list):
+        counts[i] = len(f)
+        feats[i, :len(f)] = f
+    return feats, counts
+
+
+def _theta(R):
+    R = np.asarray(R).reshape(2, 2)
+    return np.arctan2(R[1, 0], R[0, 0])
+
+
+def test_batch_matches_reference_goldens(golden):
+    fr, st = golden["tiny_frames"], golden["tiny_stages"]
+    fe = _engine(f32=1)
+    try:
+        b = fe.new_batch()
+        raw = np.stack([fr[f"raw_{i}"] for i in range(3)])
+        feats, counts = _pad([st["feat_in_0"], st["feat_in_1"]], 256)
+        T0 = st["mds_Twj0_0"]
+        prev_pose = np.array([[T0[0, 2], T0[1, 2], np.arctan2(T0[1, 0], T0[0, 0])], [0, 0, 0]])
+        res, nxt, corr = b.track(raw, [[0, 1], [1, 2]], feats, counts, prev_pose=prev_pose, with_mds=True)
+        klt_st, err = b.klt_status()
+        for p in range(2):
+            K = counts[p]
+            ref_status = st[f"klt_status_{p}"].ravel()
+            assert np.array_equal(klt_st[p, :K], ref_status)
+            good = ref_status.astype(bool)
+            assert np.abs(nxt[p, :K][good] - st[f"klt_good_new_{p}"]).max() <= TOL_PX
+            want = ref_status.copy()
+            want[good] &= st[f"rej_mask_{p}"].astype(np.uint8)
+            assert np.array_equal(corr[p, :K], want)                       # Tracker.py:102-104
+            assert not corr[p, K:].any()
+            r = res[p]
+            assert (r["n_features"], r["n_good"], r["n_inliers"]) == (K, good.sum(), st[f"rej_mask_{p}"].sum())
+            assert r["status"] == 0
+            assert np.abs(r["h"] - st[f"svd_h_{p}"].ravel() * RES).max() <= TOL_M
+            assert abs(_theta(r["R"]) - _theta(st[f"svd_R_{p}"])) <= TOL_RAD
+        # pair 0: previous frame == keyframe with zero velocity -> the fused MDS problem is the reference's
+        x, ref = res[0]["mds_x"], st["mds_x_0"]
+        assert np.abs(x[3:5] - ref[3:5]).max() <= TOL_M and abs(x[5] - ref[5]) <= TOL_RAD
+        # frames converted inside the batch are bit-exact too
+        import hashlib
+        assert hashlib.sha256(b.frame(1, 0).tobytes()).hexdigest() == str(fr["cart_sha256_1"])
+        assert hashlib.sha256(b.frame(2, 1).tobytes()).hexdigest() == str(fr["u8_sha256_2"])
+        b.close()
+    finally:
+        fe.close()
+
+
+def test_batch_synthetic_sequence_vs_reference_libraries():
+    """BASELINE config 2/3 shape (0.0438 m/bin -> 1997 bins, 1996^2 image): every pair of a seeded
+    synthetic sequence against the reference's own cv2/scipy/networkx/numpy calls."""
+    from oracle import ref_pipeline as P
+    from radarslampy_b200 import synthetic as S
+    res_m, n = 0.0438, 6
+    rb = int(87.5 / res_m)
+    world = S.World()
+    raw, poses = S.make_sequence(n, res_m=res_m, world=world)
+    pair_idx, feats, counts = S.sequence_pairs(n, world, poses, res_m, rb, k=200, max_features=256)
+    fe = _engine(range_bins=rb, res=res_m)
+    try:
+        b = fe.new_batch()
+        res, nxt, corr = b.track(raw, pair_idx, feats, counts, prev_pose=poses[:-1], with_mds=True)
+        klt_st, _ = b.klt_status()
+        assert np.array_equal(b.frame(0, 1), (P.polar_to_cart(P.extract_polar(raw[0], res_m)) * 255).astype(np.uint8))
+        for p in range(n - 1):
+            K = counts[p]
+            o = P.track_pair(raw[p], raw[p + 1], feats[p, :K], prev_pose=poses[p], with_mds=True, range_res_m=res_m)
+            assert np.array_equal(corr[p, :K], o["corr_status"]), f"pair {p}: inlier set differs"
+            assert res[p]["n_good"] == o["n_good"] and res[p]["n_inliers"] == o["n_inliers"]
+            g = klt_st[p, :K].astype(bool)
+            assert np.abs(nxt[p, :K][g] - o["good_new"]).max() <= TOL_PX
+            assert np.abs(res[p]["h"] - o["h"]).max() <= TOL_M
+            assert abs(_theta(res[p]["R"]) - _theta(o["R"])) <= TOL_RAD
+            assert np.abs(res[p]["mds_x"][3:5] - o["mds_x"][3:5]).max() <= TOL_M
+            assert abs(res[p]["mds_x"][5] - o["mds_x"][5]) <= TOL_RAD
+            # and the estimate is physically right: 2.5 m / 0.025 rad per frame
+            assert abs(_theta(res[p]["R"]) - 0.025) < 2e-3
+        b.close()
+    finally:
+        fe.close()
+
+
+def test_batch_edge_cases():
+    from radarslampy_b200 import synthetic as S
+    fe = _engine(max_pairs=4, max_frames=4, max_features=64)
+    try:
+        b = fe.new_batch()
+        rng = np.random.default_rng(1)
+        raw = rng.integers(0, 256, (2, 400, 3779), dtype=np.uint8)
+        feats = np.zeros((3, 64, 2), np.float32)
+        feats[1, :5] = [[-100, -100], [5000, 5000], [10, 10], [1000, 1000], [2023, 2023]]
+        feats[2, :64] = rng.uniform(0, 2024, (64, 2))
+        counts = np.array([0, 5, 64], np.int32)
+        res, nxt, corr = b.track(raw, [[0, 1], [0, 0], [1, 1]], feats, counts, with_mds=True)
+        assert res[0]["n_good"] == 0 and res[0]["n_inliers"] == 0
+        assert np.array_equal(np.asarray(res[0]["R"]), [1, 0, 0, 1]) and not np.asarray(res[0]["h"]).any()
+        assert res[1]["n_good"] <= 3                       # the two far-outside points are lost (status 0)
+        # identical frames: every tracked point stays put -> identity transform, all good points inliers
+        assert res[2]["n_inliers"] == res[2]["n_good"] > 0
+        assert abs(_theta(res[2]["R"])) < 1e-6 and np.abs(res[2]["h"]).max() < 1e-3
+        assert np.all(np.isfinite(res["mds_x"]))
+        # capacity and argument errors are reported, not crashed on
+        with pytest.raises(ValueError):
+            b.track(raw, [[0, 2]], feats[:1], counts[:1])
+        with pytest.raises(ValueError):
+            b.track(np.zeros((5, 400, 3779), np.uint8), [[0, 1]], feats[:1], counts[:1])
+        with pytest.raises(ValueError):
+            b.track(raw, [[0, 1]], feats[:1], np.array([65], np.int32))
+        # empty batch
+        res, _, _ = b.track(raw, np.zeros((0, 2), np.int32), np.zeros((0, 64, 2), np.float32), np.zeros(0, np.int32))
+        assert len(res) == 0
+        b.close()
+    finally:
+        fe.close()
+
+
+def test_batch_profiling_and_launch_count():
+    from radarslampy_b200 import synthetic as S
+    fe = _engine(max_pairs=4, max_frames=4, max_features=64)
+    try:
+        b = fe.new_batch()
+        rng = np.random.default_rng(2)
+        raw = rng.integers(0, 256, (2, 400, 3779), dtype=np.uint8)
+        feats = rng.uniform(100, 1900, (1, 64, 2)).astype(np.float32)
+        b.upload(raw, [[0, 1]], feats, [64])
+        b.set_profiling(True)
+        n0 = fe.launch_count()
+        for _ in range(3):
+            b.run_async(with_mds=True)
+        fe.sync()
+        assert fe.launch_count() - n0 == 3 * 11      # p2c, 3 pyramid levels, klt, compact, adjacency, clique, kabsch, mds, finish
+        ms, runs = b.stage_times()
+        assert runs == 3 and all(v >= 0 for v in ms.values()) and ms["polar2cart"] > 0 and ms["klt"] > 0
+        b.close()
+    finally:
+        fe.close()
