@@ -145,7 +145,9 @@ RF_API int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const fl
 /* Test hook: the clique search alone on a caller-supplied adjacency matrix (K x K bytes,
  * diagonal ignored).  prune == 0 enumerates EVERY maximal clique in networkx order and
  * returns their count plus an order-sensitive FNV-1a hash over (size, members...) of each
- * yield, so tests can pin the enumeration ORDER against the oracle.  mask_out: K int32. */
+ * yield, so tests can pin the enumeration ORDER against the oracle.  prune | 2 runs the
+ * production configuration (no hash, clique shortcut enabled) and reports only mask/size/nodes.
+ * mask_out: K int32. */
 RF_API int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, int32_t* mask_out, int* size,
                      int64_t* n_yields, uint64_t* order_hash, int64_t* nodes);
 

@@ -30,6 +30,7 @@ struct CliqueGeom {
     int TABN;    // int16 slots in an explicit table (Kpad / 2)
     int SW;      // 32-bit words per set = NW + 4 + TABN / 2
     int SEQCAP;  // max degree of a node whose adjacency set has a table smaller than Kpad
+    int RS;      // row stride (words) of the adjacency rows staged in shared memory (odd: no bank conflicts)
 };
 
 __host__ __device__ inline int growth_size(int n) {
@@ -49,7 +50,9 @@ struct SetRef {
     __device__ int16_t* tab() const { return (int16_t*)(w + NW + 4); }
 };
 
-// ---- sequential emulation helpers (lane 0 only) -------------------------------------
+#define FULL 0xffffffffu
+
+// ---- sequential emulation helpers (lane 0 only; fallback for sequences longer than a warp) ----
 __device__ void tab_insert_clean(int16_t* t, int mask, int key) {
     unsigned perturb = (unsigned)key;
     unsigned i = (unsigned)key & mask;
@@ -64,9 +67,7 @@ __device__ void tab_insert_clean(int16_t* t, int mask, int key) {
     }
 }
 
-// Build the explicit table of a FRESH set from an insertion sequence (no dummies, no
-// duplicates): successive adds with CPython's growth rule.  `tmp` is scratch of >= n keys.
-__device__ void tab_build_by_adds(int16_t* t, const int16_t* seq, int n, int16_t* tmp) {
+__device__ __noinline__ void tab_build_by_adds_seq(int16_t* t, const int16_t* seq, int n, int16_t* tmp) {
     int mask = 7, fill = 0;
     for (int i = 0; i < 8; ++i) t[i] = EMPTY_SLOT;
     for (int s = 0; s < n; ++s) {
@@ -84,18 +85,152 @@ __device__ void tab_build_by_adds(int16_t* t, const int16_t* seq, int n, int16_t
     }
 }
 
+// ---- warp-parallel open-addressing insertion ----------------------------------------------
+// Lane l holds the l-th key of an insertion sequence (l < n <= 32) into an EMPTY table.
+// Sequential insertion places key j at the first slot of its probe sequence that no key
+// i < j occupies.  That assignment is the unique fix-point of "every key claims its current
+// probe slot; the lowest insertion index wins a contested slot; losers (and evicted keys)
+// advance along their own probe sequence" — proved by induction on j: a slot that ever
+// rejected j stays held by some key < j.  So all keys probe concurrently and only genuine
+// collisions cost extra rounds.  Probe sequence = CPython set_insert_clean: i, i+1..i+9
+// (only if i+9 <= mask), then i = (5i + 1 + (perturb >>= 5)) & mask.
+__device__ __forceinline__ int par_insert(int key, bool active, int mask, int lane) {
+    unsigned i = (unsigned)key & (unsigned)mask, j = 0, perturb = (unsigned)key;
+    for (;;) {
+        const int slot = (int)(i + j);
+        const unsigned grp = __match_any_sync(FULL, active ? slot : (0x40000000 | lane));
+        const bool lose = active && (__ffs(grp) - 1 != lane);
+        if (!__any_sync(FULL, lose)) return slot;
+        if (lose) {
+            if (i + 9 <= (unsigned)mask && j < 9) ++j;
+            else { perturb >>= 5; i = (i * 5 + 1 + perturb) & (unsigned)mask; j = 0; }
+        }
+    }
+}
+
+__device__ __forceinline__ void tab_clear(int16_t* t, int size, int lane) {
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(t);       // tables are 4-byte aligned, size >= 8
+    for (int i = lane; i < (size >> 1); i += 32) t32[i] = 0xFFFFFFFFu;   // EMPTY_SLOT == -1
+}
+
+// Same fix-point for up to 96 keys (three per lane: key index j = lane + 32 r) into an empty
+// table of at most 128 slots: contested slots are arbitrated through `own` (one word per
+// slot, atomicMin of the insertion index) instead of a warp match.
+#define PAR_KPL 3
+__device__ __noinline__ void par_insert_multi(int16_t* t, int mask, const int16_t* seq, int n, uint32_t* own, int lane) {
+    const int size = mask + 1;
+    for (int i = lane; i < size; i += 32) own[i] = 0xFFFFFFFFu;
+    unsigned pi[PAR_KPL], pj[PAR_KPL], pp[PAR_KPL];
+    int key[PAR_KPL];
+#pragma unroll
+    for (int r = 0; r < PAR_KPL; ++r) {
+        const int j = lane + 32 * r;
+        key[r] = j < n ? seq[j] : 0;
+        pi[r] = (unsigned)key[r] & (unsigned)mask; pj[r] = 0; pp[r] = (unsigned)key[r];
+    }
+    __syncwarp();
+    for (;;) {
+#pragma unroll
+        for (int r = 0; r < PAR_KPL; ++r)
+            if (lane + 32 * r < n) atomicMin(&own[pi[r] + pj[r]], (unsigned)(lane + 32 * r));
+        __syncwarp();
+        bool lose = false;
+#pragma unroll
+        for (int r = 0; r < PAR_KPL; ++r) {
+            if (lane + 32 * r < n && own[pi[r] + pj[r]] != (unsigned)(lane + 32 * r)) {
+                lose = true;
+                if (pi[r] + 9 <= (unsigned)mask && pj[r] < 9) ++pj[r];
+                else { pp[r] >>= 5; pi[r] = (pi[r] * 5 + 1 + pp[r]) & (unsigned)mask; pj[r] = 0; }
+            }
+        }
+        if (!__any_sync(FULL, lose)) break;
+    }
+#pragma unroll
+    for (int r = 0; r < PAR_KPL; ++r)
+        if (lane + 32 * r < n) t[pi[r] + pj[r]] = (int16_t)key[r];
+    __syncwarp();
+}
+
+// rank of this lane's slot among the first `m` lanes (slot order of a table of <= 32 slots)
+__device__ __forceinline__ int slot_rank(int slot, int m, int lane) {
+    const unsigned occ = __reduce_or_sync(FULL, lane < m ? (1u << slot) : 0u);
+    return lane < m ? __popc(occ & ((1u << slot) - 1u)) : lane;
+}
+
+// Explicit table of a FRESH set grown by n successive adds of seq[0..n) (no dummies, no
+// duplicates), CPython growth rule: 8 slots; after the 5th add -> 32 (old entries re-inserted
+// in SLOT order); after the 19th -> 128; after the 77th -> 512; ...
+__device__ __noinline__ void tab_build_by_adds(int16_t* t, const int16_t* seq, int n, int16_t* tmp, uint32_t* own, int lane) {
+    if (n > 76) {
+        if (lane == 0) tab_build_by_adds_seq(t, seq, n, tmp);
+        __syncwarp();
+        return;
+    }
+    const int size = n <= 4 ? 8 : (n <= 18 ? 32 : 128);
+    tab_clear(t, size, lane);
+    int key = lane < n ? seq[lane] : 0;
+    int slot;
+    if (n <= 4) {
+        slot = par_insert(key, lane < n, 7, lane);
+    } else {
+        int s = par_insert(key, lane < 5, 7, lane);
+        int rank = slot_rank(s, 5, lane);
+        __syncwarp();
+        if (lane < n) tmp[rank] = (int16_t)key;
+        __syncwarp();
+        key = lane < n ? tmp[lane] : 0;
+        const int m = n < 19 ? n : 19;
+        s = par_insert(key, lane < m, 31, lane);
+        if (n < 19) slot = s;
+        else {
+            rank = slot_rank(s, 19, lane);
+            __syncwarp();
+            if (lane < n) tmp[rank] = (int16_t)key;
+            __syncwarp();
+            if (n > 32) {
+                // insertion order into the 128-slot table: the 19 re-inserted keys, then seq[19..n)
+                for (int j = 32 + lane; j < n; j += 32) tmp[j] = seq[j];
+                __syncwarp();
+                par_insert_multi(t, 127, tmp, n, own, lane);
+                return;
+            }
+            key = lane < n ? tmp[lane] : 0;
+            slot = par_insert(key, lane < n, 127, lane);
+        }
+    }
+    __syncwarp();
+    if (lane < n) t[slot] = (int16_t)key;
+    __syncwarp();
+}
+
+// clean re-insertion of seq[0..m) (in that order) into an empty table with `mask`
+__device__ __noinline__ void tab_reinsert(int16_t* t, int mask, const int16_t* seq, int m, uint32_t* own, int lane) {
+    tab_clear(t, mask + 1, lane);
+    __syncwarp();
+    if (m <= 32) {
+        const int key = lane < m ? seq[lane] : 0;
+        const int slot = par_insert(key, lane < m, mask, lane);
+        if (lane < m) t[slot] = (int16_t)key;
+    } else if (m <= 32 * PAR_KPL && mask <= 127) {
+        par_insert_multi(t, mask, seq, m, own, lane);
+    } else if (lane == 0) {
+        for (int i = 0; i < m; ++i) tab_insert_clean(t, mask, seq[i]);
+    }
+    __syncwarp();
+}
+
 // ---- warp-cooperative primitives ----------------------------------------------------
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, d);
+        int t = __shfl_up_sync(FULL, v, d);
         if (lane >= d) v += t;
     }
     return v;
 }
 
 // ascending keys of (a [& | &~] f) -> out ; returns count
-__device__ int bits_to_seq(const uint32_t* a, const uint32_t* f, bool want_in, int NW, int16_t* out, int lane) {
+__device__ __noinline__ int bits_to_seq(const uint32_t* a, const uint32_t* f, bool want_in, int NW, int16_t* out, int lane) {
     int total = 0;
     for (int w0 = 0; w0 < NW; w0 += 32) {
         const int w = w0 + lane;
@@ -105,20 +240,20 @@ __device__ int bits_to_seq(const uint32_t* a, const uint32_t* f, bool want_in, i
         const int incl = warp_incl_scan(c, lane);
         int base = total + incl - c;
         while (v) { const int b = __ffs(v) - 1; out[base++] = (int16_t)(w * 32 + b); v &= v - 1; }
-        total += __shfl_sync(0xffffffffu, incl, 31);
+        total += __shfl_sync(FULL, incl, 31);
     }
     return total;
 }
 
 // live keys of explicit table in slot order, filtered -> out ; returns count
-__device__ int tab_to_seq(const int16_t* t, int size, const uint32_t* f, bool want_in, int16_t* out, int lane) {
+__device__ __noinline__ int tab_to_seq(const int16_t* t, int size, const uint32_t* f, bool want_in, int16_t* out, int lane) {
     int total = 0;
     for (int i0 = 0; i0 < size; i0 += 32) {
         const int i = i0 + lane;
         const int k = i < size ? t[i] : -1;
         bool ok = k >= 0;
         if (ok && f) ok = (((f[k >> 5] >> (k & 31)) & 1u) != 0) == want_in;
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const unsigned m = __ballot_sync(FULL, ok);
         if (ok) out[total + __popc(m & ((1u << lane) - 1))] = (int16_t)k;
         total += __popc(m);
     }
@@ -126,28 +261,26 @@ __device__ int tab_to_seq(const int16_t* t, int size, const uint32_t* f, bool wa
 }
 
 // ordered live keys of a set (optionally filtered by bitset f)
-__device__ int set_to_seq(const SetRef& s, int K, const uint32_t* f, bool want_in, int16_t* out, int lane) {
+__device__ __forceinline__ int set_to_seq(const SetRef& s, int K, int NWe, const uint32_t* f, bool want_in, int16_t* out, int lane) {
     const int size = s.mask() + 1;
-    if (size >= K) return bits_to_seq(s.bits(), f, want_in, s.NW, out, lane);
+    if (size >= K) return bits_to_seq(s.bits(), f, want_in, NWe, out, lane);
     return tab_to_seq(s.tab(), size, f, want_in, out, lane);
 }
 
-__device__ int bits_count2(const uint32_t* a, const uint32_t* b, bool and_not, int NW, int lane) {
+__device__ __forceinline__ int bits_count2(const uint32_t* a, const uint32_t* b, bool and_not, int NWe, int lane) {
     int c = 0;
-    for (int w = lane; w < NW; w += 32) c += __popc(and_not ? (a[w] & ~b[w]) : (a[w] & b[w]));
-    return __reduce_add_sync(0xffffffffu, c);
+    for (int w = lane; w < NWe; w += 32) c += __popc(and_not ? (a[w] & ~b[w]) : (a[w] & b[w]));
+    return __reduce_add_sync(FULL, c);
 }
 
-// dst = fresh set holding (a op b) where the insertion order is given by `seq` when the
-// table is small; bits are always a op b.
-__device__ void fresh_from(const SetRef& dst, const uint32_t* a, const uint32_t* b, bool and_not, int n, int K,
-                           const int16_t* seq, int16_t* tmp, int lane) {
-    for (int w = lane; w < dst.NW; w += 32) dst.bits()[w] = and_not ? (a[w] & ~b[w]) : (a[w] & b[w]);
+// dst = fresh set holding (a op b); `seq` is the insertion order (needed only when the table
+// is smaller than the node count); bits are always a op b.
+__device__ __forceinline__ void fresh_from(const SetRef& dst, const uint32_t* a, const uint32_t* b, bool and_not, int n, int K,
+                                           int NWe, const int16_t* seq, int16_t* tmp, uint32_t* own, int lane) {
+    for (int w = lane; w < NWe; w += 32) dst.bits()[w] = and_not ? (a[w] & ~b[w]) : (a[w] & b[w]);
     const int size = growth_size(n);
-    if (lane == 0) {
-        dst.mask() = size - 1; dst.fill() = n; dst.used() = n; dst.finger() = 0;
-        if (size < K) tab_build_by_adds(dst.tab(), seq, n, tmp);
-    }
+    if (lane == 0) { dst.mask() = size - 1; dst.fill() = n; dst.used() = n; dst.finger() = 0; }
+    if (size < K) tab_build_by_adds(dst.tab(), seq, n, tmp, own, lane);
     __syncwarp();
 }
 
@@ -158,9 +291,9 @@ struct CliqueArgs {
     int Kmax;                  // row capacity of the per-problem arrays (== g.Kpad)
     const uint32_t* adjbits;   // [P][Kpad][NW]
     int16_t* adjseq;           // [P][Kpad][SEQCAP] slot-ordered neighbours of small-table nodes
-    int16_t* deg;              // [P][Kpad]
     uint32_t* stack;           // [P][Kpad + 1][3 * SW]
     int prune;
+    int adj_in_smem;           // adjacency rows staged in shared memory (row stride g.RS words)
     long long node_limit;
     // outputs
     uint8_t* mask;             // [P][Kpad]
@@ -176,40 +309,37 @@ __device__ __forceinline__ unsigned long long fnv_mix(unsigned long long hsh, in
     return hsh;
 }
 
-// dst = a & adj[q]   (CPython set_intersection: iterate the smaller operand; on a tie iterate adj[q])
-__device__ int set_and_adj(const SetRef& dst, const SetRef& a, int q, int K, const uint32_t* adjq, int degq,
-                           const int16_t* adjseq_q, int16_t* seq, int16_t* tmp, int lane) {
-    const int n = bits_count2(a.bits(), adjq, false, a.NW, lane);
-    if (n == 0) { if (lane == 0) dst.used() = 0; __syncwarp(); return 0; }
+// dst = a & adj[q], |result| = n > 0 already known.
+// CPython set_intersection iterates the smaller operand (adj[q] on a tie) and adds the keys
+// found in the other one, so the insertion order is the slot order of that operand.
+__device__ __noinline__ void build_and_adj(const SetRef& dst, const SetRef& a, int n, int K, int NWe, const uint32_t* adjq,
+                                           int degq, const int16_t* adjseq_q, int16_t* seq, int16_t* tmp, uint32_t* own, int lane) {
     if (growth_size(n) < K) {
-        int m;
         if (degq <= a.used()) {
-            if (growth_size(degq) >= K) m = bits_to_seq(adjq, a.bits(), true, a.NW, seq, lane);
+            if (growth_size(degq) >= K) bits_to_seq(adjq, a.bits(), true, NWe, seq, lane);
             else {
                 // neighbours of q in adj[q]'s slot order, keep those in a
-                m = 0;
+                int m = 0;
                 for (int i0 = 0; i0 < degq; i0 += 32) {
                     const int i = i0 + lane;
                     const int k = i < degq ? adjseq_q[i] : -1;
                     const bool ok = k >= 0 && ((a.bits()[k >> 5] >> (k & 31)) & 1u);
-                    const unsigned bm = __ballot_sync(0xffffffffu, ok);
+                    const unsigned bm = __ballot_sync(FULL, ok);
                     if (ok) seq[m + __popc(bm & ((1u << lane) - 1))] = (int16_t)k;
                     m += __popc(bm);
                 }
             }
         } else {
-            m = set_to_seq(a, K, adjq, true, seq, lane);
+            set_to_seq(a, K, NWe, adjq, true, seq, lane);
         }
         __syncwarp();
     }
-    fresh_from(dst, a.bits(), adjq, false, n, K, seq, tmp, lane);
-    return n;
+    fresh_from(dst, a.bits(), adjq, false, n, K, NWe, seq, tmp, own, lane);
 }
 
 // dst = a - adj[u]   (CPython set_difference, both branches)
-__device__ void set_sub_adj(const SetRef& dst, const SetRef& a, int K, const uint32_t* adju, int degu, int16_t* seq,
-                            int16_t* tmp, int lane) {
-    const int NW = a.NW;
+__device__ __noinline__ void set_sub_adj(const SetRef& dst, const SetRef& a, int K, int NWe, const uint32_t* adju, int degu,
+                                         int16_t* seq, int16_t* tmp, uint32_t* own, int lane) {
     if ((a.used() >> 2) > degu) {
         // set_copy_and_difference: copy a (one up-front resize to used*2), then discard
         const int a_used = a.used(), a_fill = a.fill(), a_mask = a.mask();
@@ -220,25 +350,21 @@ __device__ void set_sub_adj(const SetRef& dst, const SetRef& a, int K, const uin
         if (explicit_tab) {
             if (newmask == a_mask && a_fill == a_used) {   // slot-for-slot copy
                 for (int i = lane; i <= newmask; i += 32) dst.tab()[i] = a.tab()[i];
-            } else {
-                m = set_to_seq(a, K, nullptr, true, seq, lane);
                 __syncwarp();
-                if (lane == 0) {
-                    int16_t* t = dst.tab();
-                    for (int i = 0; i <= newmask; ++i) t[i] = EMPTY_SLOT;
-                    for (int i = 0; i < m; ++i) tab_insert_clean(t, newmask, seq[i]);
-                }
+            } else {
+                m = set_to_seq(a, K, NWe, nullptr, true, seq, lane);
+                __syncwarp();
+                tab_reinsert(dst.tab(), newmask, seq, m, own, lane);
             }
-            __syncwarp();
         }
-        const int removed = bits_count2(a.bits(), adju, false, NW, lane);
+        const int removed = bits_count2(a.bits(), adju, false, NWe, lane);
         if (explicit_tab) {
             for (int i = lane; i <= newmask; i += 32) {
                 const int k = dst.tab()[i];
                 if (k >= 0 && ((adju[k >> 5] >> (k & 31)) & 1u)) dst.tab()[i] = DUMMY_SLOT;
             }
         }
-        for (int w = lane; w < NW; w += 32) dst.bits()[w] = a.bits()[w] & ~adju[w];
+        for (int w = lane; w < NWe; w += 32) dst.bits()[w] = a.bits()[w] & ~adju[w];
         __syncwarp();
         int fill = a_used, used = a_used - removed, mask = newmask;
         if ((fill - used) > mask / 4) {   // "more than 1/4 dummies": rebuild at used*4
@@ -246,21 +372,11 @@ __device__ void set_sub_adj(const SetRef& dst, const SetRef& a, int K, const uin
             if (explicit_tab) {
                 m = tab_to_seq(dst.tab(), mask + 1, nullptr, true, seq, lane);
                 __syncwarp();
-                if (ns < K) {
-                    if (lane == 0) {
-                        int16_t* t = dst.tab();
-                        for (int i = 0; i < ns; ++i) t[i] = EMPTY_SLOT;
-                        for (int i = 0; i < m; ++i) tab_insert_clean(t, ns - 1, seq[i]);
-                    }
-                }
+                if (ns < K) tab_reinsert(dst.tab(), ns - 1, seq, m, own, lane);
             } else if (ns < K) {
-                m = bits_to_seq(dst.bits(), nullptr, true, NW, seq, lane);
+                m = bits_to_seq(dst.bits(), nullptr, true, NWe, seq, lane);
                 __syncwarp();
-                if (lane == 0) {
-                    int16_t* t = dst.tab();
-                    for (int i = 0; i < ns; ++i) t[i] = EMPTY_SLOT;
-                    for (int i = 0; i < m; ++i) tab_insert_clean(t, ns - 1, seq[i]);
-                }
+                tab_reinsert(dst.tab(), ns - 1, seq, m, own, lane);
             }
             mask = ns - 1; fill = used;
         }
@@ -268,29 +384,28 @@ __device__ void set_sub_adj(const SetRef& dst, const SetRef& a, int K, const uin
         __syncwarp();
         return;
     }
-    const int n = bits_count2(a.bits(), adju, true, NW, lane);
-    if (n > 0 && growth_size(n) < K) { set_to_seq(a, K, adju, false, seq, lane); __syncwarp(); }
-    fresh_from(dst, a.bits(), adju, true, n, K, seq, tmp, lane);
+    const int n = bits_count2(a.bits(), adju, true, NWe, lane);
+    if (n > 0 && growth_size(n) < K) { set_to_seq(a, K, NWe, adju, false, seq, lane); __syncwarp(); }
+    fresh_from(dst, a.bits(), adju, true, n, K, NWe, seq, tmp, own, lane);
 }
 
 // ext.pop(): first live slot at or after finger (wrapping)
-__device__ int set_pop(const SetRef& s, int K, int lane) {
+__device__ __noinline__ int set_pop(const SetRef& s, int K, int NWe, int lane) {
     const int mask = s.mask(), size = mask + 1;
     const int start = s.finger() & mask;
     int found = -1, slot = -1;
     if (size >= K) {
         // identity layout: slot == key.  next set bit >= start, else lowest set bit
-        const int NW = s.NW;
         for (int pass = 0; pass < 2 && found < 0; ++pass) {
             const int from = pass == 0 ? start : 0;
-            for (int w0 = (from >> 5); w0 < NW && found < 0; w0 += 32) {
+            for (int w0 = (from >> 5); w0 < NWe && found < 0; w0 += 32) {
                 const int w = w0 + lane;
-                uint32_t v = w < NW ? s.bits()[w] : 0u;
+                uint32_t v = w < NWe ? s.bits()[w] : 0u;
                 if (w == (from >> 5)) v &= ~0u << (from & 31);
-                const unsigned bm = __ballot_sync(0xffffffffu, v != 0u);
+                const unsigned bm = __ballot_sync(FULL, v != 0u);
                 if (bm) {
                     const int src = __ffs(bm) - 1;
-                    const uint32_t vv = __shfl_sync(0xffffffffu, v, src);
+                    const uint32_t vv = __shfl_sync(FULL, v, src);
                     found = (w0 + src) * 32 + (__ffs(vv) - 1);
                 }
             }
@@ -303,10 +418,10 @@ __device__ int set_pop(const SetRef& s, int K, int lane) {
             for (int i0 = from & ~31; i0 < size && found < 0; i0 += 32) {
                 const int i = i0 + lane;
                 const int k = (i < size && i >= from) ? t[i] : -1;
-                const unsigned bm = __ballot_sync(0xffffffffu, k >= 0);
+                const unsigned bm = __ballot_sync(FULL, k >= 0);
                 if (bm) {
                     const int src = __ffs(bm) - 1;
-                    found = __shfl_sync(0xffffffffu, k, src);
+                    found = __shfl_sync(FULL, k, src);
                     slot = i0 + src;
                 }
             }
@@ -323,7 +438,7 @@ __device__ int set_pop(const SetRef& s, int K, int lane) {
 }
 
 // cand.remove(q)
-__device__ void set_remove(const SetRef& s, int K, int q, int lane) {
+__device__ __forceinline__ void set_remove(const SetRef& s, int K, int q, int lane) {
     const int size = s.mask() + 1;
     if (size < K) {
         int16_t* t = s.tab();
@@ -333,8 +448,14 @@ __device__ void set_remove(const SetRef& s, int K, int q, int lane) {
     __syncwarp();
 }
 
-__device__ void set_copy_words(uint32_t* dst, const uint32_t* src, int words, int lane) {
-    for (int i = lane; i < words; i += 32) dst[i] = src[i];
+// words of a set that carry state: bitset + header (+ table when it is explicit)
+__device__ __forceinline__ int set_live_words(const SetRef& s, int K) {
+    const int size = s.mask() + 1;
+    return s.NW + 4 + (size < K ? (size >> 1) : 0);
+}
+__device__ __forceinline__ void set_copy(uint32_t* dst, const SetRef& s, int K, int lane) {
+    const int n = set_live_words(s, K);
+    for (int i = lane; i < n; i += 32) dst[i] = s.w[i];
 }
 
 __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
@@ -345,15 +466,20 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     const CliqueGeom g = a.g;
     const int K = a.counts[p];
     const int NW = g.NW, SW = g.SW;
-    // shared layout: subg | cand | ext | ch_subg | ch_cand | seq[Kpad] | tmp[Kpad] | Q[Kpad] | bestQ[Kpad]
+    const int NWe = (K + 31) >> 5;       // words that can hold a set bit
+    // shared layout: subg | cand | ext | ch_subg | ch_cand | seq[Kpad] | tmp[Kpad] | Q[Kpad] | bestQ[Kpad] | deg[Kpad] | adj rows
     SetRef subg{sm, NW}, cand{sm + SW, NW}, ext{sm + 2 * SW, NW}, chs{sm + 3 * SW, NW}, chc{sm + 4 * SW, NW};
     int16_t* seq = (int16_t*)(sm + 5 * SW);
     int16_t* tmp = seq + g.Kpad;
     int16_t* Q = tmp + g.Kpad;
     int16_t* bestQ = Q + g.Kpad;
-    const uint32_t* adjbits = a.adjbits + (size_t)p * g.Kpad * NW;
+    int16_t* deg = bestQ + g.Kpad;
+    uint32_t* own = (uint32_t*)(deg + g.Kpad);     // [128] slot arbitration scratch of par_insert_multi
+    uint32_t* adj_sm = own + 128;
+    const uint32_t* adj_gl = a.adjbits + (size_t)p * g.Kpad * NW;
+    const uint32_t* adjbits = a.adj_in_smem ? adj_sm : adj_gl;
+    const int RS = a.adj_in_smem ? g.RS : NW;       // row stride in words
     int16_t* adjseq = a.adjseq + (size_t)p * g.Kpad * g.SEQCAP;
-    int16_t* deg = a.deg + (size_t)p * g.Kpad;
     uint32_t* stack = a.stack + (size_t)p * (g.Kpad + 1) * 3 * SW;
     uint8_t* outmask = a.mask + (size_t)p * g.Kpad;
 
@@ -362,20 +488,33 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         if (lane == 0) { a.n_inliers[p] = 0; a.nodes[p] = 0; a.status[p] = RF_OK; if (a.n_yields) a.n_yields[p] = 0; if (a.order_hash) a.order_hash[p] = 14695981039346656037ULL; }
         return;
     }
-    // ---- degrees and slot orders of small-table adjacency sets ------------------------
-    for (int u = 0; u < K; ++u) {
-        const uint32_t* row = adjbits + (size_t)u * NW;
+    if (a.adj_in_smem) {
+        for (int t = lane; t < K * NWe; t += 32) {
+            const int r = t / NWe, w = t - r * NWe;
+            adj_sm[r * RS + w] = adj_gl[(size_t)r * NW + w];
+        }
+        __syncwarp();
+    }
+    // ---- degrees (one lane per node) and slot orders of small-table adjacency sets -------
+    for (int u0 = 0; u0 < K; u0 += 32) {
+        const int u = u0 + lane;
         int c = 0;
-        for (int w = lane; w < NW; w += 32) c += __popc(row[w]);
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) deg[u] = (int16_t)c;
-        if (c > 0 && growth_size(c) < K) {
-            // adj[u] = {v for v in G[u] if v != u}: ascending adds into a small table
-            const int m = bits_to_seq(row, nullptr, true, NW, seq, lane);
+        if (u < K) {
+            const uint32_t* row = adjbits + (size_t)u * RS;
+            for (int w = 0; w < NWe; ++w) c += __popc(row[w]);
+            deg[u] = (int16_t)c;
+        }
+        unsigned need = __ballot_sync(FULL, u < K && c > 0 && growth_size(c) < K);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int v = u0 + src;
+            const int cv = __shfl_sync(FULL, c, src);
+            // adj[v] = {x for x in G[v] if x != v}: ascending adds into a small table
+            const int m = bits_to_seq(adjbits + (size_t)v * RS, nullptr, true, NWe, seq, lane);
             __syncwarp();
-            if (lane == 0) tab_build_by_adds(chs.tab(), seq, m, tmp);
-            __syncwarp();
-            tab_to_seq(chs.tab(), growth_size(c), nullptr, true, adjseq + (size_t)u * g.SEQCAP, lane);
+            tab_build_by_adds(chs.tab(), seq, m, tmp, own, lane);
+            tab_to_seq(chs.tab(), growth_size(cv), nullptr, true, adjseq + (size_t)v * g.SEQCAP, lane);
             __syncwarp();
         }
     }
@@ -397,26 +536,58 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     unsigned long long hsh = 14695981039346656037ULL;
     int status = RF_OK;
 
+    // Clique shortcut (production mode only; the order-hash test hook enumerates every level).
+    // If cand is itself a clique, the subtree below this node yields at most ONE maximal clique,
+    // Q + cand — and only if no excluded vertex (subg \ cand) is adjacent to all of cand — and
+    // has no effect on the parent's sets, so its |cand| levels need not be walked: the order of
+    // all yields, and therefore "the first strictly larger clique", is unchanged.
+    const bool shortcut = a.order_hash == nullptr;
     auto choose_pivot_and_ext = [&]() {
-        // u = max(subg, key=lambda u: len(cand & adj[u])) — first maximum in subg's iteration order
-        const int m = set_to_seq(subg, K, nullptr, true, seq, lane);
-        __syncwarp();
+        // u = max(subg, key=lambda u: len(cand & adj[u])) — first maximum in subg's iteration order.
+        // Iteration order = slot order; a lane scores the key of "its" slots, ties go to the lowest slot.
+        const int size = subg.mask() + 1;
+        const bool ident = size >= K;          // identity layout: slot == key
+        const int nslots = ident ? K : size;
+        const int ncand = cand.used();
         unsigned bestkey = 0;
-        for (int i0 = 0; i0 < m; i0 += 32) {
-            const int i = i0 + lane;
-            unsigned key = 0;
-            if (i < m) {
-                const uint32_t* row = adjbits + (size_t)seq[i] * NW;
+        int min_in = 0x7fffffff, max_out = -1;
+        for (int i = lane; i < nslots; i += 32) {
+            int u;
+            if (ident) u = ((subg.bits()[i >> 5] >> (i & 31)) & 1u) ? i : -1;
+            else u = subg.tab()[i];
+            if (u >= 0) {
+                const uint32_t* row = adjbits + (size_t)u * RS;
                 int c = 0;
-                for (int w = 0; w < NW; ++w) c += __popc(cand.bits()[w] & row[w]);
-                key = ((unsigned)c << 16) | (unsigned)(0xFFFF - i);
+                for (int w = 0; w < NWe; ++w) c += __popc(cand.bits()[w] & row[w]);
+                bestkey = max(bestkey, ((unsigned)c << 16) | (unsigned)(0xFFFF - i));
+                if ((cand.bits()[u >> 5] >> (u & 31)) & 1u) min_in = min(min_in, c);
+                else max_out = max(max_out, c);
             }
-            bestkey = max(bestkey, key);
         }
-        bestkey = __reduce_max_sync(0xffffffffu, bestkey);
-        const int u = seq[0xFFFF - (bestkey & 0xFFFF)];
-        __syncwarp();
-        set_sub_adj(ext, cand, K, adjbits + (size_t)u * NW, deg[u], seq, tmp, lane);
+        bestkey = __reduce_max_sync(FULL, bestkey);
+        if (shortcut) {
+            min_in = __reduce_min_sync(FULL, min_in);
+            if (min_in == ncand - 1) {                       // every candidate is adjacent to all the others
+                max_out = __reduce_max_sync(FULL, max_out);
+                if (max_out < ncand) {                       // maximal: one yield of size (qn - 1) + ncand
+                    ++ny;
+                    const int csize = qn - 1 + ncand;
+                    if (csize > best) {                      // outlierRejection.py:73 strict '>'
+                        best = csize;
+                        for (int i = lane; i < qn - 1; i += 32) bestQ[i] = Q[i];
+                        __syncwarp();
+                        bits_to_seq(cand.bits(), nullptr, true, NWe, bestQ + (qn - 1), lane);
+                        __syncwarp();
+                    }
+                }
+                if (lane == 0) ext.used() = 0;               // nothing left to expand at this node
+                __syncwarp();
+                return;
+            }
+        }
+        const int slot = 0xFFFF - (int)(bestkey & 0xFFFF);
+        const int u = ident ? slot : subg.tab()[slot];
+        set_sub_adj(ext, cand, K, NWe, adjbits + (size_t)u * RS, deg[u], seq, tmp, own, lane);
     };
     choose_pivot_and_ext();
 
@@ -424,13 +595,11 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         if (ext.used() > 0) {
             if (pops >= a.node_limit) { status = RF_E_WORKLIMIT; break; }
             ++pops;
-            const int q = set_pop(ext, K, lane);
+            const int q = set_pop(ext, K, NWe, lane);
             set_remove(cand, K, q, lane);
             if (lane == 0) Q[qn - 1] = (int16_t)q;
-            const uint32_t* adjq = adjbits + (size_t)q * NW;
-            const int degq = deg[q];
-            const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
-            const int nsub = set_and_adj(chs, subg, q, K, adjq, degq, adjseq_q, seq, tmp, lane);
+            const uint32_t* adjq = adjbits + (size_t)q * RS;
+            const int nsub = bits_count2(subg.bits(), adjq, false, NWe, lane);
             if (nsub == 0) {
                 ++ny;
                 __syncwarp();
@@ -441,18 +610,23 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     __syncwarp();
                 }
             } else {
-                const int ncand = bits_count2(cand.bits(), adjq, false, NW, lane);
+                const int ncand = bits_count2(cand.bits(), adjq, false, NWe, lane);
+                // a child is descended only if it can still beat the best clique so far; the parent's
+                // sets do not depend on that decision, so the order of later yields is unchanged
                 if (ncand > 0 && !(a.prune && qn + ncand <= best)) {
-                    set_and_adj(chc, cand, q, K, adjq, degq, adjseq_q, seq, tmp, lane);
-                    // push parent frame
+                    const int degq = deg[q];
+                    const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
+                    build_and_adj(chs, subg, nsub, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
+                    build_and_adj(chc, cand, ncand, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
+                    // push parent frame (live words only)
                     uint32_t* fr = stack + (size_t)sp * 3 * SW;
-                    set_copy_words(fr, sm, 3 * SW, lane);
+                    set_copy(fr, subg, K, lane); set_copy(fr + SW, cand, K, lane); set_copy(fr + 2 * SW, ext, K, lane);
                     ++sp;
                     __syncwarp();
                     if (lane == 0) Q[qn] = -1;
                     ++qn;
-                    set_copy_words(subg.w, chs.w, SW, lane);
-                    set_copy_words(cand.w, chc.w, SW, lane);
+                    set_copy(subg.w, chs, K, lane);
+                    set_copy(cand.w, chc, K, lane);
                     __syncwarp();
                     choose_pivot_and_ext();
                 }
@@ -461,9 +635,11 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
             --qn;
             if (sp == 0) break;
             --sp;
-            const uint32_t* fr = stack + (size_t)sp * 3 * SW;
+            uint32_t* fr = stack + (size_t)sp * 3 * SW;
             __syncwarp();
-            set_copy_words(sm, fr, 3 * SW, lane);
+            // header first (it says how many words are live), then the rest
+            SetRef f0{fr, NW}, f1{fr + SW, NW}, f2{fr + 2 * SW, NW};
+            set_copy(subg.w, f0, K, lane); set_copy(cand.w, f1, K, lane); set_copy(ext.w, f2, K, lane);
             __syncwarp();
         }
     }
@@ -534,7 +710,7 @@ k_bytes_to_bits(const uint8_t* __restrict__ adj, int K, int Kpad, int NW, uint32
 struct CliqueWorkspace {
     CliqueGeom g;
     int P;
-    uint32_t* adjbits; int16_t* adjseq; int16_t* deg; uint32_t* stack;
+    uint32_t* adjbits; int16_t* adjseq; uint32_t* stack;
     uint8_t* mask; int32_t *n_inliers, *nodes, *status; long long* n_yields; unsigned long long* hash;
 };
 
@@ -544,12 +720,13 @@ static CliqueGeom make_geom(int Kmax) {
     g.Kpad = kp; g.NW = kp / 32; g.TABN = kp / 2; g.SW = g.NW + 4 + g.TABN / 2;
     g.SEQCAP = kp <= 512 ? 76 : (kp <= 2048 ? 306 : 1228);
     if (g.SEQCAP > kp) g.SEQCAP = kp;
+    g.RS = g.NW | 1;
     return g;
 }
 
 size_t rf_clique_workspace_bytes(int Kmax, int P) {
     CliqueGeom g = make_geom(Kmax);
-    size_t per = (size_t)g.Kpad * g.NW * 4 + (size_t)g.Kpad * g.SEQCAP * 2 + (size_t)g.Kpad * 2 +
+    size_t per = (size_t)g.Kpad * g.NW * 4 + (size_t)g.Kpad * g.SEQCAP * 2 +
                  (size_t)(g.Kpad + 1) * 3 * g.SW * 4 + (size_t)g.Kpad + 64;
     return per * P + 4096;
 }
@@ -563,7 +740,6 @@ static CliqueWorkspace carve(void* base, int Kmax, int P) {
     ws.stack = (uint32_t*)take((size_t)P * (g.Kpad + 1) * 3 * g.SW * 4);
     ws.adjbits = (uint32_t*)take((size_t)P * g.Kpad * g.NW * 4);
     ws.adjseq = (int16_t*)take((size_t)P * g.Kpad * g.SEQCAP * 2);
-    ws.deg = (int16_t*)take((size_t)P * g.Kpad * 2);
     ws.mask = (uint8_t*)take((size_t)P * g.Kpad);
     ws.n_inliers = (int32_t*)take((size_t)P * 4);
     ws.nodes = (int32_t*)take((size_t)P * 4);
@@ -577,16 +753,19 @@ size_t rf_clique_ws_total(int Kmax, int P) {
     CliqueGeom g = make_geom(Kmax);
     auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
     return r((size_t)P * (g.Kpad + 1) * 3 * g.SW * 4) + r((size_t)P * g.Kpad * g.NW * 4) + r((size_t)P * g.Kpad * g.SEQCAP * 2) +
-           r((size_t)P * g.Kpad * 2) + r((size_t)P * g.Kpad) + 3 * r((size_t)P * 4) + 2 * r((size_t)P * 8);
+           r((size_t)P * g.Kpad) + 3 * r((size_t)P * 4) + 2 * r((size_t)P * 8);
 }
 
 static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t* d_counts, int prune, bool debug) {
     CliqueArgs a;
     a.g = ws.g; a.P = ws.P; a.counts = d_counts; a.Kmax = ws.g.Kpad; a.adjbits = ws.adjbits; a.adjseq = ws.adjseq;
-    a.deg = ws.deg; a.stack = ws.stack; a.prune = prune; a.node_limit = h->cfg.clique_node_limit;
+    a.stack = ws.stack; a.prune = prune; a.node_limit = h->cfg.clique_node_limit;
     a.mask = ws.mask; a.n_inliers = ws.n_inliers; a.nodes = ws.nodes; a.status = ws.status;
     a.n_yields = debug ? ws.n_yields : nullptr; a.order_hash = debug ? ws.hash : nullptr;
-    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)4 * ws.g.Kpad * 2;
+    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + 128 * 4;
+    const size_t adj_bytes = (size_t)ws.g.Kpad * ws.g.RS * 4;
+    a.adj_in_smem = smem + adj_bytes <= 96 * 1024;      // K <= 512: rows live next to the search frame
+    if (a.adj_in_smem) smem += adj_bytes;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_clique, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return rf_fail(h, RF_E_CUDA, "clique smem %zu: %s", smem, cudaGetErrorString(e));
@@ -686,7 +865,7 @@ int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, int32_t
     RF_CUDA(h, cudaMemcpyAsync(dc, &K, 4, cudaMemcpyHostToDevice, h->stream));
     k_bytes_to_bits<<<64, 256, 0, h->stream>>>(dadj, K, ws.g.Kpad, ws.g.NW, ws.adjbits);
     RF_CHECK_LAUNCH(h);
-    rc = launch_clique(h, ws, dc, prune, true);
+    rc = launch_clique(h, ws, dc, prune & 1, !(prune & 2));
     if (rc) return rc;
     std::vector<uint8_t> m(K);
     int32_t o[3]; long long ny; unsigned long long hs;
@@ -694,8 +873,11 @@ int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, int32_t
     RF_CUDA(h, cudaMemcpyAsync(&o[0], ws.n_inliers, 4, cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaMemcpyAsync(&o[1], ws.nodes, 4, cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaMemcpyAsync(&o[2], ws.status, 4, cudaMemcpyDeviceToHost, h->stream));
-    RF_CUDA(h, cudaMemcpyAsync(&ny, ws.n_yields, 8, cudaMemcpyDeviceToHost, h->stream));
-    RF_CUDA(h, cudaMemcpyAsync(&hs, ws.hash, 8, cudaMemcpyDeviceToHost, h->stream));
+    ny = 0; hs = 0;
+    if (!(prune & 2)) {
+        RF_CUDA(h, cudaMemcpyAsync(&ny, ws.n_yields, 8, cudaMemcpyDeviceToHost, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(&hs, ws.hash, 8, cudaMemcpyDeviceToHost, h->stream));
+    }
     RF_CUDA(h, cudaStreamSynchronize(h->stream));
     if (clique_mask_out) for (int i = 0; i < K; ++i) clique_mask_out[i] = m[i];
     if (size) *size = o[0];

@@ -45,6 +45,29 @@ def test_clique_enumeration_order_matches_oracle(fe):
         mask_p, size_p, _, _, nodes_p = fe.clique_search(adj, prune=True)
         assert np.array_equal(mask_p, ref_mask), f"K={K} p={p}: pruned search picked another clique"
         assert nodes_p <= nodes
+        mask_s, size_s, _, _, nodes_s = fe.clique_search(adj, prune=3)      # production mode: clique shortcut on
+        assert np.array_equal(mask_s, ref_mask), f"K={K} p={p}: shortcut search picked another clique"
+        assert nodes_s <= nodes_p
+
+
+def test_clique_production_mode_dense_graphs(fe):
+    """Inlier-dominated graphs (one big clique + noise), the regime of the synthetic sequences.
+    Reference = the oracle's order-safe pruned search (full enumeration is exponential here)."""
+    from oracle import restate as R
+    rng = np.random.default_rng(17)
+    for K, n_in, p_noise, p_in in [(120, 100, .1, 1.0), (140, 90, .3, 1.0), (200, 150, .2, 1.0), (260, 200, .05, 1.0),
+                                   (64, 60, .5, 1.0), (130, 40, .4, 1.0), (120, 100, .3, .995)]:
+        M = rng.random((K, K)) < p_noise
+        M[:n_in, :n_in] |= rng.random((n_in, n_in)) < p_in
+        M = np.triu(M, 1); M = M | M.T
+        perm = rng.permutation(K)
+        M = M[np.ix_(perm, perm)]
+        np.fill_diagonal(M, True)
+        adj = M.astype(np.uint8)
+        clique, _ = R.first_max_clique_pruned(adj)
+        ref_mask = np.zeros(K, bool); ref_mask[clique] = True
+        mask_s, size_s, _, _, _ = fe.clique_search(adj, prune=3)
+        assert size_s == len(clique) and np.array_equal(mask_s, ref_mask), f"K={K}"
 
 
 def test_reject_outliers_reference_fixture(fe, golden):
