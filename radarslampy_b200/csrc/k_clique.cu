@@ -291,7 +291,7 @@ struct CliqueArgs {
     int Kmax;                  // row capacity of the per-problem arrays (== g.Kpad)
     const uint32_t* adjbits;   // [P][Kpad][NW]
     int16_t* adjseq;           // [P][Kpad][SEQCAP] slot-ordered neighbours of small-table nodes
-    uint32_t* stack;           // [P][Kpad + 1][3 * SW]
+    uint32_t* stack;           // [P][Kpad + 1][3 * SW + 1]  (subg | cand | ext | qn)
     int prune;
     int adj_in_smem;           // adjacency rows staged in shared memory (row stride g.RS words)
     long long node_limit;
@@ -474,13 +474,14 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     int16_t* Q = tmp + g.Kpad;
     int16_t* bestQ = Q + g.Kpad;
     int16_t* deg = bestQ + g.Kpad;
-    uint32_t* own = (uint32_t*)(deg + g.Kpad);     // [128] slot arbitration scratch of par_insert_multi
-    uint32_t* adj_sm = own + 128;
+    uint32_t* own = (uint32_t*)(deg + g.Kpad);     // [max(128, 2 NW)] slot arbitration / bitset scratch
+    uint32_t* adj_sm = own + (2 * NW > 128 ? 2 * NW : 128);
     const uint32_t* adj_gl = a.adjbits + (size_t)p * g.Kpad * NW;
     const uint32_t* adjbits = a.adj_in_smem ? adj_sm : adj_gl;
     const int RS = a.adj_in_smem ? g.RS : NW;       // row stride in words
     int16_t* adjseq = a.adjseq + (size_t)p * g.Kpad * g.SEQCAP;
-    uint32_t* stack = a.stack + (size_t)p * (g.Kpad + 1) * 3 * SW;
+    const int FS = 3 * SW + 1;           // search frame: three sets + the depth of Q
+    uint32_t* stack = a.stack + (size_t)p * (g.Kpad + 1) * FS;
     uint8_t* outmask = a.mask + (size_t)p * g.Kpad;
 
     for (int i = lane; i < g.Kpad; i += 32) outmask[i] = 0;
@@ -531,65 +532,151 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         subg.mask() = size - 1; subg.fill() = K; subg.used() = K; subg.finger() = 0;
     }
     __syncwarp();
-    int qn = 1, sp = 0, best = 0;
+    int qn = 1, sp = 0, best = 0, nbest = 0;    // nbest: members currently recorded in bestQ
     long long pops = 0, ny = 0;
     unsigned long long hsh = 14695981039346656037ULL;
     int status = RF_OK;
+    // Production mode (no order hash requested) adds three ORDER-SAFE accelerations; the test hook
+    // with the hash walks every level exactly like networkx does.
+    const bool fast = a.order_hash == nullptr;
 
-    // Clique shortcut (production mode only; the order-hash test hook enumerates every level).
-    // If cand is itself a clique, the subtree below this node yields at most ONE maximal clique,
-    // Q + cand — and only if no excluded vertex (subg \ cand) is adjacent to all of cand — and
-    // has no effect on the parent's sets, so its |cand| levels need not be walked: the order of
-    // all yields, and therefore "the first strictly larger clique", is unchanged.
-    const bool shortcut = a.order_hash == nullptr;
-    auto choose_pivot_and_ext = [&]() {
-        // u = max(subg, key=lambda u: len(cand & adj[u])) — first maximum in subg's iteration order.
-        // Iteration order = slot order; a lane scores the key of "its" slots, ties go to the lowest slot.
-        const int size = subg.mask() + 1;
-        const bool ident = size >= K;          // identity layout: slot == key
-        const int nslots = ident ? K : size;
-        const int ncand = cand.used();
-        unsigned bestkey = 0;
-        int min_in = 0x7fffffff, max_out = -1;
-        for (int i = lane; i < nslots; i += 32) {
-            int u;
-            if (ident) u = ((subg.bits()[i >> 5] >> (i & 31)) & 1u) ? i : -1;
-            else u = subg.tab()[i];
-            if (u >= 0) {
-                const uint32_t* row = adjbits + (size_t)u * RS;
-                int c = 0;
-                for (int w = 0; w < NWe; ++w) c += __popc(cand.bits()[w] & row[w]);
-                bestkey = max(bestkey, ((unsigned)c << 16) | (unsigned)(0xFFFF - i));
-                if ((cand.bits()[u >> 5] >> (u & 31)) & 1u) min_in = min(min_in, c);
-                else max_out = max(max_out, c);
-            }
+    // (1) Lower bound on the answer: a clique found by min-degree peeling has size L <= M (the
+    // maximum), and the reference's answer is the first clique of size M.  Starting the
+    // "strictly larger" test at L - 1 only discards cliques smaller than L, none of which can be
+    // the answer, so children that cannot reach L are skipped from the very first level.
+    if (fast && a.prune && K > 1) {
+        uint32_t* S = own;                         // NWe words (scratch is free until the first table build)
+        int16_t* dS = tmp;                         // degree within S
+        for (int w = lane; w < NWe; w += 32) S[w] = cand.bits()[w];
+        for (int v = lane; v < K; v += 32) dS[v] = deg[v];
+        __syncwarp();
+        int ns = K;
+        for (;;) {
+            unsigned mk = 0xFFFFFFFFu;
+            for (int v = lane; v < K; v += 32)
+                if ((S[v >> 5] >> (v & 31)) & 1u) mk = min(mk, ((unsigned)dS[v] << 16) | (unsigned)v);
+            mk = __reduce_min_sync(FULL, mk);
+            if ((int)(mk >> 16) >= ns - 1) break;  // every member is adjacent to all the others
+            const int r = (int)(mk & 0xFFFF);
+            __syncwarp();
+            if (lane == 0) S[r >> 5] &= ~(1u << (r & 31));
+            --ns;
+            const uint32_t* rowr = adjbits + (size_t)r * RS;
+            for (int v = lane; v < K; v += 32)
+                if ((rowr[v >> 5] >> (v & 31)) & 1u) dS[v] -= 1;
+            __syncwarp();
         }
-        bestkey = __reduce_max_sync(FULL, bestkey);
-        if (shortcut) {
-            min_in = __reduce_min_sync(FULL, min_in);
-            if (min_in == ncand - 1) {                       // every candidate is adjacent to all the others
+        best = ns - 1;
+    }
+
+    auto enter_node = [&]() {
+        for (;;) {
+            // u = max(subg, key=lambda u: len(cand & adj[u])) — first maximum in subg's iteration order.
+            // Iteration order = slot order; a lane scores the key of "its" slots, ties go to the lowest slot.
+            const int size = subg.mask() + 1;
+            const bool ident = size >= K;          // identity layout: slot == key
+            const int nslots = ident ? K : size;
+            const int ncand = cand.used();
+            unsigned bestkey = 0;
+            int n_univ = 0, max_out = -1;
+            uint32_t* D = own;                     // universal candidates (ident layout only): NWe words
+            for (int i0 = 0; i0 < nslots; i0 += 32) {
+                const int i = i0 + lane;
+                int u = -1;
+                if (i < nslots) {
+                    if (ident) u = ((subg.bits()[i >> 5] >> (i & 31)) & 1u) ? i : -1;
+                    else u = subg.tab()[i];
+                }
+                bool univ = false;
+                if (u >= 0) {
+                    const uint32_t* row = adjbits + (size_t)u * RS;
+                    int c = 0;
+                    for (int w = 0; w < NWe; ++w) c += __popc(cand.bits()[w] & row[w]);
+                    bestkey = max(bestkey, ((unsigned)c << 16) | (unsigned)(0xFFFF - i));
+                    if ((cand.bits()[u >> 5] >> (u & 31)) & 1u) univ = c == ncand - 1;
+                    else max_out = max(max_out, c);
+                }
+                if (fast) {
+                    const unsigned bm = __ballot_sync(FULL, univ);
+                    n_univ += __popc(bm);
+                    if (ident && lane == 0) D[i0 >> 5] = bm;
+                }
+            }
+            bestkey = __reduce_max_sync(FULL, bestkey);
+            if (fast) {
                 max_out = __reduce_max_sync(FULL, max_out);
-                if (max_out < ncand) {                       // maximal: one yield of size (qn - 1) + ncand
-                    ++ny;
-                    const int csize = qn - 1 + ncand;
-                    if (csize > best) {                      // outlierRejection.py:73 strict '>'
-                        best = csize;
-                        for (int i = lane; i < qn - 1; i += 32) bestQ[i] = Q[i];
+                __syncwarp();
+                // (2) cand is a clique: the subtree yields at most ONE maximal clique, Q + cand — and only
+                // if no excluded vertex (subg \ cand) is adjacent to all of cand — and leaves the parent's
+                // sets untouched, so its |cand| levels need not be walked.
+                if (n_univ == ncand) {
+                    if (max_out < ncand) {
+                        ++ny;
+                        const int csize = qn - 1 + ncand;
+                        if (csize > best) {                      // outlierRejection.py:73 strict '>'
+                            best = csize; nbest = csize;
+                            for (int i = lane; i < qn - 1; i += 32) bestQ[i] = Q[i];
+                            __syncwarp();
+                            bits_to_seq(cand.bits(), nullptr, true, NWe, bestQ + (qn - 1), lane);
+                            __syncwarp();
+                        }
+                    }
+                    if (lane == 0) ext.used() = 0;               // nothing left to expand at this node
+                    __syncwarp();
+                    return;
+                }
+                // (3) chain of universal candidates.  Let D = candidates adjacent to every other candidate.
+                // If no excluded vertex reaches that score, the pivot is a member of D, ext = {pivot}, the
+                // only child is (Q + pivot, subg & N(pivot), cand - pivot), and there D - pivot is again the
+                // set of universal candidates: |D| levels without any branching or yield.  While the sets
+                // stay in identity layout (table >= node count) their state after the chain is independent
+                // of the order in which D was consumed, so the chain is taken in one step.
+                if (ident && n_univ > 0 && max_out < ncand - 1) {
+                    if (a.prune && qn - 1 + ncand <= best) {     // the single child cannot beat the best
+                        if (lane == 0) ext.used() = 0;
                         __syncwarp();
-                        bits_to_seq(cand.bits(), nullptr, true, NWe, bestQ + (qn - 1), lane);
+                        return;
+                    }
+                    const int nc2 = ncand - n_univ;
+                    // subg'' = members of subg adjacent to all of D
+                    uint32_t* S2 = own + NW;
+                    int ns2 = 0;
+                    for (int i0 = 0; i0 < K; i0 += 32) {
+                        const int v = i0 + lane;
+                        bool keep = false;
+                        if (v < K && ((subg.bits()[v >> 5] >> (v & 31)) & 1u)) {
+                            const uint32_t* row = adjbits + (size_t)v * RS;
+                            int c = 0;
+                            for (int w = 0; w < NWe; ++w) c += __popc(D[w] & row[w]);
+                            keep = c == n_univ;
+                        }
+                        const unsigned bm = __ballot_sync(FULL, keep);
+                        ns2 += __popc(bm);
+                        if (lane == 0) S2[i0 >> 5] = bm;
+                    }
+                    __syncwarp();
+                    if (growth_size(nc2) >= K && growth_size(ns2) >= K) {
+                        bits_to_seq(D, nullptr, true, NWe, Q + (qn - 1), lane);
+                        qn += n_univ;
+                        pops += n_univ;
+                        for (int w = lane; w < NWe; w += 32) { cand.bits()[w] &= ~D[w]; subg.bits()[w] = S2[w]; }
+                        if (lane == 0) {
+                            Q[qn - 1] = -1;
+                            cand.mask() = growth_size(nc2) - 1; cand.fill() = nc2; cand.used() = nc2; cand.finger() = 0;
+                            subg.mask() = growth_size(ns2) - 1; subg.fill() = ns2; subg.used() = ns2; subg.finger() = 0;
+                        }
                         __syncwarp();
+                        continue;
                     }
                 }
-                if (lane == 0) ext.used() = 0;               // nothing left to expand at this node
-                __syncwarp();
-                return;
             }
+            const int slot = 0xFFFF - (int)(bestkey & 0xFFFF);
+            const int u = ident ? slot : subg.tab()[slot];
+            set_sub_adj(ext, cand, K, NWe, adjbits + (size_t)u * RS, deg[u], seq, tmp, own, lane);
+            return;
         }
-        const int slot = 0xFFFF - (int)(bestkey & 0xFFFF);
-        const int u = ident ? slot : subg.tab()[slot];
-        set_sub_adj(ext, cand, K, NWe, adjbits + (size_t)u * RS, deg[u], seq, tmp, own, lane);
     };
-    choose_pivot_and_ext();
+    enter_node();
 
     for (;;) {
         if (ext.used() > 0) {
@@ -605,7 +692,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                 __syncwarp();
                 if (a.order_hash) { hsh = fnv_mix(hsh, qn); for (int i = 0; i < qn; ++i) hsh = fnv_mix(hsh, Q[i]); }
                 if (qn > best) {   // outlierRejection.py:73 strict '>'
-                    best = qn;
+                    best = qn; nbest = qn;
                     for (int i = lane; i < qn; i += 32) bestQ[i] = Q[i];
                     __syncwarp();
                 }
@@ -618,35 +705,35 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
                     build_and_adj(chs, subg, nsub, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
                     build_and_adj(chc, cand, ncand, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
-                    // push parent frame (live words only)
-                    uint32_t* fr = stack + (size_t)sp * 3 * SW;
+                    // push parent frame (live words only) and the depth of Q to return to
+                    uint32_t* fr = stack + (size_t)sp * FS;
                     set_copy(fr, subg, K, lane); set_copy(fr + SW, cand, K, lane); set_copy(fr + 2 * SW, ext, K, lane);
+                    if (lane == 0) { fr[3 * SW] = (uint32_t)qn; Q[qn] = -1; }
                     ++sp;
                     __syncwarp();
-                    if (lane == 0) Q[qn] = -1;
                     ++qn;
                     set_copy(subg.w, chs, K, lane);
                     set_copy(cand.w, chc, K, lane);
                     __syncwarp();
-                    choose_pivot_and_ext();
+                    enter_node();
                 }
             }
         } else {
-            --qn;
             if (sp == 0) break;
             --sp;
-            uint32_t* fr = stack + (size_t)sp * 3 * SW;
+            uint32_t* fr = stack + (size_t)sp * FS;
             __syncwarp();
             // header first (it says how many words are live), then the rest
             SetRef f0{fr, NW}, f1{fr + SW, NW}, f2{fr + 2 * SW, NW};
             set_copy(subg.w, f0, K, lane); set_copy(cand.w, f1, K, lane); set_copy(ext.w, f2, K, lane);
+            qn = (int)fr[3 * SW];
             __syncwarp();
         }
     }
     __syncwarp();
-    for (int i = lane; i < best; i += 32) outmask[bestQ[i]] = 1;
+    for (int i = lane; i < nbest; i += 32) outmask[bestQ[i]] = 1;
     if (lane == 0) {
-        a.n_inliers[p] = best;
+        a.n_inliers[p] = nbest;
         a.nodes[p] = (int32_t)(pops > 0x7fffffff ? 0x7fffffff : pops);
         a.status[p] = status;
         if (a.n_yields) a.n_yields[p] = ny;
@@ -727,7 +814,7 @@ static CliqueGeom make_geom(int Kmax) {
 size_t rf_clique_workspace_bytes(int Kmax, int P) {
     CliqueGeom g = make_geom(Kmax);
     size_t per = (size_t)g.Kpad * g.NW * 4 + (size_t)g.Kpad * g.SEQCAP * 2 +
-                 (size_t)(g.Kpad + 1) * 3 * g.SW * 4 + (size_t)g.Kpad + 64;
+                 (size_t)(g.Kpad + 1) * (3 * g.SW + 1) * 4 + (size_t)g.Kpad + 64;
     return per * P + 4096;
 }
 
@@ -737,7 +824,7 @@ static CliqueWorkspace carve(void* base, int Kmax, int P) {
     const CliqueGeom& g = ws.g;
     char* p = (char*)base;
     auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
-    ws.stack = (uint32_t*)take((size_t)P * (g.Kpad + 1) * 3 * g.SW * 4);
+    ws.stack = (uint32_t*)take((size_t)P * (g.Kpad + 1) * (3 * g.SW + 1) * 4);
     ws.adjbits = (uint32_t*)take((size_t)P * g.Kpad * g.NW * 4);
     ws.adjseq = (int16_t*)take((size_t)P * g.Kpad * g.SEQCAP * 2);
     ws.mask = (uint8_t*)take((size_t)P * g.Kpad);
@@ -752,7 +839,7 @@ static CliqueWorkspace carve(void* base, int Kmax, int P) {
 size_t rf_clique_ws_total(int Kmax, int P) {
     CliqueGeom g = make_geom(Kmax);
     auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return r((size_t)P * (g.Kpad + 1) * 3 * g.SW * 4) + r((size_t)P * g.Kpad * g.NW * 4) + r((size_t)P * g.Kpad * g.SEQCAP * 2) +
+    return r((size_t)P * (g.Kpad + 1) * (3 * g.SW + 1) * 4) + r((size_t)P * g.Kpad * g.NW * 4) + r((size_t)P * g.Kpad * g.SEQCAP * 2) +
            r((size_t)P * g.Kpad) + 3 * r((size_t)P * 4) + 2 * r((size_t)P * 8);
 }
 
@@ -762,7 +849,7 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     a.stack = ws.stack; a.prune = prune; a.node_limit = h->cfg.clique_node_limit;
     a.mask = ws.mask; a.n_inliers = ws.n_inliers; a.nodes = ws.nodes; a.status = ws.status;
     a.n_yields = debug ? ws.n_yields : nullptr; a.order_hash = debug ? ws.hash : nullptr;
-    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + 128 * 4;
+    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + (size_t)(2 * ws.g.NW > 128 ? 2 * ws.g.NW : 128) * 4;
     const size_t adj_bytes = (size_t)ws.g.Kpad * ws.g.RS * 4;
     a.adj_in_smem = smem + adj_bytes <= 96 * 1024;      // K <= 512: rows live next to the search frame
     if (a.adj_in_smem) smem += adj_bytes;
