@@ -19,6 +19,8 @@
 // memory; parents are pushed to a per-pair stack in global memory.
 // Search-tree children that cannot beat the best clique so far are skipped (order-safe: the
 // parent's state does not depend on whether a child was descended).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define EMPTY_SLOT (-1)
@@ -302,6 +304,7 @@ struct CliqueArgs {
     int32_t* status;           // [P]
     long long* n_yields;       // [P] (may be null)
     unsigned long long* order_hash;  // [P] (may be null) FNV-1a over (size, members...) of every yield
+    long long* prof;           // [P][8] cycle counters per phase (null unless RF_CLIQUE_PROFILE is set)
 };
 
 __device__ __forceinline__ unsigned long long fnv_mix(unsigned long long hsh, int v) {
@@ -458,7 +461,10 @@ __device__ __forceinline__ void set_copy(uint32_t* dst, const SetRef& s, int K, 
     for (int i = lane; i < n; i += 32) dst[i] = s.w[i];
 }
 
+#define PROF_MARK(slot) do { if (a.prof) { const long long _t = clock64(); pc[slot] += _t - tprev; tprev = _t; } } while (0)
 __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
     extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x;
     const int p = blockIdx.x;
@@ -496,6 +502,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         }
         __syncwarp();
     }
+    PROF_MARK(0);   // staging
     // ---- degrees (one lane per node) and slot orders of small-table adjacency sets -------
     for (int u0 = 0; u0 < K; u0 += 32) {
         const int u = u0 + lane;
@@ -520,6 +527,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         }
     }
     __syncwarp();
+    PROF_MARK(1);   // degrees + adjacency slot orders
     // ---- root: cand = set(G) ; subg = cand.copy() --------------------------------------
     for (int w = lane; w < NW; w += 32) {
         const int lo = w * 32;
@@ -568,6 +576,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         }
         best = ns - 1;
     }
+    PROF_MARK(2);   // greedy bound
 
     auto enter_node = [&]() {
         for (;;) {
@@ -623,6 +632,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     }
                     if (lane == 0) ext.used() = 0;               // nothing left to expand at this node
                     __syncwarp();
+                    PROF_MARK(3);
                     return;
                 }
                 // (3) chain of universal candidates.  Let D = candidates adjacent to every other candidate.
@@ -672,7 +682,9 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
             }
             const int slot = 0xFFFF - (int)(bestkey & 0xFFFF);
             const int u = ident ? slot : subg.tab()[slot];
+            PROF_MARK(3);   // pivot scoring / shortcut / chain
             set_sub_adj(ext, cand, K, NWe, adjbits + (size_t)u * RS, deg[u], seq, tmp, own, lane);
+            PROF_MARK(4);   // ext = cand - adj[u]
             return;
         }
     };
@@ -687,6 +699,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
             if (lane == 0) Q[qn - 1] = (int16_t)q;
             const uint32_t* adjq = adjbits + (size_t)q * RS;
             const int nsub = bits_count2(subg.bits(), adjq, false, NWe, lane);
+            PROF_MARK(5);   // pop + remove + count
             if (nsub == 0) {
                 ++ny;
                 __syncwarp();
@@ -705,16 +718,22 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
                     build_and_adj(chs, subg, nsub, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
                     build_and_adj(chc, cand, ncand, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
-                    // push parent frame (live words only) and the depth of Q to return to
-                    uint32_t* fr = stack + (size_t)sp * FS;
-                    set_copy(fr, subg, K, lane); set_copy(fr + SW, cand, K, lane); set_copy(fr + 2 * SW, ext, K, lane);
-                    if (lane == 0) { fr[3 * SW] = (uint32_t)qn; Q[qn] = -1; }
-                    ++sp;
+                    PROF_MARK(6);   // child sets
+                    // push the parent frame (live words only) and the depth of Q to return to — unless q was
+                    // the parent's last child: an exhausted frame would only be popped and discarded
+                    if (ext.used() > 0) {
+                        uint32_t* fr = stack + (size_t)sp * FS;
+                        set_copy(fr, subg, K, lane); set_copy(fr + SW, cand, K, lane); set_copy(fr + 2 * SW, ext, K, lane);
+                        if (lane == 0) fr[3 * SW] = (uint32_t)qn;
+                        ++sp;
+                    }
+                    if (lane == 0) Q[qn] = -1;
                     __syncwarp();
                     ++qn;
                     set_copy(subg.w, chs, K, lane);
                     set_copy(cand.w, chc, K, lane);
                     __syncwarp();
+                    PROF_MARK(7);   // frame push
                     enter_node();
                 }
             }
@@ -728,6 +747,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
             set_copy(subg.w, f0, K, lane); set_copy(cand.w, f1, K, lane); set_copy(ext.w, f2, K, lane);
             qn = (int)fr[3 * SW];
             __syncwarp();
+            PROF_MARK(7);   // frame pop
         }
     }
     __syncwarp();
@@ -738,6 +758,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         a.status[p] = status;
         if (a.n_yields) a.n_yields[p] = ny;
         if (a.order_hash) a.order_hash[p] = hsh;
+        if (a.prof) for (int k = 0; k < 8; ++k) a.prof[(size_t)p * 8 + k] = pc[k];
     }
 }
 
@@ -849,6 +870,10 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     a.stack = ws.stack; a.prune = prune; a.node_limit = h->cfg.clique_node_limit;
     a.mask = ws.mask; a.n_inliers = ws.n_inliers; a.nodes = ws.nodes; a.status = ws.status;
     a.n_yields = debug ? ws.n_yields : nullptr; a.order_hash = debug ? ws.hash : nullptr;
+    a.prof = nullptr;
+    static const bool want_prof = getenv("RF_CLIQUE_PROFILE") != nullptr;
+    long long* d_prof = nullptr;
+    if (want_prof && cudaMalloc(&d_prof, (size_t)ws.P * 64) == cudaSuccess) a.prof = d_prof;
     size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + (size_t)(2 * ws.g.NW > 128 ? 2 * ws.g.NW : 128) * 4;
     const size_t adj_bytes = (size_t)ws.g.Kpad * ws.g.RS * 4;
     a.adj_in_smem = smem + adj_bytes <= 96 * 1024;      // K <= 512: rows live next to the search frame
@@ -859,6 +884,20 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     }
     k_clique<<<ws.P, 32, smem, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
+    if (d_prof) {   // diagnostic only: synchronous dump of the per-phase cycle counters
+        std::vector<long long> hp((size_t)ws.P * 8);
+        cudaMemcpyAsync(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(d_prof);
+        static const char* names[8] = {"stage", "deg+adjseq", "greedy", "pivot", "ext", "pop", "children", "frames"};
+        long long tot[8] = {0}, mx = 0; int arg = 0;
+        for (int p = 0; p < ws.P; ++p) { long long t = 0; for (int k = 0; k < 8; ++k) { tot[k] += hp[p * 8 + k]; t += hp[p * 8 + k]; } if (t > mx) { mx = t; arg = p; } }
+        fprintf(stderr, "[clique profile] P=%d  mean cycles:", ws.P);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], tot[k] / ws.P);
+        fprintf(stderr, "\n[clique profile] slowest pair %d (%lld cycles):", arg, mx);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], hp[arg * 8 + k]);
+        fprintf(stderr, "\n");
+    }
     return RF_OK;
 }
 
