@@ -156,8 +156,12 @@ RF_API int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, 
 RF_API int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, double R[4], double hvec[2]);
 
 /* ---- a8  MotionDistortionSolver.optimize_library         motionDistortion.py:80-325 */
+/* sigma_p[2] / sigma_v[3] are the DIAGONALS the solver object was built with (the reference
+ * weights residuals by 1/sigma, motionDistortion.py:96-99); NULL -> rf_config values;
+ * period <= 0 -> rf_config.mds_period. */
 RF_API int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const double* p_jt, int N,
-                 const double T_wj[9], double x_out[6], int* iters, double* cost);
+                 const double T_wj[9], const double* sigma_p, const double* sigma_v, double period,
+                 double x_out[6], int* iters, double* cost);
 /* static MotionDistortionSolver.undistort                  motionDistortion.py:127-153 */
 RF_API int rf_mds_undistort(rf_handle* h, const double v[3], const double* pts_xy, int N, double period,
                      double* out_xy);
@@ -169,11 +173,19 @@ RF_API int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double tol
 
 /* ---- a10 detector (response + 3x3 NMS + threshold)       getFeatures.py:22-53 ------ */
 /* mode 0: min-eigenvalue structure tensor (Sobel 3x3, 3x3 box), cv2.cornerMinEigenVal
- * semantics.  Candidates are returned sorted by (response desc, index asc):
- * out [cap,3] f64 (row, col, response).  *n receives the total candidate count. */
+ * semantics on the f32 Cartesian image.  Candidates are sorted by (response desc, index desc):
+ * out [cap,3] f64 (row, col, response).  *n receives the total candidate count.
+ * threshold >= 0 is absolute; threshold < 0 means the fraction -threshold of the maximum response
+ * (cv2.goodFeaturesToTrack's qualityLevel). */
 RF_API int rf_detect(rf_handle* h, const rf_frame* f, int mode, float threshold, double* out, int cap, int* n);
 /* response map only (f32 [2R,2R]) — used by the parity tests */
 RF_API int rf_corner_response(rf_handle* h, const rf_frame* f, int mode, float* resp);
+/* selection half of rf_detect on a caller-supplied response map (f32 [rows, cols]): interior
+ * pixels with resp > threshold that equal their 3x3 maximum, ordered like
+ * cv2.goodFeaturesToTrack orders its candidates (response descending, then pixel index
+ * descending).  out [cap,3] f64 (row, col, response); *n = total candidate count.  Bit-exact. */
+RF_API int rf_nms_select(rf_handle* h, const float* resp, int rows, int cols, float threshold, double* out, int cap,
+                  int* n);
 
 /* ---- a12 getPointCloud.getPointCloudPolarInd             getPointCloud.py:11-54 ---- */
 /* polar f32 [A, W] -> out [cap,2] i64 (azimuth, range), azimuth-major order. */

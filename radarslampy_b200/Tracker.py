@@ -1,0 +1,49 @@
+"""Drop-in for the reference's Tracker.py: per-pair front end (KLT -> outlier rejection ->
+corrStatus fix-up) and the metric rigid transform.  Tracker.py:16-127."""
+from typing import Tuple
+
+import numpy as np
+
+from .getTransformKLT import calculateTransformSVD, getTrackedPointsKLT
+from .outlierRejection import rejectOutliers
+from .parseData import RANGE_RESOLUTION_CART_M
+
+
+class Tracker():
+
+    def __init__(self, sequenceName: str, imgPathArr: list, filePaths: dict, paramFlags: dict) -> None:
+        self.sequenceName = sequenceName
+        self.imgPathArr = imgPathArr
+        self.sequenceSize = len(self.imgPathArr)
+        self.filePaths = filePaths
+        self.paramFlags = paramFlags
+        self.estTraj = None
+        self.gtTraj = None
+
+    def initTraj(self, estTraj, gtTraj=None):
+        self.estTraj = estTraj
+        self.gtTraj = gtTraj
+
+    def track(self, prevImgCart: np.ndarray, currImgCart: np.ndarray, prevImgPolar: np.ndarray,
+              currImgPolar: np.ndarray, featureCoord: np.ndarray, seqInd: int
+              ) -> Tuple[np.ndarray, np.ndarray, float, np.ndarray]:
+        """Tracker.py:35-106 -> (good_old, good_new, angleRotRad, corrStatus u8 [K,1]).
+        The FMT rotation prior (Tracker.py:62-63) is computed-but-unused in the reference and is
+        not part of this front end: angleRotRad is returned as 0.0."""
+        angleRotRad = 0.0
+        good_new, good_old, bad_new, bad_old, corrStatus = getTrackedPointsKLT(prevImgCart, currImgCart, featureCoord)
+        nFeatures = good_new.shape[0] + bad_new.shape[0]
+        if self.paramFlags.get("rejectOutliers", True):
+            good_old, good_new, pruning_mask = rejectOutliers(good_old, good_new)
+        else:
+            pruning_mask = np.ones(good_old.shape[0], dtype=bool)   # the reference leaves this unbound (NameError)
+        rng = np.arange(nFeatures)
+        corrStatus[rng[corrStatus.flatten().astype(bool)]] &= pruning_mask[:, np.newaxis]   # Tracker.py:103-104
+        return good_old, good_new, angleRotRad, corrStatus
+
+    def getTransform(self, srcCoord: np.ndarray, targetCoord: np.ndarray, pixel: bool) -> Tuple[np.ndarray, np.ndarray]:
+        """Tracker.py:108-127: (R, h) with src = R @ target + h; h in metres unless pixel."""
+        R, h = calculateTransformSVD(srcCoord, targetCoord)
+        if not pixel:
+            h *= RANGE_RESOLUTION_CART_M
+        return R, h

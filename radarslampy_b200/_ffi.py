@@ -47,7 +47,7 @@ SYMBOLS = [
     "rf_timer_start", "rf_timer_stop_ms", "rf_launch_count", "rf_extract_polar", "rf_frame_create",
     "rf_frame_destroy", "rf_polar_to_cart", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
     "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
-    "rf_detect", "rf_corner_response", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
+    "rf_detect", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
     "rf_batch_stage_times", "rf_host_alloc", "rf_host_free",
@@ -413,18 +413,20 @@ class RadarFE:
         return R, h
 
     # -- a8 ---------------------------------------------------------------------
-    def mds_solve(self, T_wj0, p_w, p_jt, T_wj):
+    def mds_solve(self, T_wj0, p_w, p_jt, T_wj, sigma_p=None, sigma_v=None, period=0.0):
         T0 = _c(T_wj0, np.float64).reshape(3, 3)
         T1 = _c(T_wj, np.float64).reshape(3, 3)
         pw = _c(np.asarray(p_w)[:, :2], np.float64)
         pj = _c(np.asarray(p_jt)[:, :2], np.float64)
         if pw.shape != pj.shape:
             raise ValueError("p_w and p_jt must have the same shape")
+        sp = None if sigma_p is None else _c(sigma_p, np.float64).reshape(2)
+        sv = None if sigma_v is None else _c(sigma_v, np.float64).reshape(3)
         x = np.zeros(6, np.float64)
         it = C.c_int(0)
         cost = C.c_double(0)
-        self._check(self.lib.rf_mds_solve(self.h, _ptr(T0), _ptr(pw), _ptr(pj), pw.shape[0], _ptr(T1), _ptr(x),
-                                          C.byref(it), C.byref(cost)))
+        self._check(self.lib.rf_mds_solve(self.h, _ptr(T0), _ptr(pw), _ptr(pj), pw.shape[0], _ptr(T1), _ptr(sp), _ptr(sv),
+                                          C.c_double(period), _ptr(x), C.byref(it), C.byref(cost)))
         return x, it.value, cost.value
 
     def mds_undistort(self, v, pts_xy, period):
@@ -450,6 +452,15 @@ class RadarFE:
         out = np.zeros((cap, 3), np.float64)
         n = C.c_int(0)
         self._check(self.lib.rf_detect(self.h, frame.p, mode, C.c_float(threshold), _ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy(), n.value
+
+    def nms_select(self, resp, threshold, cap=None):
+        resp = _c(resp, np.float32)
+        rows, cols = resp.shape
+        cap = rows * cols if cap is None else cap
+        out = np.zeros((max(cap, 1), 3), np.float64)
+        n = C.c_int(0)
+        self._check(self.lib.rf_nms_select(self.h, _ptr(resp), rows, cols, C.c_float(threshold), _ptr(out), cap, C.byref(n)))
         return out[:min(n.value, cap)].copy(), n.value
 
     def corner_response(self, frame: Frame, mode=0):

@@ -93,7 +93,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->R = cfg->downsample > 1 ? cfg->range_bins / cfg->downsample : cfg->range_bins;  // parseData.py:119-122
     h->n = 2 * h->R;
-    h->map = nullptr; h->d_raw = nullptr; h->d_polar = nullptr; h->d_polar_u8 = nullptr;
+    h->map = nullptr; h->map2 = nullptr; h->d_raw = nullptr; h->d_polar = nullptr; h->d_polar_u8 = nullptr;
     h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
     h->launches = 0;
     h->ev0 = h->ev1 = nullptr;
@@ -109,10 +109,11 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
     if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
         return bail(rf_fail(nullptr, RF_E_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&h->map, (size_t)h->n * h->n * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&h->map2, (size_t)h->n * h->n * sizeof(uint2)) != cudaSuccess ||
         cudaMalloc(&h->d_raw, (size_t)cfg->azimuths * cfg->raw_width) != cudaSuccess ||
         cudaMalloc(&h->d_polar, (size_t)cfg->azimuths * cfg->range_bins * sizeof(float)) != cudaSuccess)
         return bail(rf_fail(nullptr, RF_E_NOMEM, "rf_create: device allocation failed"));
-    if ((rc = rf_launch_build_map(h)) != RF_OK) { g_rf_err = h->err; return bail(rc); }
+    if ((rc = rf_launch_build_map(h)) != RF_OK || (rc = rf_launch_build_map2(h)) != RF_OK) { g_rf_err = h->err; return bail(rc); }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(rf_fail(nullptr, RF_E_CUDA, "map build failed"));
     *out = h;
     return RF_OK;
@@ -123,6 +124,7 @@ void rf_destroy(rf_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->map) cudaFree(h->map);
+    if (h->map2) cudaFree(h->map2);
     if (h->d_raw) cudaFree(h->d_raw);
     if (h->d_polar) cudaFree(h->d_polar);
     if (h->d_polar_u8) cudaFree(h->d_polar_u8);

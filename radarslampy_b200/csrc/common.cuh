@@ -36,6 +36,7 @@ struct rf_handle {
     int sm_count;
     // geometry table: packed fixed-point sample coordinates of cv2.warpPolar's inverse map
     uint32_t* map;  // [n][n]  (sx | sy << 17), sx = round(32*rho), sy = round(32*(phi+1))
+    uint2* map2;    // [n][n]  geometry records of the fused batch path (k_fused.cu)
     // staging
     uint8_t* d_raw;      // one raw scan
     float* d_polar;      // one f32 polar image
@@ -93,6 +94,12 @@ int rf_launch_cart_to_u8(rf_handle* h, const FrameSet& fs);
 int rf_launch_pyramid(rf_handle* h, const FrameSet& fs, int first, int n_frames);
 int rf_launch_extract(rf_handle* h, const uint8_t* d_raw, float* d_polar);
 
+// k_fused.cu — batch image path (interleaved scans -> level 0 + pyramid)
+int rf_fused_wp(const rf_handle* h);
+size_t rf_interleave_words(const rf_handle* h, int max_frames);
+int rf_launch_build_map2(rf_handle* h);
+int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out);
+int rf_launch_scan_to_pyramid(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames);
 // k_klt.cu
 int rf_launch_klt(rf_handle* h, const FrameSet& prev, const FrameSet& next, const int32_t* d_pair_idx, const float* d_pts,
                   const int32_t* d_counts, int Kmax, int P, float* d_next, uint8_t* d_status, float* d_err, int gate);

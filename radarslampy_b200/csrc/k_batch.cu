@@ -29,6 +29,7 @@ struct rf_batch {
     int max_frames, max_pairs, Kmax;
     int raw_pitch, raw_cols;
     uint8_t* d_raw;
+    uint32_t* d_rawi;            // frame-interleaved scans (4 frames per word), input of the fused image kernel
     FrameSet fs;
     int32_t* d_pair_idx; float* d_feats; int32_t* d_counts; double* d_prev_pose;
     float* d_next; uint8_t* d_status; float* d_err;
@@ -105,7 +106,7 @@ k_finish_pairs(int P, int Kmax, const int32_t* __restrict__ counts, const int32_
 static void batch_free(rf_batch* b) {
     if (!b) return;
     auto F = [](void* p) { if (p) cudaFree(p); };
-    F(b->d_raw); rf_frameset_free(&b->fs);
+    F(b->d_raw); F(b->d_rawi); rf_frameset_free(&b->fs);
     F(b->d_pair_idx); F(b->d_feats); F(b->d_counts); F(b->d_prev_pose);
     F(b->d_next); F(b->d_status); F(b->d_err);
     F(b->d_good_old); F(b->d_good_new); F(b->d_good_src); F(b->d_ngood);
@@ -134,10 +135,11 @@ int rf_batch_create(rf_handle* h, rf_batch** out) {
     rf_batch* b = new rf_batch();
     memset(b, 0, sizeof(*b));
     b->max_frames = c.max_frames; b->max_pairs = c.max_pairs; b->Kmax = c.max_features;
-    b->raw_cols = c.meta_bytes + c.range_bins;
+    b->raw_cols = c.range_bins;                 // power bins only: the 11 metadata bytes are decoded on the host
     b->raw_pitch = (b->raw_cols + 15) & ~15;
     const size_t P = b->max_pairs, K = b->Kmax;
-    RF_BALLOC(b->d_raw, (size_t)b->max_frames * c.azimuths * b->raw_pitch);
+    RF_BALLOC(b->d_raw, (size_t)b->max_frames * c.azimuths * b->raw_pitch + 16);
+    RF_BALLOC(b->d_rawi, rf_interleave_words(h, b->max_frames) * sizeof(uint32_t));
     int rc = rf_frameset_alloc(h, &b->fs, b->max_frames, c.write_cart_f32 != 0);
     if (rc) { batch_free(b); return rc; }
     RF_BALLOC(b->d_pair_idx, P * 2 * sizeof(int32_t));
@@ -186,7 +188,7 @@ int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_f
             return rf_fail(h, RF_E_BADARG, "rf_batch_upload: pair %d references a frame outside [0, %d)", p, n_frames);
     }
     if (n_frames)
-        RF_CUDA(h, cudaMemcpy2DAsync(b->d_raw, b->raw_pitch, raw, c.raw_width, b->raw_cols, (size_t)n_frames * c.azimuths,
+        RF_CUDA(h, cudaMemcpy2DAsync(b->d_raw, b->raw_pitch, raw + c.meta_bytes, c.raw_width, b->raw_cols, (size_t)n_frames * c.azimuths,
                                      cudaMemcpyHostToDevice, h->stream));
     if (n_pairs) {
         RF_CUDA(h, cudaMemcpyAsync(b->d_pair_idx, pair_idx, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -226,13 +228,18 @@ int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
     auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], h->stream); ++stage; };
     int rc;
     mark();
-    if (F) {
-        rc = rf_launch_polar2cart_u8(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, c.meta_bytes, b->fs, 0, F,
+    const bool fused = b->fs.cart == nullptr && b->fs.n_levels >= 2;
+    if (F && fused) {
+        // interleave (part of the conversion stage) then level 0 + level 1 in one kernel, higher levels after
+        if ((rc = rf_launch_interleave(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, F, b->d_rawi))) return rc;
+    } else if (F) {
+        rc = rf_launch_polar2cart_u8(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, 0, b->fs, 0, F,
                                      b->fs.cart != nullptr);
         if (rc) return rc;
     }
     mark();
-    if (F && (rc = rf_launch_pyramid(h, b->fs, 0, F))) return rc;
+    if (F && fused) { if ((rc = rf_launch_scan_to_pyramid(h, b->d_rawi, b->fs, F))) return rc; }
+    else if (F && (rc = rf_launch_pyramid(h, b->fs, 0, F))) return rc;
     mark();
     if (P) {
         if ((rc = rf_launch_klt(h, b->fs, b->fs, b->d_pair_idx, b->d_feats, b->d_counts, K, P, b->d_next, b->d_status,

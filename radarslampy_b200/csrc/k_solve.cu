@@ -380,7 +380,7 @@ int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, dou
 }
 
 int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const double* p_jt, int N, const double T_wj[9],
-                 double x_out[6], int* iters, double* cost) {
+                 const double* sigma_p, const double* sigma_v, double period, double x_out[6], int* iters, double* cost) {
     if (!h || !T_wj0 || !T_wj || !x_out || N < 0 || (N > 0 && (!p_w || !p_jt)))
         return rf_fail(h, RF_E_BADARG, "rf_mds_solve: bad argument");
     const int Ns = N > 0 ? N : 1;
@@ -401,6 +401,9 @@ int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const d
     RF_CUDA(h, cudaMemcpyAsync(dc, &N, 4, cudaMemcpyHostToDevice, h->stream));
     MdsArgs a; memset(&a, 0, sizeof(a));
     fill_mds_cfg(h, a);
+    if (sigma_p) { a.sig_p0 = sigma_p[0]; a.sig_p1 = sigma_p[1]; }
+    if (sigma_v) { a.sig_v0 = sigma_v[0]; a.sig_v1 = sigma_v[1]; a.sig_v2 = sigma_v[2]; }
+    if (period > 0) a.period = period;
     a.P = 1; a.p_w = dpw; a.p_jt = dpj; a.counts = dc; a.Nstride = Ns; a.T_wj0 = dT0; a.T_wj = dTw;
     a.x_out = dx; a.iters = dit; a.cost = dcost; a.scratch = dsc;
     k_mds<<<1, 32, 0, h->stream>>>(a);

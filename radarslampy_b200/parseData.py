@@ -1,0 +1,88 @@
+"""Drop-in for the reference's parseData.py (scan decode and polar -> Cartesian conversion) on
+libradarfe.so.  Same names, arguments and return values as parseData.py:17-53,100-135,160-226;
+the arithmetic runs in rf_extract_polar / rf_polar_to_cart (csrc/k_image.cu)."""
+import os
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _engine
+
+RANGE_RESOLUTION_M = 0.0432            # parseData.py:9
+DOWNSAMPLE_FACTOR = 2                  # parseData.py:10
+RANGE_RESOLUTION_CART_M = RANGE_RESOLUTION_M * DOWNSAMPLE_FACTOR
+MAX_RANGE_CLIP_DEFAULT = 87.5          # parseData.py:14
+META_BYTES = 11
+
+
+def extractDataFromRadarImage(polarImgData: np.ndarray, maxRangeClipM: float = MAX_RANGE_CLIP_DEFAULT
+                              ) -> Tuple[np.ndarray, np.ndarray, float, float, np.ndarray, np.ndarray]:
+    """parseData.py:17-53 -> (range_azimuth_data f32 [A, W], azimuths f32 [A,1], range_resolution,
+    azimuth_resolution, valid bool [A,1], timestamps i64 [A,1])."""
+    raw = np.ascontiguousarray(polarImgData, dtype=np.uint8)
+    A, wtot = raw.shape
+    bins = wtot - META_BYTES
+    if maxRangeClipM > 0:
+        bins = min(bins, int(maxRangeClipM / RANGE_RESOLUTION_M))
+    fe = _engine.engine(range_bins=bins, azimuths=A, raw_width=wtot)
+    polar, timestamps, azimuths, valid = fe.extract_polar(raw)
+    azimuth_resolution = azimuths[1] - azimuths[0]
+    return polar, azimuths, RANGE_RESOLUTION_M, azimuth_resolution, valid, timestamps
+
+
+def convertPolarImageToCartesian(imgPolar: np.ndarray, logPolarMode: bool = False,
+                                 downsampleFactor: int = DOWNSAMPLE_FACTOR,
+                                 changeGlobalRangeResolution: bool = False) -> np.ndarray:
+    """parseData.py:100-135 (cv2.warpPolar, inverse linear map) -> f32 [2R, 2R].  The returned array
+    also keeps its device frame (u8 image + LK pyramid) for getTrackedPointsKLT."""
+    if logPolarMode:
+        raise NotImplementedError("log-polar conversion is only used by the FMT rotation prior, which is outside "
+                                  "this front end (SURVEY.md §8f N1)")
+    imgPolar = np.ascontiguousarray(imgPolar, dtype=np.float32)
+    A, W = imgPolar.shape
+    if changeGlobalRangeResolution:
+        global RANGE_RESOLUTION_CART_M
+        RANGE_RESOLUTION_CART_M = RANGE_RESOLUTION_M * downsampleFactor
+    fe = _engine.engine(range_bins=W, azimuths=A, downsample=max(int(downsampleFactor), 1))
+    frame, cart = fe.polar_to_cart(polar=imgPolar)
+    return _engine.wrap(cart, fe, frame)
+
+
+def convertRawScanToCartesian(polarImgData: np.ndarray, maxRangeClipM: float = MAX_RANGE_CLIP_DEFAULT) -> np.ndarray:
+    """Fused extractDataFromRadarImage + convertPolarImageToCartesian straight from the raw u8 scan
+    (no f32 polar image on the host); bit-identical to calling the two in sequence."""
+    raw = np.ascontiguousarray(polarImgData, dtype=np.uint8)
+    A, wtot = raw.shape
+    bins = wtot - META_BYTES
+    if maxRangeClipM > 0:
+        bins = min(bins, int(maxRangeClipM / RANGE_RESOLUTION_M))
+    fe = _engine.engine(range_bins=bins, azimuths=A, raw_width=wtot)
+    frame, cart = fe.polar_to_cart(raw=raw)
+    return _engine.wrap(cart, fe, frame)
+
+
+# ---- file access (parseData.py:160-226): PNG decode stays on the host ---------------------------
+def getDataFromImgPathsByIndex(imgPathArr: List[str], index: int):
+    import cv2
+    imgPolarData = cv2.imread(imgPathArr[index], cv2.IMREAD_GRAYSCALE)
+    if imgPolarData is None:
+        raise FileNotFoundError(imgPathArr[index])
+    return extractDataFromRadarImage(imgPolarData)
+
+
+def getPolarImageFromImgPaths(imgPathArr: List[str], index: int) -> np.ndarray:
+    return getDataFromImgPathsByIndex(imgPathArr, index)[0]
+
+
+def getCartImageFromImgPaths(imgPathArr: List[str], index: int) -> np.ndarray:
+    return convertPolarImageToCartesian(getPolarImageFromImgPaths(imgPathArr, index))
+
+
+def getRadarImgPaths(dataPath: str, timestampPath: str) -> List[str]:
+    imgPathArr = []
+    with open(timestampPath, "r") as f:
+        for line in f:
+            stamp, valid = line.strip().split(" ")
+            if valid:                                  # parseData.py:221 (a non-empty string, so "0" passes too)
+                imgPathArr.append(os.path.join(dataPath, stamp + ".png"))
+    return imgPathArr

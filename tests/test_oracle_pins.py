@@ -205,3 +205,17 @@ def test_polar_peaks_match_reference_and_scipy(golden, tiny):
     assert np.array_equal(got, golden["peaks_fixture"]["peaks"].astype(np.int64))
     row = np.array([0, 1, 1, 1, 0, 2, 3, 3, 2, 5, 5, 1, 4], np.float32)
     assert find_peaks(row)[0].tolist() == [2, 6, 9]
+
+
+# ---- a10 detector (structure tensor) -----------------------------------------------------
+def test_corner_response_and_selection_match_live_cv2(tiny):
+    """oracle restatement of cv2.cornerMinEigenVal (<= 2e-6 abs) and of cv2.goodFeaturesToTrack's
+    candidate rule + ordering (exact, given cv2's own response map)."""
+    import cv2
+    cart = tiny[0][2]
+    ref = cv2.cornerMinEigenVal(cart, 3, ksize=3)
+    assert np.abs(R.corner_min_eig(cart) - ref).max() <= 2e-6
+    pts = cv2.goodFeaturesToTrack(cart, 0, 0.01, 0, blockSize=3, useHarrisDetector=False).reshape(-1, 2)
+    sel = R.nms_select(ref, float(ref.max()) * 0.01)
+    assert len(sel) == len(pts) > 1000
+    assert np.array_equal(sel[:, 1], pts[:, 0]) and np.array_equal(sel[:, 0], pts[:, 1])
