@@ -24,6 +24,7 @@ int rf_ensure_scratch(rf_handle* h, size_t bytes) {
     bytes = (bytes + (1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
     RF_CUDA(h, cudaMalloc(&h->d_scratch, bytes));
     h->scratch_bytes = bytes;
+    h->scratch_gen++;
     return RF_OK;
 }
 
@@ -94,7 +95,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
     h->R = cfg->downsample > 1 ? cfg->range_bins / cfg->downsample : cfg->range_bins;  // parseData.py:119-122
     h->n = 2 * h->R;
     h->map = nullptr; h->map2 = nullptr; h->d_raw = nullptr; h->d_polar = nullptr; h->d_polar_u8 = nullptr;
-    h->d_scratch = nullptr; h->scratch_bytes = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
+    h->d_scratch = nullptr; h->scratch_bytes = 0; h->scratch_gen = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
     h->launches = 0;
     h->ev0 = h->ev1 = nullptr;
     int rc = RF_OK;

@@ -42,6 +42,7 @@ struct rf_handle {
     float* d_polar;      // one f32 polar image
     uint8_t* d_polar_u8; // [A][range_bins] u8 recovered from an f32 polar
     void* d_scratch; size_t scratch_bytes;    // generic device scratch (grown on demand)
+    uint64_t scratch_gen;                     // bumped whenever the arena is reallocated (contents lost)
     void* h_pinned; size_t pinned_bytes;      // generic pinned host staging
     cudaEvent_t ev0, ev1;
     int64_t launches;

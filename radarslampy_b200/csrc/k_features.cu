@@ -161,9 +161,9 @@ extern "C" int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double
         if (!(fcc >= 0 && fcr >= 0)) return rf_fail(h, RF_E_BADARG, "rf_ssc: negative cell size (ANMS.py:45-47)");
         if ((fcc + 1) * (fcr + 1) > 1073741824.0) {   // > 2^30 cells: grid-free pass
             const size_t co_bytes = ((size_t)n * sizeof(double) + 255) & ~(size_t)255;
-            const void* before = h->d_scratch;
+            const uint64_t before = h->scratch_gen;
             if ((rc = rf_ensure_scratch(h, need + 2 * co_bytes))) return rc;
-            if (h->d_scratch != before)
+            if (h->scratch_gen != before)
                 RF_CUDA(h, cudaMemcpyAsync(h->d_scratch, kp, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             char* base = (char*)h->d_scratch;
             SscSparse sp;
@@ -189,9 +189,9 @@ extern "C" int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double
         if (cov_bytes <= SSC_SMEM_MAX) {
             smem = cov_bytes;
         } else {
-            const void* before = h->d_scratch;
+            const uint64_t before = h->scratch_gen;
             if ((rc = rf_ensure_scratch(h, need + cov_bytes))) return rc;
-            if (h->d_scratch != before) {   // the arena moved: stage the keypoints again (earlier results are obsolete)
+            if (h->scratch_gen != before) {   // the arena moved: stage the keypoints again (earlier results are obsolete)
                 if (n) RF_CUDA(h, cudaMemcpyAsync(h->d_scratch, kp, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             }
         }

@@ -1,0 +1,103 @@
+"""Multi-GPU host logic on CPU: contiguous pair blocks per rank, fixed-width pose
+records gathered to rank 0 with torch.distributed (gloo here, NCCL on the GPU box), concatenated in
+pair order.  world_size 2 and 3, uneven blocks included.  No kernels run: every rank fabricates the
+records of its block from the pair index so the test can check placement exactly."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from radarslampy_b200 import _shard
+
+
+def test_block_range_covers_everything():
+    for n in (0, 1, 7, 255, 4096):
+        for world in (1, 2, 3, 8):
+            blocks = [_shard.block_range(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    # config 4 of BASELINE.json: 4096 pairs over 8 GPUs -> 512 each
+    assert _shard.block_range(4096, 8, 3) == (1536, 2048)
+
+
+def test_shard_pairs_reindexes_frames():
+    pair_idx = np.array([[i, i + 1] for i in range(10)])
+    lo, hi, frames, local = _shard.shard_pairs(pair_idx, 2, 1)
+    assert (lo, hi) == (5, 10)
+    assert frames.tolist() == list(range(5, 11))
+    assert np.array_equal(frames[local], pair_idx[lo:hi])
+
+
+def test_record_roundtrip():
+    from radarslampy_b200 import _ffi
+    res = np.zeros(3, dtype=_ffi.PAIR_RESULT_DTYPE)
+    rng = np.random.default_rng(0)
+    res["R"] = rng.normal(size=(3, 4)); res["h"] = rng.normal(size=(3, 2)); res["mds_x"] = rng.normal(size=(3, 6))
+    res["n_features"] = [200, 199, 0]; res["n_good"] = [150, 3, 0]; res["n_inliers"] = [100, 2, 0]; res["status"] = [0, -4, 0]
+    rec = _shard.pack_records(res)
+    back = _shard.unpack_records(rec)
+    assert np.array_equal(back["R"].reshape(3, 4), res["R"]) and np.array_equal(back["h"], res["h"])
+    assert np.array_equal(back["mds_x"], res["mds_x"])
+    assert back["n_inliers"].tolist() == [100, 2, 0] and back["status"].tolist() == [0, -4, 0]
+
+
+def test_chain_poses_matches_matrix_product():
+    rng = np.random.default_rng(1)
+    th = rng.normal(scale=0.05, size=20)
+    R = np.stack([[np.cos(t), -np.sin(t), np.sin(t), np.cos(t)] for t in th]).reshape(-1, 2, 2)
+    h = rng.normal(size=(20, 2))
+    traj = _shard.chain_poses(R, h)
+    T = np.eye(3)
+    for k in range(20):
+        A = np.eye(3); A[:2, :2] = R[k]; A[:2, 2] = h[k]
+        T = T @ A
+    assert np.allclose(traj[-1], (T[0, 2], T[1, 2], np.arctan2(T[1, 0], T[0, 0])), atol=1e-12)
+    assert np.allclose(traj[-1, 2], th.sum(), atol=1e-12)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, n_pairs, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = _shard.block_range(n_pairs, world, rank)
+        rec = np.zeros((hi - lo, _shard.RECORD_WIDTH))
+        rec[:, 0] = np.arange(lo, hi)            # "R[0]" carries the global pair id
+        rec[:, 14] = rank                        # n_inliers carries the producing rank
+        g = _shard.PoseGatherer(n_pairs, world, rank)
+        for _ in range(2):                       # buffers are reused across steps
+            out = g.gather(rec)
+        if rank == 0:
+            q.put(out)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_pairs", [(2, 255), (2, 4096), (3, 10)])
+def test_gather_world(world, n_pairs):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out.shape == (n_pairs, _shard.RECORD_WIDTH)
+    assert np.array_equal(out[:, 0], np.arange(n_pairs))          # pair order preserved across ranks
+    for r in range(world):
+        lo, hi = _shard.block_range(n_pairs, world, r)
+        assert np.all(out[lo:hi, 14] == r)
