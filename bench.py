@@ -113,7 +113,7 @@ def workload(args, rank):
     return rb, kmax, raw, poses, pair_idx, feats, counts
 
 
-def stage_bytes(cfgd, S_frames, P, K_total, write_f32, levels):
+def stage_bytes(cfgd, S_frames, P, K_total, write_f32, levels, fused):
     """ALGORITHMIC bytes per launch group: every input read once, every mandated output
     written once."""
     A, W, n = cfgd["azimuths"], cfgd["range_bins"], cfgd["n"]
@@ -122,8 +122,16 @@ def stage_bytes(cfgd, S_frames, P, K_total, write_f32, levels):
         lv.append(((lv[-1][0] + 1) // 2, (lv[-1][1] + 1) // 2))
     px = [a * b for a, b in lv]
     b = {}
-    b["polar2cart"] = S_frames * (A * W + px[0] + (4 * px[0] if write_f32 else 0))
-    b["pyramid"] = S_frames * sum(px[l - 1] + px[l] for l in range(1, levels))
+    if fused:
+        # the interleave is a layout pass (read the used bins, write them back 4 frames per word)
+        b["polar2cart"] = S_frames * 2 * A * W
+        # scan -> level 0 + level 1: read the used polar bins once, write both levels once
+        b["scan_to_l0l1"] = S_frames * (A * W + px[0] + px[1])
+        b["pyr_down"] = S_frames * sum(px[l - 1] + px[l] for l in range(2, levels))
+    else:
+        b["polar2cart"] = S_frames * (A * W + px[0] + (4 * px[0] if write_f32 else 0))
+        b["scan_to_l0l1"] = 0
+        b["pyr_down"] = S_frames * sum(px[l - 1] + px[l] for l in range(1, levels))
     # one track: per level an 18x18 previous-image patch + at least one 16x16 next-image window, + the err pass
     b["klt"] = K_total * (levels * (324 + 256) + 256) + K_total * (8 + 8 + 1 + 4)
     b["compact"] = K_total * (8 + 8 + 1) + K_total * (8 + 8 + 4)
@@ -235,7 +243,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from radarslampy_b200 import _ffi
+    from radarslampy_b200 import _ffi, _shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - this framework has no CPU fallback (use --impl reference for the CPU arm)")
@@ -253,72 +261,96 @@ def main():
     cfg.write_cart_f32 = args.write_f32
     stream = torch.cuda.Stream()
     fe = _ffi.RadarFE(cfg, device=local_rank, stream=stream.cuda_stream)
-    batch = fe.new_batch()
-    # pinned host staging (what a caller streaming scans from disk would fill)
-    raw = _ffi.pinned_empty(raw_np.shape, np.uint8); raw[...] = raw_np
-    feats_p = _ffi.pinned_empty(feats.shape, np.float32); feats_p[...] = feats
-    outs = batch.alloc_outputs(pinned=True)
-    prev_pose = poses[:-1].copy()
-    gather_buf = None
-    res_dev = torch.zeros((P, 15), dtype=torch.float64, device="cuda") if world > 1 else None
-    if world > 1:
-        gather_buf = [torch.zeros_like(res_dev) for _ in range(world)] if rank == 0 else None
+    # Two batches used alternately (double buffering): the upload of one overlaps the kernels of the other
+    # and the latency-bound clique search of one overlaps the image stage of the next.
+    NB = 2
+    batches = [fe.new_batch() for _ in range(NB)]
+    # pinned host staging (what a caller streaming scans from disk would fill); everything that is uploaded
+    # asynchronously must be page-locked or the copy call blocks the host
+    def pin(a, dt):
+        out = _ffi.pinned_empty(a.shape, dt); out[...] = a
+        return out
+    raw = pin(raw_np, np.uint8)
+    feats_p = pin(feats, np.float32)
+    pair_idx_p = pin(np.asarray(pair_idx, np.int32), np.int32)
+    counts_p = pin(np.asarray(counts, np.int32), np.int32)
+    prev_pose = pin(poses[:-1], np.float64)
+    outs = [b.alloc_outputs(pinned=True) for b in batches]
+    gatherer = _shard.PoseGatherer(world * P, world, rank, device="cuda") if world > 1 else None
+    with_mds = bool(args.mds)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        fe.sync()
 
     def gather_poses(res_host):
-        """trajectory concatenation: poses of every rank to rank 0 over NCCL"""
-        if world == 1:
-            return
-        flat = np.concatenate([res_host["R"], res_host["h"], res_host["mds_x"], res_host["n_good"][:, None],
-                               res_host["n_inliers"][:, None], res_host["status"][:, None]], axis=1)
-        res_dev.copy_(torch.from_numpy(flat), non_blocking=True)
-        dist.gather(res_dev, gather_buf, dst=0)
+        """trajectory concatenation: poses of every rank to rank 0 over NCCL (SURVEY.md §8e)"""
+        if world > 1:
+            gatherer.gather(_shard.pack_records(res_host))
+
+    def upload(b):
+        b.upload(raw, pair_idx_p, feats_p, counts_p, prev_pose=prev_pose, sync=False)
 
     # ---- device-resident arm: scans already in HBM ------------------------------------------
-    batch.upload(raw, pair_idx, feats_p, counts, prev_pose=prev_pose)
-    batch.set_profiling(True)
-    for _ in range(args.warmup):
-        batch.run_async(with_mds=bool(args.mds))
+    for b in batches:
+        upload(b)
+        b.set_profiling(True)
     fe.sync()
-    batch.stage_times()
+    for i in range(max(args.warmup, NB)):
+        batches[i % NB].run_async(with_mds=with_mds)
+    fe.sync()
+    for b in batches:
+        b.stage_times()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     n0 = fe.launch_count()
     fe.timer_start()
-    for _ in range(args.steps):
-        batch.run_async(with_mds=bool(args.mds))
-    ms = fe.timer_stop_ms()
+    for i in range(args.steps):
+        batches[i % NB].run_async(with_mds=with_mds)
+    ms = fe.timer_stop_ms()          # joins the tail streams: every step's poses are complete
     launches = fe.launch_count() - n0
     barrier()
-    stage_ms, runs = batch.stage_times()
-    res, nxt, corr = batch.download(outs)
+    stage_ms, runs = {}, 0
+    for b in batches:
+        sm, r = b.stage_times()
+        runs += r
+        for k, v in sm.items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v
+    res, nxt, corr = batches[0].download(outs[0])
     fe.sync()
     gather_poses(res)
     barrier()
 
     # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ------
-    batch.set_profiling(False)
-    for _ in range(args.warmup):
-        batch.upload(raw, pair_idx, feats_p, counts, prev_pose=prev_pose, sync=False)
-        batch.run_async(with_mds=bool(args.mds))
-        r2 = batch.download(outs, sync=False, want_tracks=False)
-        fe.sync()
+    for b in batches:
+        b.set_profiling(False)
+
+    def e2e_loop(n):
+        prev = None
+        for i in range(n):
+            k = i % NB
+            b = batches[k]
+            upload(b)                                   # H2D of every scan of the step (copy stream)
+            b.run_async(with_mds=with_mds)
+            b.download(outs[k], sync=False, want_tracks=False)   # D2H of the poses (tail stream)
+            if prev is not None:                        # the caller reads the poses of the previous step
+                batches[prev].wait()
+                gather_poses(outs[prev][0][:P])
+            prev = k
+        batches[prev].wait()
+        gather_poses(outs[prev][0][:P])
+
+    e2e_loop(max(args.warmup, NB))
     barrier()
     t0 = time.perf_counter()
     fe.timer_start()
-    for _ in range(args.steps):
-        batch.upload(raw, pair_idx, feats_p, counts, prev_pose=prev_pose, sync=False)
-        batch.run_async(with_mds=bool(args.mds))
-        r2 = batch.download(outs, sync=False, want_tracks=False)
-        fe.sync()                                   # the caller reads the poses of this step
-        gather_poses(r2[0])
-    ms_e2e = fe.timer_stop_ms()                   # CUDA events on the handle's stream (every step ends in a sync)
+    e2e_loop(args.steps)
+    ms_e2e = fe.timer_stop_ms()
     barrier()
+    ms_e2e = max(ms_e2e, 0.0)
     if world > 1:                                 # the NCCL gather runs on torch's stream: bound it by the host clock
         ms_e2e = max(ms_e2e, (time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop()
@@ -335,13 +367,17 @@ def main():
 
     K_total = int(counts.sum())
     cfgd = {"azimuths": cfg.azimuths, "range_bins": rb, "n": fe.n}
-    sb = stage_bytes(cfgd, S, P, K_total, bool(args.write_f32), 4)
+    sb = stage_bytes(cfgd, S, P, K_total, bool(args.write_f32), 4, fused=not args.write_f32)
     peak, peak_src = peaks()
     stages = {}
     for name, tot in stage_ms.items():
         per = tot / max(runs, 1)
         stages[name] = {"ms": per, "alg_bytes": sb[name], "gbs": (sb[name] / (per * 1e-3) / 1e9) if per > 0 else None}
-    dom = max(stages, key=lambda k: stages[k]["ms"])
+    # dominant kernel = the HBM-streaming stage with the largest share of the step (the clique search is a
+    # latency-bound combinatorial kernel with ~3 KB of traffic per pair; it has no bandwidth roofline and is
+    # reported in `stages` and `clique`)
+    streaming = [k for k in ("polar2cart", "scan_to_l0l1", "pyr_down", "klt") if stages[k]["ms"] > 0]
+    dom = max(streaming, key=lambda k: stages[k]["ms"])
     achieved = stages[dom]["gbs"] or 0.0
     value = world * P * args.steps / (ms * 1e-3)
     e2e = world * P * args.steps / (ms_e2e * 1e-3)
@@ -350,7 +386,7 @@ def main():
     line = {
         "metric": "radar frames/sec polar->pose", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/f32/f64", "data": "synthetic", "config": workload_config(args, rb, kmax),
+        "dtype": "u8/f32/f64", "data": "synthetic", "config": dict(workload_config(args, rb, kmax), pipelining=f"{NB} batches alternate on one handle (copy / image+KLT / rejection+solve streams)"),
         "klt_tracks_per_s": world * K_total * args.steps / (ms * 1e-3),
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},
@@ -363,11 +399,14 @@ def main():
         "pose_check": {"median_dtheta_rad": float(np.median(np.arctan2(res["R"][:, 2], res["R"][:, 0]))),
                        "expected_dtheta_rad": 0.025, "median_inliers": float(np.median(res["n_inliers"])),
                        "worklimit_pairs": int((res["status"] != 0).sum())},
+        "clique": {"nodes_median": float(np.median(res["clique_nodes"])), "nodes_p90": float(np.percentile(res["clique_nodes"], 90)),
+                   "nodes_max": int(res["clique_nodes"].max()), "good_median": float(np.median(res["n_good"]))},
     }
     if cpu_line is not None:
         line["cpu_baseline"] = cpu_line
     print(json.dumps(line), flush=True)
-    batch.close()
+    for b in batches:
+        b.close()
     fe.close()
     if world > 1:
         dist.destroy_process_group()

@@ -203,9 +203,17 @@ RF_API int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_
  * be pinned, see rf_host_alloc) until rf_sync returns. */
 RF_API int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
                           int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose);
-/* Device-only: every stage for every pair, no host synchronisation before return. */
+/* Device-only: every stage for every pair, no host synchronisation before return.
+ * Pipelining: uploads run on a copy stream, the image + KLT stages on the handle's stream and the
+ * rejection / solve stages (and the download) on a per-batch tail stream, chained by events; with two
+ * batches used alternately on one handle the upload of one overlaps the kernels of the other.  An
+ * upload into a batch waits (on the device) until the previous run of that batch has consumed its
+ * inputs. */
 RF_API int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds);
+/* Block until everything queued on the handle (all its streams, all its batches) has finished. */
 RF_API int rf_sync(rf_handle* h);
+/* Block until the last run + download queued for this batch has finished (other batches keep going). */
+RF_API int rf_batch_wait(rf_handle* h, rf_batch* b);
 /* Device -> host: results [n_pairs]; next_xy [n_pairs,max_features,2] and status
  * [n_pairs,max_features] may be NULL. */
 RF_API int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status);
@@ -219,8 +227,9 @@ RF_API int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, i
 /* Per-stage CUDA-event timing on the handle's stream.  While enabled, every
  * rf_batch_run_async records events at its stage boundaries (ring of 64 runs);
  * rf_batch_stage_times synchronises, sums the elapsed ms of the runs recorded since the last
- * call into ms_sum[8] = {polar->cart, pyramid, klt, compact, reject, kabsch, mds, finish}
- * and resets the ring. */
+ * call into ms_sum[9] = {polar->cart | frame interleave, scan -> level 0 + 1, pyrDown of the remaining
+ * levels, klt, compact, reject, kabsch, mds, finish} and resets the ring.  Stages of different batches
+ * overlap when batches are pipelined, so the sums describe kernels, not the critical path. */
 RF_API int rf_batch_set_profiling(rf_handle* h, rf_batch* b, int on);
 RF_API int rf_batch_stage_times(rf_handle* h, rf_batch* b, float* ms_sum, int cap, int* n_runs);
 /* Pinned (page-locked) host memory for the *_async entry points. */

@@ -50,9 +50,9 @@ SYMBOLS = [
     "rf_detect", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
-    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free",
+    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait",
 ]
-STAGES = ("polar2cart", "pyramid", "klt", "compact", "reject", "kabsch", "mds", "finish")
+STAGES = ("polar2cart", "scan_to_l0l1", "pyr_down", "klt", "compact", "reject", "kabsch", "mds", "finish")
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -185,6 +185,10 @@ class Batch:
     def run_async(self, with_mds=False):
         self.fe._check(self.fe.lib.rf_batch_run_async(self.fe.h, self.p, int(with_mds)))
 
+    def wait(self):
+        """Block until the last run + download queued for THIS batch has finished (rf_batch_wait)."""
+        self.fe._check(self.fe.lib.rf_batch_wait(self.fe.h, self.p))
+
     def alloc_outputs(self, pinned=False):
         P, K = self.fe.cfg.max_pairs, self.fe.cfg.max_features
         mk = pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dt))
@@ -219,9 +223,9 @@ class Batch:
 
     def stage_times(self):
         """({stage: total ms}, n_runs) over the runs recorded since the last call."""
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * len(STAGES))()
         n = C.c_int(0)
-        self.fe._check(self.fe.lib.rf_batch_stage_times(self.fe.h, self.p, ms, 8, C.byref(n)))
+        self.fe._check(self.fe.lib.rf_batch_stage_times(self.fe.h, self.p, ms, len(STAGES), C.byref(n)))
         return dict(zip(STAGES, [float(v) for v in ms])), n.value
 
     def track(self, raw, pair_idx, feats, counts, prev_pose=None, with_mds=False):

@@ -97,7 +97,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
     h->map = nullptr; h->map2 = nullptr; h->d_raw = nullptr; h->d_polar = nullptr; h->d_polar_u8 = nullptr;
     h->d_scratch = nullptr; h->scratch_bytes = 0; h->scratch_gen = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
     h->launches = 0;
-    h->ev0 = h->ev1 = nullptr;
+    h->ev0 = h->ev1 = nullptr; h->stream_copy = nullptr; h->ev_copy = nullptr; h->stream = nullptr; h->owns_stream = false;
     int rc = RF_OK;
     auto bail = [&](int code) { rf_destroy(h); return code; };
     if (cudaSetDevice(device) != cudaSuccess) return bail(rf_fail(nullptr, RF_E_CUDA, "cudaSetDevice failed"));
@@ -107,7 +107,10 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
             return bail(rf_fail(nullptr, RF_E_CUDA, "cudaStreamCreate failed"));
         h->owns_stream = true;
     }
-    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(rf_fail(nullptr, RF_E_CUDA, "cudaStreamCreate failed"));
+    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess)
         return bail(rf_fail(nullptr, RF_E_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&h->map, (size_t)h->n * h->n * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&h->map2, (size_t)h->n * h->n * sizeof(uint2)) != cudaSuccess ||
@@ -123,7 +126,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
 void rf_destroy(rf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    rf_sync_all(h);
     if (h->map) cudaFree(h->map);
     if (h->map2) cudaFree(h->map2);
     if (h->d_raw) cudaFree(h->d_raw);
@@ -133,6 +136,8 @@ void rf_destroy(rf_handle* h) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->stream_copy) cudaStreamDestroy(h->stream_copy);
     if (h->owns_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -143,11 +148,15 @@ int64_t rf_launch_count(const rf_handle* h) { return h ? h->launches : 0; }
 
 int rf_timer_start(rf_handle* h) {
     if (!h) return RF_E_BADARG;
+    int rc = rf_join_streams(h);
+    if (rc) return rc;
     RF_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     return RF_OK;
 }
 int rf_timer_stop_ms(rf_handle* h, float* ms) {
     if (!h || !ms) return RF_E_BADARG;
+    int rc = rf_join_streams(h);   // the interval ends when the copy and tail streams have drained too
+    if (rc) return rc;
     RF_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     RF_CUDA(h, cudaEventSynchronize(h->ev1));
     RF_CUDA(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
@@ -155,8 +164,7 @@ int rf_timer_stop_ms(rf_handle* h, float* ms) {
 }
 int rf_sync(rf_handle* h) {
     if (!h) return RF_E_BADARG;
-    RF_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RF_OK;
+    return rf_sync_all(h);
 }
 
 // ---- a1 -------------------------------------------------------------------------------

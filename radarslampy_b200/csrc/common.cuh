@@ -26,11 +26,15 @@ struct rf_frame {
     FrameSet fs;
 };
 
+struct rf_batch;
 struct rf_handle {
     rf_config cfg;
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream;       // main stream: every single-stage entry point, and the image + KLT stages of a batch
     bool owns_stream;
+    cudaStream_t stream_copy;  // H2D staging of the batch path (overlaps the kernels of the previous batch)
+    cudaEvent_t ev_copy;       // join point of stream_copy for the timers / rf_sync
+    std::vector<rf_batch*> batches;   // live batches (each owns a tail stream for rejection + solves)
     int n;          // cartesian size 2R
     int R;
     int sm_count;
@@ -54,6 +58,9 @@ extern thread_local std::string g_rf_err;  // for failures without a handle
 int rf_fail(rf_handle* h, int code, const char* fmt, ...);
 int rf_ensure_scratch(rf_handle* h, size_t bytes);
 int rf_ensure_pinned(rf_handle* h, size_t bytes);
+// k_batch.cu: make the main stream wait for everything outstanding on the copy / tail streams; full sync
+int rf_join_streams(rf_handle* h);
+int rf_sync_all(rf_handle* h);
 
 #define RF_CUDA(h, expr)                                                                         \
     do {                                                                                         \
@@ -100,7 +107,8 @@ int rf_fused_wp(const rf_handle* h);
 size_t rf_interleave_words(const rf_handle* h, int max_frames);
 int rf_launch_build_map2(rf_handle* h);
 int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out);
-int rf_launch_scan_to_pyramid(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames);
+int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames);
+int rf_launch_pyr_levels(rf_handle* h, const FrameSet& fs, int first_level, int n_frames);
 // k_klt.cu
 int rf_launch_klt(rf_handle* h, const FrameSet& prev, const FrameSet& next, const int32_t* d_pair_idx, const float* d_pts,
                   const int32_t* d_counts, int Kmax, int P, float* d_next, uint8_t* d_status, float* d_err, int gate);

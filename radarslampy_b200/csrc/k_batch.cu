@@ -20,10 +20,22 @@
 //   good     old/new[P][Kmax][2], src_row[P][Kmax], n_good[P]
 //   clique   workspace of k_clique.cu (adjacency bitsets, search stacks, masks)
 //   poses    R[P][4], h[P][2], mds_x[P][6], results[P] (rf_pair_result)
+//
+// Streams.  A batch is pipelined over three streams so that, with two batches alternating on
+// one handle, the PCIe upload of batch B, the image + KLT kernels of batch A and the
+// latency-bound clique search of the batch before overlap:
+//   handle.stream_copy  H2D staging                        -> ev_uploaded
+//   handle.stream       interleave, scan->pyramid, KLT, compaction      -> ev_main_done
+//   batch.tail          adjacency, clique, Kabsch, MDS, finish, D2H     -> ev_tail_done
+// An upload waits for the previous run of the SAME batch (ev_main_done, ev_tail_done) before
+// it overwrites the inputs; KLT waits for the previous tail of the same batch before it
+// overwrites the track buffers.  rf_sync / the timers join all three.
+#include <algorithm>
+
 #include "common.cuh"
 
 #define RF_PROFILE_RING 64
-#define RF_N_STAGES 8   // p2c, pyramid, klt, compact, reject, kabsch, mds, finish
+#define RF_N_STAGES 9   // p2c|interleave, scan->L0+L1, pyrDown (rest), klt, compact, reject, kabsch, mds, finish
 
 struct rf_batch {
     int max_frames, max_pairs, Kmax;
@@ -42,7 +54,36 @@ struct rf_batch {
     // per-stage CUDA events of the most recent runs (ring)
     bool profiling; int prof_head; int prof_count;
     cudaEvent_t ev[RF_PROFILE_RING][RF_N_STAGES + 1];
+    // pipeline
+    cudaStream_t tail;
+    cudaEvent_t ev_uploaded, ev_main_done, ev_tail_done;
 };
+
+// Launchers take their stream from the handle: run a scope on another stream.
+struct StreamScope {
+    rf_handle* h; cudaStream_t saved;
+    StreamScope(rf_handle* h_, cudaStream_t s) : h(h_), saved(h_->stream) { h->stream = s; }
+    ~StreamScope() { h->stream = saved; }
+};
+
+int rf_join_streams(rf_handle* h) {
+    if (h->stream_copy) {
+        RF_CUDA(h, cudaEventRecord(h->ev_copy, h->stream_copy));
+        RF_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    }
+    for (rf_batch* b : h->batches) {
+        RF_CUDA(h, cudaEventRecord(b->ev_tail_done, b->tail));
+        RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_tail_done, 0));
+    }
+    return RF_OK;
+}
+
+int rf_sync_all(rf_handle* h) {
+    if (h->stream_copy) RF_CUDA(h, cudaStreamSynchronize(h->stream_copy));
+    if (h->stream) RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (rf_batch* b : h->batches) RF_CUDA(h, cudaStreamSynchronize(b->tail));
+    return RF_OK;
+}
 
 // ------------------------------------------------------------------------------------
 // getTransformKLT.py:368-376: good_new = nextPts[status == 1] (order preserved).  One warp
@@ -115,6 +156,10 @@ static void batch_free(rf_batch* b) {
     for (int i = 0; i < RF_PROFILE_RING; ++i)
         for (int s = 0; s <= RF_N_STAGES; ++s)
             if (b->ev[i][s]) cudaEventDestroy(b->ev[i][s]);
+    if (b->ev_uploaded) cudaEventDestroy(b->ev_uploaded);
+    if (b->ev_main_done) cudaEventDestroy(b->ev_main_done);
+    if (b->ev_tail_done) cudaEventDestroy(b->ev_tail_done);
+    if (b->tail) cudaStreamDestroy(b->tail);
     delete b;
 }
 
@@ -161,13 +206,25 @@ int rf_batch_create(rf_handle* h, rf_batch** out) {
     RF_BALLOC(b->d_mds_scratch, P * K * 5 * sizeof(double));
     RF_BALLOC(b->d_corr, P * K);
     RF_BALLOC(b->d_results, P * sizeof(rf_pair_result));
+    if (cudaStreamCreateWithFlags(&b->tail, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_tail_done, cudaEventDisableTiming) != cudaSuccess) {
+        batch_free(b);
+        return rf_fail(h, RF_E_CUDA, "rf_batch_create: stream/event creation failed");
+    }
+    h->batches.push_back(b);
     *out = b;
     return RF_OK;
 }
 
 void rf_batch_destroy(rf_handle* h, rf_batch* b) {
     if (!b) return;
-    if (h) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    if (h) {
+        cudaSetDevice(h->device);
+        rf_sync_all(h);
+        h->batches.erase(std::remove(h->batches.begin(), h->batches.end(), b), h->batches.end());
+    }
     batch_free(b);
 }
 
@@ -187,16 +244,21 @@ int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_f
         if (pair_idx[2 * p] < 0 || pair_idx[2 * p] >= n_frames || pair_idx[2 * p + 1] < 0 || pair_idx[2 * p + 1] >= n_frames)
             return rf_fail(h, RF_E_BADARG, "rf_batch_upload: pair %d references a frame outside [0, %d)", p, n_frames);
     }
+    cudaStream_t cs = h->stream_copy;
+    // the previous run of this batch must have consumed its inputs before they are overwritten
+    RF_CUDA(h, cudaStreamWaitEvent(cs, b->ev_main_done, 0));
+    RF_CUDA(h, cudaStreamWaitEvent(cs, b->ev_tail_done, 0));
     if (n_frames)
         RF_CUDA(h, cudaMemcpy2DAsync(b->d_raw, b->raw_pitch, raw + c.meta_bytes, c.raw_width, b->raw_cols, (size_t)n_frames * c.azimuths,
-                                     cudaMemcpyHostToDevice, h->stream));
+                                     cudaMemcpyHostToDevice, cs));
     if (n_pairs) {
-        RF_CUDA(h, cudaMemcpyAsync(b->d_pair_idx, pair_idx, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-        RF_CUDA(h, cudaMemcpyAsync(b->d_feats, feats, (size_t)n_pairs * b->Kmax * 2 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-        RF_CUDA(h, cudaMemcpyAsync(b->d_counts, feat_counts, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(b->d_pair_idx, pair_idx, (size_t)n_pairs * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        RF_CUDA(h, cudaMemcpyAsync(b->d_feats, feats, (size_t)n_pairs * b->Kmax * 2 * sizeof(float), cudaMemcpyHostToDevice, cs));
+        RF_CUDA(h, cudaMemcpyAsync(b->d_counts, feat_counts, (size_t)n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
         if (prev_pose)
-            RF_CUDA(h, cudaMemcpyAsync(b->d_prev_pose, prev_pose, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            RF_CUDA(h, cudaMemcpyAsync(b->d_prev_pose, prev_pose, (size_t)n_pairs * 3 * sizeof(double), cudaMemcpyHostToDevice, cs));
     }
+    RF_CUDA(h, cudaEventRecord(b->ev_uploaded, cs));
     b->n_frames = n_frames; b->n_pairs = n_pairs; b->has_pose = prev_pose != nullptr;
     return RF_OK;
 }
@@ -205,7 +267,7 @@ int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames,
                     const float* feats, const int32_t* feat_counts, const double* prev_pose) {
     int rc = rf_batch_upload_async(h, b, raw, n_frames, pair_idx, n_pairs, feats, feat_counts, prev_pose);
     if (rc) return rc;
-    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream_copy));
     return RF_OK;
 }
 
@@ -227,27 +289,38 @@ int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
     int stage = 0;
     auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], h->stream); ++stage; };
     int rc;
+    RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_uploaded, 0));
     mark();
     const bool fused = b->fs.cart == nullptr && b->fs.n_levels >= 2;
     if (F && fused) {
-        // interleave (part of the conversion stage) then level 0 + level 1 in one kernel, higher levels after
+        // stage 0: frame interleave; stage 1: level 0 + level 1 in one kernel; stage 2: the higher levels
         if ((rc = rf_launch_interleave(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, F, b->d_rawi))) return rc;
-    } else if (F) {
-        rc = rf_launch_polar2cart_u8(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, 0, b->fs, 0, F,
-                                     b->fs.cart != nullptr);
-        if (rc) return rc;
+        mark();
+        if ((rc = rf_launch_scan_to_l0l1(h, b->d_rawi, b->fs, F))) return rc;
+        mark();
+        if ((rc = rf_launch_pyr_levels(h, b->fs, 2, F))) return rc;
+        mark();
+    } else {
+        // stage 0: polar->Cartesian (f32 + u8 level 0); stage 2: the whole pyramid
+        if (F && (rc = rf_launch_polar2cart_u8(h, b->d_raw, (size_t)c.azimuths * b->raw_pitch, b->raw_pitch, 0, b->fs, 0, F,
+                                                b->fs.cart != nullptr))) return rc;
+        mark();
+        mark();
+        if (F && (rc = rf_launch_pyramid(h, b->fs, 0, F))) return rc;
+        mark();
     }
-    mark();
-    if (F && fused) { if ((rc = rf_launch_scan_to_pyramid(h, b->d_rawi, b->fs, F))) return rc; }
-    else if (F && (rc = rf_launch_pyramid(h, b->fs, 0, F))) return rc;
-    mark();
     if (P) {
+        // the tail of this batch's previous run still reads the track buffers KLT is about to overwrite
+        RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_tail_done, 0));
         if ((rc = rf_launch_klt(h, b->fs, b->fs, b->d_pair_idx, b->d_feats, b->d_counts, K, P, b->d_next, b->d_status,
                                 b->d_err, 1))) return rc;
         mark();
         k_compact_good<<<(P + 3) / 4, 128, 0, h->stream>>>(b->d_feats, b->d_next, b->d_status, b->d_counts, K, P,
                                                            b->d_good_old, b->d_good_new, b->d_good_src, b->d_ngood);
         RF_CHECK_LAUNCH(h);
+        RF_CUDA(h, cudaEventRecord(b->ev_main_done, h->stream));
+        RF_CUDA(h, cudaStreamWaitEvent(b->tail, b->ev_main_done, 0));
+        StreamScope on_tail(h, b->tail);     // everything below runs on the batch's tail stream
         mark();
         uint8_t* d_mask; int mask_stride; int32_t *d_ninl, *d_nodes, *d_cstatus;
         if ((rc = rf_launch_reject(h, b->d_clique_ws, b->d_good_old, b->d_good_new, b->d_ngood, K, P, &d_mask, &mask_stride,
@@ -269,8 +342,10 @@ int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
                                                            b->d_results);
         RF_CHECK_LAUNCH(h);
         mark();
+        RF_CUDA(h, cudaEventRecord(b->ev_tail_done, b->tail));
     } else {
         while (stage <= RF_N_STAGES) mark();
+        RF_CUDA(h, cudaEventRecord(b->ev_main_done, h->stream));
     }
     b->ran_mds = with_mds != 0;
     if (ev) { b->prof_head = (b->prof_head + 1) % RF_PROFILE_RING; if (b->prof_count < RF_PROFILE_RING) b->prof_count++; }
@@ -282,7 +357,8 @@ int rf_batch_stage_times(rf_handle* h, rf_batch* b, float* ms_sum, int cap, int*
     for (int s = 0; s < cap; ++s) ms_sum[s] = 0.f;
     if (n_runs) *n_runs = b->prof_count;
     if (!b->profiling) return RF_OK;
-    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    int rcs = rf_sync_all(h);
+    if (rcs) return rcs;
     for (int r = 0; r < b->prof_count; ++r) {
         const int i = (b->prof_head - 1 - r + 2 * RF_PROFILE_RING) % RF_PROFILE_RING;
         for (int s = 0; s < RF_N_STAGES; ++s) {
@@ -299,16 +375,23 @@ int rf_batch_download_async(rf_handle* h, rf_batch* b, rf_pair_result* results, 
     if (!h || !b || (b->n_pairs > 0 && !results)) return rf_fail(h, RF_E_BADARG, "rf_batch_download: null argument");
     const size_t P = b->n_pairs, K = b->Kmax;
     if (!P) return RF_OK;
-    RF_CUDA(h, cudaMemcpyAsync(results, b->d_results, P * sizeof(rf_pair_result), cudaMemcpyDeviceToHost, h->stream));
-    if (next_xy) RF_CUDA(h, cudaMemcpyAsync(next_xy, b->d_next, P * K * 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (status) RF_CUDA(h, cudaMemcpyAsync(status, b->d_corr, P * K, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(results, b->d_results, P * sizeof(rf_pair_result), cudaMemcpyDeviceToHost, b->tail));
+    if (next_xy) RF_CUDA(h, cudaMemcpyAsync(next_xy, b->d_next, P * K * 2 * sizeof(float), cudaMemcpyDeviceToHost, b->tail));
+    if (status) RF_CUDA(h, cudaMemcpyAsync(status, b->d_corr, P * K, cudaMemcpyDeviceToHost, b->tail));
+    RF_CUDA(h, cudaEventRecord(b->ev_tail_done, b->tail));
     return RF_OK;
 }
 
 int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status) {
     int rc = rf_batch_download_async(h, b, results, next_xy, status);
     if (rc) return rc;
-    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(b->tail));
+    return RF_OK;
+}
+
+int rf_batch_wait(rf_handle* h, rf_batch* b) {
+    if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_wait: null argument");
+    RF_CUDA(h, cudaStreamSynchronize(b->tail));
     return RF_OK;
 }
 
@@ -316,6 +399,7 @@ int rf_batch_klt_status(rf_handle* h, rf_batch* b, uint8_t* klt_status, float* e
     if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_klt_status: null argument");
     const size_t P = b->n_pairs, K = b->Kmax;
     if (!P) return RF_OK;
+    { int rcs = rf_sync_all(h); if (rcs) return rcs; }
     if (klt_status) RF_CUDA(h, cudaMemcpyAsync(klt_status, b->d_status, P * K, cudaMemcpyDeviceToHost, h->stream));
     if (err) RF_CUDA(h, cudaMemcpyAsync(err, b->d_err, P * K * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -333,6 +417,7 @@ int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, 
 
 int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, int what, void* out, int* rows, int* cols) {
     if (!h || !b || frame < 0 || frame >= b->n_frames) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: bad frame");
+    { int rcs = rf_sync_all(h); if (rcs) return rcs; }
     if (what == 0) {
         if (!b->fs.cart) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: batch was created with write_cart_f32 = 0");
         if (rows) *rows = h->n;

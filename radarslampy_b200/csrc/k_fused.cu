@@ -223,10 +223,43 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
     const int ox1 = tx * FT_TW1, oy1 = ty * FT_TH1;
     const uint8_t* __restrict__ s = src + (size_t)frame * src_stride;
-    uint8_t* tb = reinterpret_cast<uint8_t*>(s_tile[warp]);
+    uint32_t* tw = s_tile[warp];
+    const int x0 = 2 * ox1 - 2;
+    // Region word k (k = lane, plus word 32 on lane 0) holds source bytes x0 + 4k .. x0 + 4k + 3 of the row.
+    // Words that lie fully inside the row are cut out of two ALIGNED 32-bit loads with a funnel shift (rows are
+    // only byte-aligned: widths are odd at the higher levels); the few words that straddle an image edge fall
+    // back to REFLECT_101 byte loads.  Aligned loads may run up to 7 bytes past the row end: into the next row,
+    // or into the padding every level allocation carries (rf_frameset_alloc).
+    const int xk = x0 + 4 * lane, xk32 = x0 + 128;
+    const bool in_k = xk >= 0 && xk + 3 < sw, in_32 = xk32 + 3 < sw;
+#pragma unroll 5
     for (int r = 0; r < FT_RH; ++r) {
         const uint8_t* row = s + (size_t)reflect101_safe(2 * oy1 - 2 + r, sh) * sw;
-        for (int c = lane; c < FT_RW; c += 32) tb[r * FT_RW + c] = __ldg(row + reflect101_safe(2 * ox1 - 2 + c, sw));
+        const uint8_t* p = row + x0;
+        const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
+        // (the left-edge tile starts 2 bytes before the row: never read in front of the frame)
+        const uint32_t a = (reinterpret_cast<const uint8_t*>(ap + lane) >= s) ? __ldg(ap + lane) : 0u;
+        const uint32_t b = __ldg(ap + 32 + (lane & 1));                     // words 32, 33 (x0 + 128 > 0 always)
+        uint32_t nxt = __shfl_down_sync(0xffffffffu, a, 1);
+        const uint32_t w32 = __shfl_sync(0xffffffffu, b, 0), w33 = __shfl_sync(0xffffffffu, b, 1);
+        if (lane == 31) nxt = w32;
+        uint32_t v = __funnelshift_r(a, nxt, 8 * m);
+        if (!in_k) {
+            v = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v |= (uint32_t)__ldg(row + reflect101_safe(xk + q, sw)) << (8 * q);
+        }
+        tw[r * FT_RWW + lane] = v;
+        if (lane == 0) {
+            uint32_t v2 = __funnelshift_r(w32, w33, 8 * m);
+            if (!in_32) {
+                v2 = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v2 |= (uint32_t)__ldg(row + reflect101_safe(xk32 + q, sw)) << (8 * q);
+            }
+            tw[r * FT_RWW + 32] = v2;
+        }
     }
     __syncwarp();
     warp_pyr_tile(s_tile[warp], s_hs[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane);
@@ -259,7 +292,7 @@ size_t rf_interleave_words(const rf_handle* h, int max_frames) {
     return (size_t)(2 * ((max_frames + FT_FR - 1) / FT_FR)) * h->cfg.azimuths * rf_fused_wp(h);
 }
 
-int rf_launch_scan_to_pyramid(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames) {
+int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames) {
     if (h->n % 4) return rf_fail(h, RF_E_BADARG, "cartesian size %d is not a multiple of 4", h->n);
     if (fs.n_levels < 2) return rf_fail(h, RF_E_BADARG, "fused image path needs at least two pyramid levels");
     static bool attr_set = false;
@@ -276,7 +309,12 @@ int rf_launch_scan_to_pyramid(rf_handle* h, const uint32_t* d_rawi, const FrameS
     dim3 grd((fs.w[1] + FT_TW1 - 1) / FT_TW1, (fs.h[1] + FT_TH1 - 1) / FT_TH1, (n_frames + FT_FR - 1) / FT_FR);
     k_scan_to_l0l1<<<grd, 256, FT_SMEM_BYTES, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
-    for (int l = 2; l < fs.n_levels; ++l) {
+    return RF_OK;
+}
+
+// levels first_level .. n_levels-1 from their predecessors
+int rf_launch_pyr_levels(rf_handle* h, const FrameSet& fs, int first_level, int n_frames) {
+    for (int l = first_level; l < fs.n_levels; ++l) {
         const int tiles_x = (fs.w[l] + FT_TW1 - 1) / FT_TW1, tiles_y = (fs.h[l] + FT_TH1 - 1) / FT_TH1;
         const int n_tiles = tiles_x * tiles_y * n_frames;
         k_pyr_down_w<<<(n_tiles + 3) / 4, 128, 0, h->stream>>>(fs.lvl[l - 1], fs.lvl_stride[l - 1], fs.w[l - 1], fs.h[l - 1],

@@ -204,7 +204,8 @@ int rf_frameset_alloc(rf_handle* h, FrameSet* fs, int count, bool with_f32) {
         }
         fs->w[l] = w; fs->h[l] = hh;
         fs->lvl_stride[l] = ((size_t)w * hh + 255) & ~(size_t)255;
-        RF_CUDA(h, cudaMalloc(&fs->lvl[l], fs->lvl_stride[l] * count));
+        // + 256: the warp-tile pyrDown reads aligned words that may run a few bytes past the last row
+        RF_CUDA(h, cudaMalloc(&fs->lvl[l], fs->lvl_stride[l] * count + 256));
         nl = l + 1;
     }
     fs->n_levels = nl;

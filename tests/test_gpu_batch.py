@@ -155,9 +155,77 @@ def test_batch_profiling_and_launch_count():
         for _ in range(3):
             b.run_async(with_mds=True)
         fe.sync()
-        assert fe.launch_count() - n0 == 3 * 11      # p2c, 3 pyramid levels, klt, compact, adjacency, clique, kabsch, mds, finish
+        assert fe.launch_count() - n0 == 3 * 11      # interleave, scan->L0+L1, 2 pyrDown levels, klt, compact, adjacency, clique, kabsch, mds, finish
         ms, runs = b.stage_times()
         assert runs == 3 and all(v >= 0 for v in ms.values()) and ms["polar2cart"] > 0 and ms["klt"] > 0
         b.close()
+    finally:
+        fe.close()
+
+
+@pytest.mark.parametrize("range_bins,res,n_frames", [(2025, 0.0432, 3), (1997, 0.0438, 9)])
+def test_fused_image_path_all_levels_bit_exact(range_bins, res, n_frames):
+    """The batch image path (frame interleave -> scan -> level 0 + 1 in one kernel -> warp-tile pyrDown) must give
+    the u8 image and EVERY pyramid level bit-identical to the oracle's warpPolar / truncation / pyrDown chain, for
+    frame counts that are not a multiple of the 8-frame interleave group and for both scan geometries."""
+    from oracle import restate as R
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 256, (n_frames, 400, 3779), dtype=np.uint8)
+    raw[1, :, 11:] = 255                                    # saturated scan: every blend must give exactly 255
+    raw[2, ::2, 11:] = 0                                    # azimuth comb: wrap-around rows and borders
+    fe = _engine(range_bins=range_bins, res=res, max_pairs=2, max_frames=n_frames, max_features=64, f32=0)
+    try:
+        b = fe.new_batch()
+        b.upload(raw, np.zeros((0, 2), np.int32), np.zeros((0, 64, 2), np.float32), np.zeros(0, np.int32))
+        b.run_async()
+        fe.sync()
+        for f in sorted({0, 1, 2, n_frames - 1}):
+            want = R.to_u8(R.warp_polar(R.extract_polar(raw[f], range_bins)))
+            for lvl in range(4):
+                got = b.frame(f, 1 + lvl)
+                assert got.shape == want.shape, (f, lvl)
+                assert np.array_equal(got, want), f"frame {f} level {lvl} differs"
+                want = R.pyr_down(want)
+        b.close()
+    finally:
+        fe.close()
+
+
+def test_two_batches_pipelined_equal_serial():
+    """Two batches alternating on one handle (copy / image+KLT / tail streams overlapping) must return exactly what
+    each returns on its own, run after run (no cross-batch races, deterministic reductions)."""
+    from radarslampy_b200 import synthetic as S
+    res_m, n = 0.0438, 5
+    rb = int(87.5 / res_m)
+    seqs = []
+    for seed in (1, 2):
+        world = S.World(seed=seed)
+        raw, poses = S.make_sequence(n, res_m=res_m, world=world)
+        seqs.append((raw, poses) + tuple(S.sequence_pairs(n, world, poses, res_m, rb, k=150, max_features=192)))
+    fe = _engine(range_bins=rb, res=res_m, max_pairs=n - 1, max_frames=n, max_features=192)
+    try:
+        serial = []
+        for raw, poses, pi, feats, counts in seqs:
+            b = fe.new_batch()
+            r, nx, c = b.track(raw, pi, feats, counts, prev_pose=poses[:-1], with_mds=True)
+            serial.append((r.copy(), nx.copy(), c.copy()))
+            b.close()
+        bs = [fe.new_batch(), fe.new_batch()]
+        outs = [b.alloc_outputs(pinned=True) for b in bs]
+        for it in range(6):
+            k = it % 2
+            raw, poses, pi, feats, counts = seqs[k]
+            bs[k].upload(raw, pi, feats, counts, prev_pose=poses[:-1], sync=False)
+            bs[k].run_async(with_mds=True)
+            bs[k].download(outs[k], sync=False)
+            if it:
+                j = 1 - k
+                bs[j].wait()
+                for name in ("R", "h", "mds_x", "n_good", "n_inliers", "clique_nodes", "status"):
+                    assert np.array_equal(outs[j][0][:n - 1][name], serial[j][0][name]), (it, name)
+                assert np.array_equal(outs[j][1][:n - 1], serial[j][1]) and np.array_equal(outs[j][2][:n - 1], serial[j][2])
+        fe.sync()
+        for b in bs:
+            b.close()
     finally:
         fe.close()
