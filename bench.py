@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--write-f32", type=int, default=0, help="also materialise the f32 Cartesian image per frame")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = 2 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batches", type=int, default=3, help="batches in flight on one handle (pipeline depth)")
     return ap.parse_args()
 
 
@@ -261,9 +262,10 @@ def main():
     cfg.write_cart_f32 = args.write_f32
     stream = torch.cuda.Stream()
     fe = _ffi.RadarFE(cfg, device=local_rank, stream=stream.cuda_stream)
-    # Two batches used alternately (double buffering): the upload of one overlaps the kernels of the other
-    # and the latency-bound clique search of one overlaps the image stage of the next.
-    NB = 2
+    # NB batches used in rotation: the upload of one overlaps the image + KLT kernels of the previous one and the
+    # latency-bound clique search of the one before that.  With two, an upload has to wait for the
+    # tail of the same batch's previous run; three keep all three streams busy.
+    NB = max(1, args.batches)
     batches = [fe.new_batch() for _ in range(NB)]
     # pinned host staging (what a caller streaming scans from disk would fill); everything that is uploaded
     # asynchronously must be page-locked or the copy call blocks the host
@@ -329,19 +331,19 @@ def main():
         b.set_profiling(False)
 
     def e2e_loop(n):
-        prev = None
+        # NB steps in flight: a batch's poses are read (and gathered) right before that batch is re-used
         for i in range(n):
             k = i % NB
             b = batches[k]
+            if i >= NB:
+                b.wait()
+                gather_poses(outs[k][0][:P])
             upload(b)                                   # H2D of every scan of the step (copy stream)
             b.run_async(with_mds=with_mds)
             b.download(outs[k], sync=False, want_tracks=False)   # D2H of the poses (tail stream)
-            if prev is not None:                        # the caller reads the poses of the previous step
-                batches[prev].wait()
-                gather_poses(outs[prev][0][:P])
-            prev = k
-        batches[prev].wait()
-        gather_poses(outs[prev][0][:P])
+        for i in range(max(0, n - NB), n):
+            batches[i % NB].wait()
+            gather_poses(outs[i % NB][0][:P])
 
     e2e_loop(max(args.warmup, NB))
     barrier()

@@ -1,22 +1,33 @@
 // k_fused.cu — the batch image path: raw scans -> u8 Cartesian level 0 + LK pyramid, for many
 // frames at once.  Bit-identical to k_polar2cart + k_pyr_down (k_image.cu), restructured around
-// what bounds that pair on B200: issue slots, not HBM.
+// what bounds that pair on B200: issue slots and L1 wavefronts, not HBM.
 //
 // Replaces (reference file:line), for a whole batch of frames:
 //   parseData.py:17-53,100-135   extractDataFromRadarImage + convertPolarImageToCartesian (cv2.warpPolar)
 //   getTransformKLT.py:356-357   (img * 255).astype(np.uint8)
 //   cv2.buildOpticalFlowPyramid  (pyrDown 5x5, REFLECT_101) inside calcOpticalFlowPyrLK (getTransformKLT.py:359)
 //
-//   k_interleave     raw [F][A][pitch] u8 -> [F/4][A][Wp] words, byte f of a word = frame 4g+f.
-//                    One 32-bit gather then serves a bilinear tap of FOUR frames.
-//   k_build_map2     per-pixel geometry record (8 B): tap word offset + 5-bit fractions + tap
+//   k_interleave16   raw [F][A][pitch] u8 -> [F/16][A][Wp] uint4, byte f of a sample = frame 16g+f.
+//                    One 128-bit gather then serves a bilinear tap of SIXTEEN frames.
+//   k_build_map2     per-pixel geometry record (8 B): tap sample offset + 5-bit fractions + tap
 //                    validity, derived once per handle from the fixed-point inverse map.
-//   k_scan_to_l0l1   CTA = 128x32 level-0 pixels (+ pyrDown halo) x 8 frames.  Each thread decodes
-//                    the geometry of a pixel ONCE and applies it to 8 frames; u8 -> f32/255 goes
-//                    through a bank-replicated shared-memory table (exact IEEE quotient, no
-//                    conflicts); the level-0 tile never leaves shared memory before level 1 is
+//   k_scan16_to_l0l1 CTA = 128x32 level-0 pixels (+ pyrDown halo) x 16 frames, one pixel per lane
+//                    (neighbouring lanes gather neighbouring samples).  The u8 result is
+//                    floor(V / 1024), V = sum of tap byte x 10-bit integer weight, whenever V is not
+//                    a multiple of 1024: the f32 chain cv2 evaluates is then within 1.1e-4 of V/1024
+//                    and cannot cross an integer (see `exactness` below).  V is formed for two frames
+//                    per instruction in packed 16-bit lanes (horizontal) + one dp2a per frame
+//                    (vertical).  The 1-3 % of (pixel, frame) pairs with V = 0 mod 1024 re-run cv2's
+//                    exact f32 chain.  The level-0 tile never leaves shared memory before level 1 is
 //                    built from it (dp4a horizontal taps, packed-u16 vertical taps).
 //   k_pyr_down_w     the same warp-tile pyrDown for levels >= 2, input from global memory.
+//
+// exactness.  cv2: out = ((S00*w00 + S01*w01) + S10*w10) + S11*w11 with S = fl(b / 255), w = m / 1024
+// (m = (32 - fy | fy)(32 - fx | fx), exact), every product and sum rounded to f32, then
+// u8 = trunc(fl(out * 255)).  Nine roundings of relative size 2^-24 on values <= 1, times 255:
+// |fl(out*255) - V/1024| < 1.1e-4 < 1/1024.  V/1024 has a fractional part that is a multiple of 1/1024,
+// so unless that part is 0 the truncation of both is the same integer.  (tests: bit-exact against the
+// plain-C restatement of cv2 on real Oxford scans, where 2.8 % of the pixels take the exact path.)
 #include "common.cuh"
 
 #define FT_TW1 64
@@ -24,11 +35,10 @@
 #define FT_RW (2 * FT_TW1 + 4)   // 132 region columns: level-0 x in [2*ox1 - 2, 2*ox1 + 130)
 #define FT_RH (2 * FT_TH1 + 3)   // 35 region rows:     level-0 y in [2*oy1 - 2, 2*oy1 + 33)
 #define FT_RWW (FT_RW / 4)       // 33 words per region row
-#define FT_FR 8                  // frames per CTA (two interleave groups)
-#define FT_LUT_WORDS (256 * 32)
+#define FT_FR 16                 // frames per CTA (one interleave group)
 #define FT_TILE_WORDS (FT_RH * FT_RWW)
-#define FT_HS_WORDS (FT_RH * 32)
-#define FT_SMEM_BYTES ((FT_LUT_WORDS + FT_FR * FT_TILE_WORDS + 8 * FT_HS_WORDS) * 4)
+#define FT_TILE_BYTES (FT_TILE_WORDS * 4)
+#define FT_SMEM_BYTES ((FT_FR * FT_TILE_WORDS + 8 * 64) * 4)   // tiles + 8 per-warp deferred lists
 
 __device__ __forceinline__ int reflect101_safe(int p, int len) {
     p = min(max(p, -(len - 1)), 2 * len - 2);
@@ -36,32 +46,38 @@ __device__ __forceinline__ int reflect101_safe(int p, int len) {
 }
 
 // ------------------------------------------------------------------------------------
-// frame interleave: 4 frames -> one word per polar sample
+// frame interleave: 16 frames -> one uint4 per polar sample
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_interleave(const uint8_t* __restrict__ raw, size_t frame_stride, int pitch, int A, int W, int n_frames,
-             uint32_t* __restrict__ out, int Wp) {
+k_interleave16(const uint8_t* __restrict__ raw, size_t frame_stride, int pitch, int A, int W, int n_frames,
+               uint4* __restrict__ out, int Wp) {
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 samples
     const int a = blockIdx.y, g = blockIdx.z;
     if (x4 * 4 >= Wp) return;
-    uint32_t w[4];
+    uint32_t o[4][4];   // o[k][c] = sample 4*x4 + k, frames 4c .. 4c+3
 #pragma unroll
-    for (int f = 0; f < 4; ++f) {
-        const int fr = 4 * g + f;
-        // raw rows are 16-byte aligned and hold only the power bins; columns >= W are padding
-        w[f] = (fr < n_frames && x4 * 4 < pitch)
-                   ? __ldg(reinterpret_cast<const uint32_t*>(raw + (size_t)fr * frame_stride + (size_t)a * pitch) + x4) : 0u;
+    for (int c = 0; c < 4; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const int fr = FT_FR * g + 4 * c + f;
+            // raw rows are 16-byte aligned and hold only the power bins; columns >= W are padding
+            w[f] = (fr < n_frames && x4 * 4 < pitch)
+                       ? __ldg(reinterpret_cast<const uint32_t*>(raw + (size_t)fr * frame_stride + (size_t)a * pitch) + x4) : 0u;
+        }
+        // 4x4 byte transpose: t[k] = (w0.bk, w1.bk, w2.bk, w3.bk)
+        const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[0], w[1], 0x7362);
+        const uint32_t t2 = __byte_perm(w[2], w[3], 0x5140), t3 = __byte_perm(w[2], w[3], 0x7362);
+        const uint32_t s0 = __byte_perm(t0, t2, 0x5410), s1 = __byte_perm(t0, t2, 0x7632);
+        const uint32_t s2 = __byte_perm(t1, t3, 0x5410), s3 = __byte_perm(t1, t3, 0x7632);
+        o[0][c] = s0; o[1][c] = s1; o[2][c] = s2; o[3][c] = s3;
     }
-    // 4x4 byte transpose: out[k] = (w0.bk, w1.bk, w2.bk, w3.bk)
-    const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[0], w[1], 0x7362);
-    const uint32_t t2 = __byte_perm(w[2], w[3], 0x5140), t3 = __byte_perm(w[2], w[3], 0x7362);
-    uint4 o;
-    o.x = __byte_perm(t0, t2, 0x5410); o.y = __byte_perm(t0, t2, 0x7632);
-    o.z = __byte_perm(t1, t3, 0x5410); o.w = __byte_perm(t1, t3, 0x7632);
     // samples beyond the used range read as 0 (they only ever meet zero weights, keep them defined)
     const int x = 4 * x4;
-    if (x + 0 >= W) o.x = 0; if (x + 1 >= W) o.y = 0; if (x + 2 >= W) o.z = 0; if (x + 3 >= W) o.w = 0;
-    reinterpret_cast<uint4*>(out + ((size_t)g * A + a) * Wp)[x4] = o;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4* q = out + ((size_t)g * A + a) * Wp + x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = (x + k >= W) ? z : make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -88,44 +104,49 @@ k_build_map2(const uint32_t* __restrict__ map, size_t count, int A, int W, int W
 }
 
 // ------------------------------------------------------------------------------------
-// warp-level pyrDown of one tile held in shared memory.
+// warp-level pyrDown of one tile held in shared memory (optionally also the level-0 store of it).
 //   tile : [FT_RH][FT_RWW] words = 35 x 132 source bytes; byte (i, j) = source (2*oy1 - 2 + i, 2*ox1 - 2 + j)
-//   hs   : [FT_RH][32] words scratch (two u16 horizontal sums per word)
-// Writes the 16 x 64 destination tile at (oy1, ox1).
+// Lane k owns destination columns ox1 + 2k, 2k + 1: their horizontal 1-4-6-4-1 sums (two u16 per word) of
+// the last five source rows roll through registers, every second row emits one destination row.
+// Writes the 16 x 64 destination tile at (oy1, ox1); with L0, also source rows 2..33 / bytes 2..129 of the
+// tile to the level-0 image (n x n) as 32 aligned words per row.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, uint32_t* __restrict__ hs,
-                                              uint8_t* __restrict__ dst, int dw, int dh, int ox1, int oy1, int lane) {
-#pragma unroll 5
-    for (int r = 0; r < FT_RH; ++r) {
-        const uint32_t w0 = tile[r * FT_RWW + lane], w1 = tile[r * FT_RWW + lane + 1];
-        const uint32_t he = __dp4a(w1, 0x00000001u, __dp4a(w0, 0x04060401u, 0u));   // columns 4k .. 4k+4
-        const uint32_t ho = __dp4a(w1, 0x00010406u, __dp4a(w0, 0x04010000u, 0u));   // columns 4k+2 .. 4k+6
-        hs[r * 32 + lane] = he | (ho << 16);
-    }
-    __syncwarp();
+template <bool L0>
+__device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
+                                              int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
     const int x = ox1 + 2 * lane;
     const bool even_pitch = (dw & 1) == 0;
-#pragma unroll 4
-    for (int r1 = 0; r1 < FT_TH1; ++r1) {
-        const uint32_t* p = hs + (2 * r1) * 32 + lane;
-        // both halves stay below 2^16 (255 * 256 + 128), so the packed sum never carries across
-        const uint32_t s = p[0] + 4u * p[32] + 6u * p[64] + 4u * p[96] + p[128] + 0x00800080u;
-        const int y = oy1 + r1;
-        if (y < dh && x < dw) {
-            const uint32_t lo = (s >> 8) & 0xFFu, hi = s >> 24;
-            uint8_t* q = dst + (size_t)y * dw + x;
-            if (even_pitch) *reinterpret_cast<uint16_t*>(q) = (uint16_t)(lo | (hi << 8));
-            else { q[0] = (uint8_t)lo; if (x + 1 < dw) q[1] = (uint8_t)hi; }
+    const bool x_ok = x < dw, x0_ok = 2 * ox1 + 4 * lane < n;
+    uint32_t h[5];
+#pragma unroll
+    for (int r = 0; r < FT_RH; ++r) {
+        const uint32_t w0 = tile[r * FT_RWW + lane], w1 = tile[r * FT_RWW + lane + 1];
+        if (L0 && r >= 2 && r < 2 + 2 * FT_TH1) {
+            const int y0 = 2 * oy1 + r - 2;
+            if (y0 < n && x0_ok) *reinterpret_cast<uint32_t*>(l0 + (size_t)y0 * n + 2 * ox1 + 4 * lane) = __funnelshift_r(w0, w1, 16);
+        }
+        const uint32_t he = __dp4a(w1, 0x00000001u, __dp4a(w0, 0x04060401u, 0u));   // columns 4k .. 4k+4
+        const uint32_t ho = __dp4a(w1, 0x00010406u, __dp4a(w0, 0x04010000u, 0u));   // columns 4k+2 .. 4k+6
+        h[r % 5] = he | (ho << 16);
+        if (r >= 4 && (r & 1) == 0) {
+            // both halves stay below 2^16 (255 * 256 + 128), so the packed sum never carries across
+            const uint32_t s = h[(r - 4) % 5] + 4u * h[(r - 3) % 5] + 6u * h[(r - 2) % 5] + 4u * h[(r - 1) % 5] + h[r % 5] + 0x00800080u;
+            const int y = oy1 + (r - 4) / 2;
+            if (y < dh && x_ok) {
+                const uint32_t lo = (s >> 8) & 0xFFu, hi = s >> 24;
+                uint8_t* q = dst + (size_t)y * dw + x;
+                if (even_pitch) *reinterpret_cast<uint16_t*>(q) = (uint16_t)(lo | (hi << 8));
+                else { q[0] = (uint8_t)lo; if (x + 1 < dw) q[1] = (uint8_t)hi; }
+            }
         }
     }
-    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------
 // raw (interleaved) -> level 0 + level 1
 // ------------------------------------------------------------------------------------
 struct FusedArgs {
-    const uint32_t* rawi; size_t group_stride;   // words per interleave group plane (A * Wp)
+    const uint4* rawi; size_t group_stride;   // samples per interleave group plane (A * Wp)
     int Wp, A;
     const uint2* map2; int n;
     uint8_t* l0; size_t l0_stride;
@@ -133,78 +154,134 @@ struct FusedArgs {
     int n_frames;
 };
 
-__device__ __forceinline__ float lut_tap(const float* __restrict__ lut_lane, uint32_t t, int f) {
-    return lut_lane[((t >> (8 * f)) & 0xFFu) << 5];
+__device__ float g_lut255[256];   // fl(b / 255), parseData.py:43 (filled by k_build_lut at handle creation)
+
+__global__ void k_build_lut() { g_lut255[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f); }
+
+// V' = 2^14 * V (V = the 10-bit fixed-point bilinear sum) for the four frames of one tap word.
+//   c0r0, c0r1 / c1r0, c1r1   left / right column taps of the two source rows (byte f = frame 4q + f)
+//   ayw = (32 - fy) << 10 | fy << 26     cx0 = (32 - fx) << 4, cx1 = fx << 4
+// Vertical blend first: one PRMT pairs the two rows of a column for two frames, one dp2a (u16 weights x u8
+// samples) per frame and column; then the horizontal blend, one IMUL + IMAD per frame.  V' <= 0xFF000000: the
+// u8 result is its top byte and V is a multiple of 1024 exactly when the low 24 bits are 0.  Such frames
+// (V != 0) are flagged in `need` and redone with cv2's f32 chain.
+#define FT_QUAD(q, c0r0, c0r1, c1r0, c1r1)                                                                        \
+    {                                                                                                             \
+        const uint32_t pa0 = __byte_perm((c0r0), (c0r1), 0x5140), pb0 = __byte_perm((c0r0), (c0r1), 0x7362);      \
+        const uint32_t pa1 = __byte_perm((c1r0), (c1r1), 0x5140), pb1 = __byte_perm((c1r0), (c1r1), 0x7362);      \
+        const uint32_t v4[4] = {__dp2a_lo(ayw, pa0, 0u) * cx0 + __dp2a_lo(ayw, pa1, 0u) * cx1,                    \
+                                __dp2a_hi(ayw, pa0, 0u) * cx0 + __dp2a_hi(ayw, pa1, 0u) * cx1,                    \
+                                __dp2a_lo(ayw, pb0, 0u) * cx0 + __dp2a_lo(ayw, pb1, 0u) * cx1,                    \
+                                __dp2a_hi(ayw, pb0, 0u) * cx0 + __dp2a_hi(ayw, pb1, 0u) * cx1};                   \
+        _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                                           \
+            if ((v4[f] & 0x00FFFFFFu) == 0u && v4[f] != 0u) need |= 1u << (4 * (q) + f);                          \
+            tb[(4 * (q) + f) * FT_TILE_BYTES] = (uint8_t)(v4[f] >> 24);                                           \
+        }                                                                                                         \
+    }
+
+struct PixelGeom {
+    const uint4 *p0, *p1;      // sample (iy, ix) and (iy + 1, ix) of the interleave group
+    unsigned fx, fy, fl;       // 5-bit fractions, tap validity (bit 0: 00, 1: 01, 2: 10, 3: 11)
+};
+
+__device__ __forceinline__ PixelGeom pixel_geom(const FusedArgs& a, const uint4* __restrict__ src, int item, int ox1, int oy1) {
+    const int ry = item / FT_RW, rx = item - ry * FT_RW;
+    const int gy = reflect101_safe(2 * oy1 - 2 + ry, a.n), gx = reflect101_safe(2 * ox1 - 2 + rx, a.n);
+    const uint2 m = __ldg(a.map2 + (size_t)gy * a.n + gx);
+    PixelGeom g;
+    g.fx = m.y & 31u; g.fy = (m.y >> 5) & 31u; g.fl = (m.y >> 10) & 15u;
+    g.p0 = src + m.x;
+    g.p1 = g.p0 + a.Wp - ((m.y & 0x4000u) ? (unsigned)a.A * (unsigned)a.Wp : 0u);
+    return g;
 }
 
-__global__ void __launch_bounds__(256, 2) k_scan_to_l0l1(const FusedArgs a) {
-    extern __shared__ uint32_t smem[];
-    float* lut = reinterpret_cast<float*>(smem);             // [256][32]: entry b replicated once per bank
-    uint32_t* tiles = smem + FT_LUT_WORDS;                   // [FT_FR][FT_RH][FT_RWW]
-    uint32_t* hs_all = tiles + FT_FR * FT_TILE_WORDS;        // [8 warps][FT_RH][32]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < FT_LUT_WORDS; i += 256) lut[i] = __fdiv_rn((float)(i >> 5), 255.0f);   // parseData.py:43
-    __syncthreads();
-    const float* lut_lane = lut + lane;
-    const int ox1 = blockIdx.x * FT_TW1, oy1 = blockIdx.y * FT_TH1;
-    const int f0 = blockIdx.z * FT_FR;
-    const uint32_t* __restrict__ g0 = a.rawi + (size_t)(2 * blockIdx.z) * a.group_stride;
-    const uint32_t* __restrict__ g1 = g0 + a.group_stride;
-    const unsigned AWp = (unsigned)a.A * (unsigned)a.Wp;
-    const int n = a.n;
+// cv2's f32 chain for one (pixel, frame): entry = item | frame << 13
+__device__ __forceinline__ void exact_pixel(const FusedArgs& a, const uint4* __restrict__ src, uint32_t entry, int ox1, int oy1,
+                                            uint8_t* __restrict__ tile_bytes) {
+    const int item = entry & 0x1FFF, f = entry >> 13;
+    const PixelGeom g = pixel_geom(a, src, item, ox1, oy1);
+    // (1 - fy)(1 - fx) etc. are exact multiples of 2^-10, as cv2 computes them; a tap outside the source has weight 0
+    const float w00 = (g.fl & 1u) ? (float)((32u - g.fy) * (32u - g.fx)) * 0.0009765625f : 0.0f;
+    const float w01 = (g.fl & 2u) ? (float)((32u - g.fy) * g.fx) * 0.0009765625f : 0.0f;
+    const float w10 = (g.fl & 4u) ? (float)(g.fy * (32u - g.fx)) * 0.0009765625f : 0.0f;
+    const float w11 = (g.fl & 8u) ? (float)(g.fy * g.fx) * 0.0009765625f : 0.0f;
+    const uint8_t* b0 = reinterpret_cast<const uint8_t*>(g.p0) + f;
+    const uint8_t* b1 = reinterpret_cast<const uint8_t*>(g.p1) + f;
+    float acc = __fmul_rn(g_lut255[__ldg(b0)], w00);
+    acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b0 + 16)], w01));
+    acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1)], w10));
+    acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1 + 16)], w11));
+    // (img * 255).astype(uint8): f32 product, truncation; 2^23 + x rounded toward zero keeps floor(x) in the low byte
+    tile_bytes[f * FT_TILE_BYTES + item] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(acc, 255.0f), 8388608.0f));
+}
 
-    for (int item = tid; item < FT_RH * FT_RWW; item += 256) {
-        const int ry = item / FT_RWW, rx4 = item - ry * FT_RWW;
-        const int gy = reflect101_safe(2 * oy1 - 2 + ry, n);
-        uint32_t word[FT_FR];
+#define FT_LIST_CAP 64   // deferred (pixel, frame) entries per warp
+
+__global__ void __launch_bounds__(256, 3) k_scan16_to_l0l1(const FusedArgs a) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* tiles = smem;                                  // [FT_FR][FT_RH][FT_RWW]
+    uint32_t* lists = tiles + FT_FR * FT_TILE_WORDS;         // [8 warps][FT_LIST_CAP]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // frame group fastest: the CTAs resident at any time share one neighbourhood of the geometry table
+    const int ox1 = blockIdx.y * FT_TW1, oy1 = blockIdx.z * FT_TH1;
+    const int f0 = blockIdx.x * FT_FR;
+    const uint4* __restrict__ src = a.rawi + (size_t)blockIdx.x * a.group_stride;
+    uint8_t* tile_bytes = reinterpret_cast<uint8_t*>(tiles);
+    uint32_t* list = lists + warp * FT_LIST_CAP;
+    int cnt = 0;                                             // warp-uniform fill of `list`
+    const unsigned lt = (1u << lane) - 1u;
+
+#pragma unroll 1
+    for (int it = 0; it < (FT_RH * FT_RW + 255) / 256; ++it) {
+        const int item = it * 256 + tid;
+        uint32_t need = 0u;
+        if (item < FT_RH * FT_RW) {
+            const PixelGeom g = pixel_geom(a, src, item, ox1, oy1);
+            uint8_t* tb = tile_bytes + item;
+            if (g.fl == 0u) {   // beyond the last range bin (image corners): WARP_FILL_OUTLIERS
 #pragma unroll
-        for (int f = 0; f < FT_FR; ++f) word[f] = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int gx = reflect101_safe(2 * ox1 - 2 + 4 * rx4 + k, n);
-            const uint2 m = __ldg(a.map2 + (size_t)gy * n + gx);
-            const int fx = m.y & 31, fy = (m.y >> 5) & 31;
-            const unsigned fl = m.y >> 10;
-            const unsigned o0 = m.x, o1 = m.x + (unsigned)a.Wp - ((fl & 16u) ? AWp : 0u);
-            // (1 - fy)(1 - fx) etc. are exact multiples of 2^-10, as cv2 computes them
-            const float w00 = (fl & 1u) ? (float)((32 - fy) * (32 - fx)) * 0.0009765625f : 0.0f;
-            const float w01 = (fl & 2u) ? (float)((32 - fy) * fx) * 0.0009765625f : 0.0f;
-            const float w10 = (fl & 4u) ? (float)(fy * (32 - fx)) * 0.0009765625f : 0.0f;
-            const float w11 = (fl & 8u) ? (float)(fy * fx) * 0.0009765625f : 0.0f;
-            const uint32_t t00[2] = {__ldg(g0 + o0), __ldg(g1 + o0)}, t01[2] = {__ldg(g0 + o0 + 1), __ldg(g1 + o0 + 1)};
-            const uint32_t t10[2] = {__ldg(g0 + o1), __ldg(g1 + o1)}, t11[2] = {__ldg(g0 + o1 + 1), __ldg(g1 + o1 + 1)};
-#pragma unroll
-            for (int f = 0; f < FT_FR; ++f) {
-                const int g = f >> 2, b = f & 3;
-                float acc = __fmul_rn(lut_tap(lut_lane, t00[g], b), w00);
-                acc = __fadd_rn(acc, __fmul_rn(lut_tap(lut_lane, t01[g], b), w01));
-                acc = __fadd_rn(acc, __fmul_rn(lut_tap(lut_lane, t10[g], b), w10));
-                acc = __fadd_rn(acc, __fmul_rn(lut_tap(lut_lane, t11[g], b), w11));
-                // (img * 255).astype(uint8): f32 product, truncation; 2^23 + x rounded toward zero keeps floor(x) in the low byte
-                const uint32_t u = __float_as_uint(__fadd_rz(__fmul_rn(acc, 255.0f), 8388608.0f));
-                word[f] = __byte_perm(word[f], u, k == 0 ? 0x3214 : k == 1 ? 0x3240 : k == 2 ? 0x3410 : 0x4210);
+                for (int f = 0; f < FT_FR; ++f) tb[f * FT_TILE_BYTES] = 0;
+            } else {
+                uint4 T00 = __ldg(g.p0), T01 = __ldg(g.p0 + 1), T10 = __ldg(g.p1), T11 = __ldg(g.p1 + 1);
+                if (g.fl != 15u) {   // a tap outside the source contributes 0
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    if (!(g.fl & 1u)) T00 = z; if (!(g.fl & 2u)) T01 = z; if (!(g.fl & 4u)) T10 = z; if (!(g.fl & 8u)) T11 = z;
+                }
+                const uint32_t ayw = ((32u - g.fy) << 10) | (g.fy << 26), cx0 = (32u - g.fx) << 4, cx1 = g.fx << 4;
+                FT_QUAD(0, T00.x, T10.x, T01.x, T11.x)
+                FT_QUAD(1, T00.y, T10.y, T01.y, T11.y)
+                FT_QUAD(2, T00.z, T10.z, T01.z, T11.z)
+                FT_QUAD(3, T00.w, T10.w, T01.w, T11.w)
             }
         }
-#pragma unroll
-        for (int f = 0; f < FT_FR; ++f) tiles[f * FT_TILE_WORDS + item] = word[f];
-    }
-    __syncthreads();
-
-    // one warp per frame from here on
-    const int frame = f0 + warp;
-    if (frame >= a.n_frames) return;
-    const uint32_t* tile = tiles + warp * FT_TILE_WORDS;
-    {   // level 0: region rows 2..33, region bytes 2..129 -> 32 aligned words per row
-        uint8_t* l0 = a.l0 + (size_t)frame * a.l0_stride;
-        const int x = 2 * ox1 + 4 * lane;
-#pragma unroll 4
-        for (int r = 0; r < 2 * FT_TH1; ++r) {
-            const int y = 2 * oy1 + r;
-            const uint32_t lo = tile[(r + 2) * FT_RWW + lane], hi = tile[(r + 2) * FT_RWW + lane + 1];
-            if (y < n && x < n) *reinterpret_cast<uint32_t*>(l0 + (size_t)y * n + x) = __funnelshift_r(lo, hi, 16);
+        // Defer the flagged frames: lanes append (pixel, frame) entries to the warp's list, and whenever 32 are
+        // waiting the whole warp redoes them with the f32 chain, one entry per lane (no divergence).
+        unsigned pending;
+        while ((pending = __ballot_sync(0xffffffffu, need != 0u)) != 0u) {
+            if (need) {
+                list[cnt + __popc(pending & lt)] = (uint32_t)item | ((uint32_t)(__ffs(need) - 1) << 13);
+                need &= need - 1u;
+            }
+            cnt += __popc(pending);
+            __syncwarp();
+            if (cnt >= 32) {
+                cnt -= 32;
+                exact_pixel(a, src, list[cnt + lane], ox1, oy1, tile_bytes);
+                __syncwarp();
+            }
         }
     }
-    warp_pyr_tile(tile, hs_all + warp * FT_HS_WORDS, a.l1 + (size_t)frame * a.l1_stride, a.w1, a.h1, ox1, oy1, lane);
+    if (lane < cnt) exact_pixel(a, src, list[lane], ox1, oy1, tile_bytes);
+    __syncthreads();
+
+    // one warp per frame from here on (two frames per warp): level-0 store + level 1 from the shared-memory tile
+#pragma unroll 1
+    for (int fw = warp; fw < FT_FR; fw += 8) {
+        const int frame = f0 + fw;
+        if (frame >= a.n_frames) break;
+        warp_pyr_tile<true>(tiles + fw * FT_TILE_WORDS, a.l1 + (size_t)frame * a.l1_stride, a.w1, a.h1, ox1, oy1, lane,
+                            a.l0 + (size_t)frame * a.l0_stride, a.n);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -215,7 +292,6 @@ __global__ void __launch_bounds__(128)
 k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh, uint8_t* __restrict__ dst,
              size_t dst_stride, int dw, int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
     __shared__ uint32_t s_tile[4][FT_TILE_WORDS];
-    __shared__ uint32_t s_hs[4][FT_HS_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 4 + warp;
     if (t >= n_tiles) return;
@@ -262,7 +338,7 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
         }
     }
     __syncwarp();
-    warp_pyr_tile(s_tile[warp], s_hs[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane);
+    warp_pyr_tile<false>(s_tile[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -275,21 +351,24 @@ int rf_launch_build_map2(rf_handle* h) {
     k_build_map2<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->map, count, h->cfg.azimuths, h->cfg.range_bins,
                                                                           rf_fused_wp(h), h->map2);
     RF_CHECK_LAUNCH(h);
+    k_build_lut<<<1, 256, 0, h->stream>>>();
+    RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
 
 // d_raw: frames of [A][pitch] power bins (no metadata), pitch a multiple of 16 and >= Wp
 int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out) {
     const int Wp = rf_fused_wp(h);
-    const int groups = 2 * ((n_frames + FT_FR - 1) / FT_FR);   // zero-filled up to a multiple of 8 frames
+    const int groups = (n_frames + FT_FR - 1) / FT_FR;   // zero-filled up to a multiple of 16 frames
     dim3 grd((Wp / 4 + 255) / 256, h->cfg.azimuths, groups);
-    k_interleave<<<grd, 256, 0, h->stream>>>(d_raw, frame_stride, pitch, h->cfg.azimuths, h->cfg.range_bins, n_frames, d_out, Wp);
+    k_interleave16<<<grd, 256, 0, h->stream>>>(d_raw, frame_stride, pitch, h->cfg.azimuths, h->cfg.range_bins, n_frames,
+                                               reinterpret_cast<uint4*>(d_out), Wp);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
 
 size_t rf_interleave_words(const rf_handle* h, int max_frames) {
-    return (size_t)(2 * ((max_frames + FT_FR - 1) / FT_FR)) * h->cfg.azimuths * rf_fused_wp(h);
+    return (size_t)((max_frames + FT_FR - 1) / FT_FR) * h->cfg.azimuths * rf_fused_wp(h) * 4;
 }
 
 int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames) {
@@ -297,17 +376,17 @@ int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet&
     if (fs.n_levels < 2) return rf_fail(h, RF_E_BADARG, "fused image path needs at least two pyramid levels");
     static bool attr_set = false;
     if (!attr_set) {
-        RF_CUDA(h, cudaFuncSetAttribute(k_scan_to_l0l1, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+        RF_CUDA(h, cudaFuncSetAttribute(k_scan16_to_l0l1, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
         attr_set = true;
     }
     FusedArgs a;
-    a.rawi = d_rawi; a.Wp = rf_fused_wp(h); a.A = h->cfg.azimuths; a.group_stride = (size_t)a.A * a.Wp;
+    a.rawi = reinterpret_cast<const uint4*>(d_rawi); a.Wp = rf_fused_wp(h); a.A = h->cfg.azimuths; a.group_stride = (size_t)a.A * a.Wp;
     a.map2 = h->map2; a.n = h->n;
     a.l0 = fs.lvl[0]; a.l0_stride = fs.lvl_stride[0];
     a.l1 = fs.lvl[1]; a.l1_stride = fs.lvl_stride[1]; a.w1 = fs.w[1]; a.h1 = fs.h[1];
     a.n_frames = n_frames;
-    dim3 grd((fs.w[1] + FT_TW1 - 1) / FT_TW1, (fs.h[1] + FT_TH1 - 1) / FT_TH1, (n_frames + FT_FR - 1) / FT_FR);
-    k_scan_to_l0l1<<<grd, 256, FT_SMEM_BYTES, h->stream>>>(a);
+    dim3 grd((n_frames + FT_FR - 1) / FT_FR, (fs.w[1] + FT_TW1 - 1) / FT_TW1, (fs.h[1] + FT_TH1 - 1) / FT_TH1);
+    k_scan16_to_l0l1<<<grd, 256, FT_SMEM_BYTES, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }

@@ -2,6 +2,8 @@
 many independent pairs) against the reference-generated goldens and against the reference's
 own library calls (oracle/ref_pipeline.py) on seeded synthetic Oxford-shaped scans.
 Tolerances (north_star): identical status / clique, tracks <= 0.02 px, pose <= 1e-4 m, 1e-5 rad."""
+import os
+
 import numpy as np
 import pytest
 
@@ -163,23 +165,31 @@ def test_batch_profiling_and_launch_count():
         fe.close()
 
 
-@pytest.mark.parametrize("range_bins,res,n_frames", [(2025, 0.0432, 3), (1997, 0.0438, 9)])
+@pytest.mark.parametrize("range_bins,res,n_frames", [(2025, 0.0432, 3), (1997, 0.0438, 9), (2025, 0.0432, 18)])
 def test_fused_image_path_all_levels_bit_exact(range_bins, res, n_frames):
     """The batch image path (frame interleave -> scan -> level 0 + 1 in one kernel -> warp-tile pyrDown) must give
     the u8 image and EVERY pyramid level bit-identical to the oracle's warpPolar / truncation / pyrDown chain, for
-    frame counts that are not a multiple of the 8-frame interleave group and for both scan geometries."""
+    frame counts that are not a multiple of the 16-frame interleave group and for both scan geometries.  The kernel
+    takes an integer shortcut wherever the fixed-point bilinear sum is not a multiple of 1024 and cv2's f32 chain
+    elsewhere: the saturated / constant / real scans below are the cases where the second path dominates."""
     from oracle import restate as R
     rng = np.random.default_rng(11)
     raw = rng.integers(0, 256, (n_frames, 400, 3779), dtype=np.uint8)
     raw[1, :, 11:] = 255                                    # saturated scan: every blend must give exactly 255
     raw[2, ::2, 11:] = 0                                    # azimuth comb: wrap-around rows and borders
+    if n_frames > 4:
+        raw[4, :, 11:] = rng.integers(0, 256, (400, 1), dtype=np.uint8)      # constant along range: equal tap pairs
+        raw[5, :, 11:] = rng.integers(0, 4, (400, 3768), dtype=np.uint8)     # tiny values: many zero sums
+    if n_frames > 17:
+        tiny = np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_frames.npz"))
+        raw[3], raw[16], raw[17] = tiny["raw_0"], tiny["raw_1"], 77          # real Oxford scans; a constant scan
     fe = _engine(range_bins=range_bins, res=res, max_pairs=2, max_frames=n_frames, max_features=64, f32=0)
     try:
         b = fe.new_batch()
         b.upload(raw, np.zeros((0, 2), np.int32), np.zeros((0, 64, 2), np.float32), np.zeros(0, np.int32))
         b.run_async()
         fe.sync()
-        for f in sorted({0, 1, 2, n_frames - 1}):
+        for f in sorted({0, 1, 2, n_frames - 1} | ({3, 4, 5} if n_frames > 5 else set()) | ({16} if n_frames > 16 else set())):
             want = R.to_u8(R.warp_polar(R.extract_polar(raw[f], range_bins)))
             for lvl in range(4):
                 got = b.frame(f, 1 + lvl)
