@@ -111,19 +111,26 @@ k_build_map2(const uint32_t* __restrict__ map, size_t count, int A, int W, int W
 // Writes the 16 x 64 destination tile at (oy1, ox1); with L0, also source rows 2..33 / bytes 2..129 of the
 // tile to the level-0 image (n x n) as 32 aligned words per row.
 // ------------------------------------------------------------------------------------
-template <bool L0>
-__device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
-                                              int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
+// INTERIOR: the whole tile lies inside both images and the destination pitch is even — no per-row or per-lane
+// bounds checks; addresses advance by pointer increments either way.
+template <bool L0, bool INTERIOR>
+__device__ __forceinline__ void warp_pyr_tile_impl(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
+                                                   int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
     const int x = ox1 + 2 * lane;
-    const bool even_pitch = (dw & 1) == 0;
-    const bool x_ok = x < dw, x0_ok = 2 * ox1 + 4 * lane < n;
+    const bool even_pitch = INTERIOR || (dw & 1) == 0;
+    const bool x_ok = INTERIOR || x < dw, x0_ok = INTERIOR || 2 * ox1 + 4 * lane < n;
+    const int rows0 = INTERIOR ? 2 * FT_TH1 : min(2 * FT_TH1, n - 2 * oy1);   // level-0 rows of this tile inside the image
+    const int rows1 = INTERIOR ? FT_TH1 : min(FT_TH1, dh - oy1);
+    uint8_t* q0 = L0 ? l0 + (size_t)(2 * oy1) * n + 2 * ox1 + 4 * lane : nullptr;
+    uint8_t* q1 = dst + (size_t)oy1 * dw + x;
+    const uint32_t* tp = tile + lane;
     uint32_t h[5];
 #pragma unroll
     for (int r = 0; r < FT_RH; ++r) {
-        const uint32_t w0 = tile[r * FT_RWW + lane], w1 = tile[r * FT_RWW + lane + 1];
+        const uint32_t w0 = tp[r * FT_RWW], w1 = tp[r * FT_RWW + 1];
         if (L0 && r >= 2 && r < 2 + 2 * FT_TH1) {
-            const int y0 = 2 * oy1 + r - 2;
-            if (y0 < n && x0_ok) *reinterpret_cast<uint32_t*>(l0 + (size_t)y0 * n + 2 * ox1 + 4 * lane) = __funnelshift_r(w0, w1, 16);
+            if (INTERIOR || (r - 2 < rows0 && x0_ok)) *reinterpret_cast<uint32_t*>(q0) = __funnelshift_r(w0, w1, 16);
+            q0 += n;
         }
         const uint32_t he = __dp4a(w1, 0x00000001u, __dp4a(w0, 0x04060401u, 0u));   // columns 4k .. 4k+4
         const uint32_t ho = __dp4a(w1, 0x00010406u, __dp4a(w0, 0x04010000u, 0u));   // columns 4k+2 .. 4k+6
@@ -131,15 +138,23 @@ __device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile,
         if (r >= 4 && (r & 1) == 0) {
             // both halves stay below 2^16 (255 * 256 + 128), so the packed sum never carries across
             const uint32_t s = h[(r - 4) % 5] + 4u * h[(r - 3) % 5] + 6u * h[(r - 2) % 5] + 4u * h[(r - 1) % 5] + h[r % 5] + 0x00800080u;
-            const int y = oy1 + (r - 4) / 2;
-            if (y < dh && x_ok) {
-                const uint32_t lo = (s >> 8) & 0xFFu, hi = s >> 24;
-                uint8_t* q = dst + (size_t)y * dw + x;
-                if (even_pitch) *reinterpret_cast<uint16_t*>(q) = (uint16_t)(lo | (hi << 8));
-                else { q[0] = (uint8_t)lo; if (x + 1 < dw) q[1] = (uint8_t)hi; }
+            if (INTERIOR || ((r - 4) / 2 < rows1 && x_ok)) {
+                const uint32_t px2 = __byte_perm(s, 0u, 0x4431);   // (s >> 8) & 0xFF | (s >> 24) << 8
+                if (even_pitch) *reinterpret_cast<uint16_t*>(q1) = (uint16_t)px2;
+                else { q1[0] = (uint8_t)px2; if (x + 1 < dw) q1[1] = (uint8_t)(px2 >> 8); }
             }
+            q1 += dw;
         }
     }
+}
+
+template <bool L0>
+__device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
+                                              int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
+    const bool interior = (dw & 1) == 0 && ox1 + FT_TW1 <= dw && oy1 + FT_TH1 <= dh &&
+                          (!L0 || (2 * ox1 + 2 * FT_TW1 <= n && 2 * oy1 + 2 * FT_TH1 <= n));
+    if (interior) warp_pyr_tile_impl<L0, true>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
+    else warp_pyr_tile_impl<L0, false>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
 }
 
 // ------------------------------------------------------------------------------------
@@ -156,26 +171,29 @@ struct FusedArgs {
 
 __device__ float g_lut255[256];   // fl(b / 255), parseData.py:43 (filled by k_build_lut at handle creation)
 
-__global__ void k_build_lut() { g_lut255[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f); }
+__device__ uint8_t g_lut_id[256];  // trunc(fl(fl(b / 255) * 255)): parseData.py:43 followed by getTransformKLT.py:356-357
 
-// V' = 2^14 * V (V = the 10-bit fixed-point bilinear sum) for the four frames of one tap word.
-//   c0r0, c0r1 / c1r0, c1r1   left / right column taps of the two source rows (byte f = frame 4q + f)
-//   ayw = (32 - fy) << 10 | fy << 26     cx0 = (32 - fx) << 4, cx1 = fx << 4
-// Vertical blend first: one PRMT pairs the two rows of a column for two frames, one dp2a (u16 weights x u8
-// samples) per frame and column; then the horizontal blend, one IMUL + IMAD per frame.  V' <= 0xFF000000: the
-// u8 result is its top byte and V is a multiple of 1024 exactly when the low 24 bits are 0.  Such frames
-// (V != 0) are flagged in `need` and redone with cv2's f32 chain.
+__global__ void k_build_lut() {
+    const float s = __fdiv_rn((float)threadIdx.x, 255.0f);
+    g_lut255[threadIdx.x] = s;
+    g_lut_id[threadIdx.x] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(s, 255.0f), 8388608.0f));
+}
+
+// V (the 10-bit fixed-point bilinear sum, <= 255 * 1024) for the four frames of one tap word.
+//   c0r0, c1r0 / c0r1, c1r1   left, right column taps of the upper / lower source row (byte f = frame 4q + f)
+//   wtop = w00 | w01 << 16, wbot = w10 | w11 << 16    the four integer weights m = (32 - fy | fy)(32 - fx | fx)
+// One PRMT pairs the two taps of a row for two frames, one dp2a (u16 weights x u8 samples) per frame and row
+// accumulates them.  The u8 result is V >> 10; V is a multiple of 1024 exactly when its low 10 bits are 0.
+// Such frames (V != 0) are flagged in `need` and redone with cv2's f32 chain.
 #define FT_QUAD(q, c0r0, c0r1, c1r0, c1r1)                                                                        \
     {                                                                                                             \
-        const uint32_t pa0 = __byte_perm((c0r0), (c0r1), 0x5140), pb0 = __byte_perm((c0r0), (c0r1), 0x7362);      \
-        const uint32_t pa1 = __byte_perm((c1r0), (c1r1), 0x5140), pb1 = __byte_perm((c1r0), (c1r1), 0x7362);      \
-        const uint32_t v4[4] = {__dp2a_lo(ayw, pa0, 0u) * cx0 + __dp2a_lo(ayw, pa1, 0u) * cx1,                    \
-                                __dp2a_hi(ayw, pa0, 0u) * cx0 + __dp2a_hi(ayw, pa1, 0u) * cx1,                    \
-                                __dp2a_lo(ayw, pb0, 0u) * cx0 + __dp2a_lo(ayw, pb1, 0u) * cx1,                    \
-                                __dp2a_hi(ayw, pb0, 0u) * cx0 + __dp2a_hi(ayw, pb1, 0u) * cx1};                   \
+        const uint32_t ta = __byte_perm((c0r0), (c1r0), 0x5140), tb4 = __byte_perm((c0r0), (c1r0), 0x7362);       \
+        const uint32_t ba = __byte_perm((c0r1), (c1r1), 0x5140), bb = __byte_perm((c0r1), (c1r1), 0x7362);        \
+        const uint32_t v4[4] = {__dp2a_lo(wbot, ba, __dp2a_lo(wtop, ta, 0u)), __dp2a_hi(wbot, ba, __dp2a_hi(wtop, ta, 0u)), \
+                                __dp2a_lo(wbot, bb, __dp2a_lo(wtop, tb4, 0u)), __dp2a_hi(wbot, bb, __dp2a_hi(wtop, tb4, 0u))}; \
         _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                                           \
-            if ((v4[f] & 0x00FFFFFFu) == 0u && v4[f] != 0u) need |= 1u << (4 * (q) + f);                          \
-            tb[(4 * (q) + f) * FT_TILE_BYTES] = (uint8_t)(v4[f] >> 24);                                           \
+            if ((v4[f] & 0x3FFu) == 0u && v4[f] != 0u) need |= 1u << (4 * (q) + f);                               \
+            tb[(4 * (q) + f) * FT_TILE_BYTES] = (uint8_t)(v4[f] >> 10);                                           \
         }                                                                                                         \
     }
 
@@ -184,10 +202,14 @@ struct PixelGeom {
     unsigned fx, fy, fl;       // 5-bit fractions, tap validity (bit 0: 00, 1: 01, 2: 10, 3: 11)
 };
 
-__device__ __forceinline__ PixelGeom pixel_geom(const FusedArgs& a, const uint4* __restrict__ src, int item, int ox1, int oy1) {
+// geometry record of region item `item` (REFLECT_101 at the image border: the pyrDown halo)
+__device__ __forceinline__ uint2 load_geom(const FusedArgs& a, int item, int ox1, int oy1) {
     const int ry = item / FT_RW, rx = item - ry * FT_RW;
     const int gy = reflect101_safe(2 * oy1 - 2 + ry, a.n), gx = reflect101_safe(2 * ox1 - 2 + rx, a.n);
-    const uint2 m = __ldg(a.map2 + (size_t)gy * a.n + gx);
+    return __ldg(a.map2 + (unsigned)(gy * a.n + gx));
+}
+
+__device__ __forceinline__ PixelGeom decode_geom(const FusedArgs& a, const uint4* __restrict__ src, uint2 m) {
     PixelGeom g;
     g.fx = m.y & 31u; g.fy = (m.y >> 5) & 31u; g.fl = (m.y >> 10) & 15u;
     g.p0 = src + m.x;
@@ -195,24 +217,46 @@ __device__ __forceinline__ PixelGeom pixel_geom(const FusedArgs& a, const uint4*
     return g;
 }
 
-// cv2's f32 chain for one (pixel, frame): entry = item | frame << 13
-__device__ __forceinline__ void exact_pixel(const FusedArgs& a, const uint4* __restrict__ src, uint32_t entry, int ox1, int oy1,
-                                            uint8_t* __restrict__ tile_bytes) {
-    const int item = entry & 0x1FFF, f = entry >> 13;
+__device__ __forceinline__ PixelGeom pixel_geom(const FusedArgs& a, const uint4* __restrict__ src, int item, int ox1, int oy1) {
+    return decode_geom(a, src, load_geom(a, item, ox1, oy1));
+}
+
+// the four taps (16 frames each) of one pixel; nothing is loaded for a pixel with no valid tap
+struct Taps { uint4 t00, t01, t10, t11; };
+__device__ __forceinline__ Taps load_taps(const FusedArgs& a, const uint4* __restrict__ src, uint2 m) {
+    Taps t;
+    t.t00 = t.t01 = t.t10 = t.t11 = make_uint4(0u, 0u, 0u, 0u);
+    if ((m.y >> 10) & 15u) {
+        const PixelGeom g = decode_geom(a, src, m);
+        t.t00 = __ldg(g.p0); t.t01 = __ldg(g.p0 + 1); t.t10 = __ldg(g.p1); t.t11 = __ldg(g.p1 + 1);
+    }
+    return t;
+}
+
+// cv2's f32 chain for the flagged frames of one pixel: entry = item | frame mask << 13
+__device__ __forceinline__ void exact_item(const FusedArgs& a, const uint4* __restrict__ src, uint32_t entry, int ox1, int oy1,
+                                           uint8_t* __restrict__ tile_bytes) {
+    const int item = entry & 0x1FFF;
+    uint32_t mask = entry >> 13;
     const PixelGeom g = pixel_geom(a, src, item, ox1, oy1);
     // (1 - fy)(1 - fx) etc. are exact multiples of 2^-10, as cv2 computes them; a tap outside the source has weight 0
     const float w00 = (g.fl & 1u) ? (float)((32u - g.fy) * (32u - g.fx)) * 0.0009765625f : 0.0f;
     const float w01 = (g.fl & 2u) ? (float)((32u - g.fy) * g.fx) * 0.0009765625f : 0.0f;
     const float w10 = (g.fl & 4u) ? (float)(g.fy * (32u - g.fx)) * 0.0009765625f : 0.0f;
     const float w11 = (g.fl & 8u) ? (float)(g.fy * g.fx) * 0.0009765625f : 0.0f;
-    const uint8_t* b0 = reinterpret_cast<const uint8_t*>(g.p0) + f;
-    const uint8_t* b1 = reinterpret_cast<const uint8_t*>(g.p1) + f;
-    float acc = __fmul_rn(g_lut255[__ldg(b0)], w00);
-    acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b0 + 16)], w01));
-    acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1)], w10));
-    acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1 + 16)], w11));
-    // (img * 255).astype(uint8): f32 product, truncation; 2^23 + x rounded toward zero keeps floor(x) in the low byte
-    tile_bytes[f * FT_TILE_BYTES + item] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(acc, 255.0f), 8388608.0f));
+    const uint8_t* b0 = reinterpret_cast<const uint8_t*>(g.p0);
+    const uint8_t* b1 = reinterpret_cast<const uint8_t*>(g.p1);
+    uint8_t* out = tile_bytes + item;
+    while (mask) {
+        const int f = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        float acc = __fmul_rn(g_lut255[__ldg(b0 + f)], w00);
+        acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b0 + f + 16)], w01));
+        acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1 + f)], w10));
+        acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1 + f + 16)], w11));
+        // (img * 255).astype(uint8): f32 product, truncation; 2^23 + x rounded toward zero keeps floor(x) in the low byte
+        out[f * FT_TILE_BYTES] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(acc, 255.0f), 8388608.0f));
+    }
 }
 
 #define FT_LIST_CAP 64   // deferred (pixel, frame) entries per warp
@@ -231,47 +275,86 @@ __global__ void __launch_bounds__(256, 3) k_scan16_to_l0l1(const FusedArgs a) {
     int cnt = 0;                                             // warp-uniform fill of `list`
     const unsigned lt = (1u << lane) - 1u;
 
-#pragma unroll 1
-    for (int it = 0; it < (FT_RH * FT_RW + 255) / 256; ++it) {
-        const int item = it * 256 + tid;
+    // Two-deep software pipeline over the CTA's 4620 region pixels (one per thread and step): while pixel `it`
+    // is blended, the taps of pixel it + 1 and the geometry record of pixel it + 2 are in flight, so neither of
+    // the two dependent gathers (L2-resident record -> scan samples) is waited for.
+    constexpr int NIT = (FT_RH * FT_RW + 255) / 256;
+    // region coordinates of the next geometry fetch; they advance by 256 items = one row + 124 columns.
+    // (A 4 x 8 pixel patch per warp instead of a 32 x 1 strip was measured: 4 % fewer L1 wavefronts, 9 % more
+    // instructions from the ragged 33 x 5 patch grid, 5 % slower.)
+    int gry = tid / FT_RW, grx = tid - gry * FT_RW;
+    int gitem = tid;
+    auto next_geom = [&](int& item) -> uint2 {
+        uint2 m = make_uint2(0u, 0u);                        // fl == 0: no taps
+        item = -1;
+        if (gitem < FT_RH * FT_RW) {
+            item = gitem;
+            const int gy = reflect101_safe(2 * oy1 - 2 + gry, a.n), gx = reflect101_safe(2 * ox1 - 2 + grx, a.n);
+            m = __ldg(a.map2 + (unsigned)(gy * a.n + gx));
+        }
+        gitem += 256; grx += 256 - FT_RW; gry += 1;
+        if (grx >= FT_RW) { grx -= FT_RW; gry += 1; }
+        return m;
+    };
+    // blend one region pixel for the 16 frames of the group, then queue its flagged frames
+    auto step = [&](const int item, const uint2 m, const Taps& T) {
         uint32_t need = 0u;
-        if (item < FT_RH * FT_RW) {
-            const PixelGeom g = pixel_geom(a, src, item, ox1, oy1);
+        if (item >= 0) {
+            const unsigned fx = m.y & 31u, fy = (m.y >> 5) & 31u, fl = (m.y >> 10) & 15u;
             uint8_t* tb = tile_bytes + item;
-            if (g.fl == 0u) {   // beyond the last range bin (image corners): WARP_FILL_OUTLIERS
+            if (fl == 0u) {   // beyond the last range bin (image corners): WARP_FILL_OUTLIERS
 #pragma unroll
                 for (int f = 0; f < FT_FR; ++f) tb[f * FT_TILE_BYTES] = 0;
+            } else if ((m.y & 0x7FFu) == 0x400u) {
+                // fx = fy = 0 and tap 00 valid: the weights are 1, 0, 0, 0 and cv2's chain collapses to
+                // trunc(fl(fl(b / 255) * 255)) of that one sample (every such V is a multiple of 1024)
+                const uint32_t q[4] = {T.t00.x, T.t00.y, T.t00.z, T.t00.w};
+#pragma unroll
+                for (int f = 0; f < FT_FR; ++f) tb[f * FT_TILE_BYTES] = g_lut_id[(q[f >> 2] >> (8 * (f & 3))) & 0xFFu];
             } else {
-                uint4 T00 = __ldg(g.p0), T01 = __ldg(g.p0 + 1), T10 = __ldg(g.p1), T11 = __ldg(g.p1 + 1);
-                if (g.fl != 15u) {   // a tap outside the source contributes 0
+                uint4 T00 = T.t00, T01 = T.t01, T10 = T.t10, T11 = T.t11;
+                if (fl != 15u) {   // a tap outside the source contributes 0
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    if (!(g.fl & 1u)) T00 = z; if (!(g.fl & 2u)) T01 = z; if (!(g.fl & 4u)) T10 = z; if (!(g.fl & 8u)) T11 = z;
+                    if (!(fl & 1u)) T00 = z; if (!(fl & 2u)) T01 = z; if (!(fl & 4u)) T10 = z; if (!(fl & 8u)) T11 = z;
                 }
-                const uint32_t ayw = ((32u - g.fy) << 10) | (g.fy << 26), cx0 = (32u - g.fx) << 4, cx1 = g.fx << 4;
+                const uint32_t wy0 = 32u - fy, wx0 = 32u - fx;
+                const uint32_t wtop = wy0 * wx0 | (wy0 * fx) << 16, wbot = fy * wx0 | (fy * fx) << 16;
                 FT_QUAD(0, T00.x, T10.x, T01.x, T11.x)
                 FT_QUAD(1, T00.y, T10.y, T01.y, T11.y)
                 FT_QUAD(2, T00.z, T10.z, T01.z, T11.z)
                 FT_QUAD(3, T00.w, T10.w, T01.w, T11.w)
             }
         }
-        // Defer the flagged frames: lanes append (pixel, frame) entries to the warp's list, and whenever 32 are
-        // waiting the whole warp redoes them with the f32 chain, one entry per lane (no divergence).
-        unsigned pending;
-        while ((pending = __ballot_sync(0xffffffffu, need != 0u)) != 0u) {
-            if (need) {
-                list[cnt + __popc(pending & lt)] = (uint32_t)item | ((uint32_t)(__ffs(need) - 1) << 13);
-                need &= need - 1u;
-            }
+        // Defer the flagged frames: a lane appends ONE entry (pixel, frame mask) to the warp's list, and whenever 32
+        // are waiting the whole warp redoes them with the f32 chain, one pixel per lane.
+        const unsigned pending = __ballot_sync(0xffffffffu, need != 0u);
+        if (pending) {
+            if (need) list[cnt + __popc(pending & lt)] = (uint32_t)item | (need << 13);
             cnt += __popc(pending);
             __syncwarp();
             if (cnt >= 32) {
                 cnt -= 32;
-                exact_pixel(a, src, list[cnt + lane], ox1, oy1, tile_bytes);
+                exact_item(a, src, list[cnt + lane], ox1, oy1, tile_bytes);
                 __syncwarp();
             }
         }
+    };
+    int iA, iB, iC, iD;
+    uint2 mA = next_geom(iA);
+    Taps TA = load_taps(a, src, mA);
+    uint2 mB = next_geom(iB);
+#pragma unroll 1
+    for (int it = 0; it + 1 < NIT; it += 2) {
+        const Taps TB = load_taps(a, src, mB);
+        const uint2 mC = next_geom(iC);
+        step(iA, mA, TA);
+        TA = load_taps(a, src, mC);
+        const uint2 mD = next_geom(iD);
+        step(iB, mB, TB);
+        mA = mC; mB = mD; iA = iC; iB = iD;
     }
-    if (lane < cnt) exact_pixel(a, src, list[lane], ox1, oy1, tile_bytes);
+    if (NIT & 1) step(iA, mA, TA);
+    if (lane < cnt) exact_item(a, src, list[lane], ox1, oy1, tile_bytes);
     __syncthreads();
 
     // one warp per frame from here on (two frames per warp): level-0 store + level 1 from the shared-memory tile
@@ -288,7 +371,7 @@ __global__ void __launch_bounds__(256, 3) k_scan16_to_l0l1(const FusedArgs a) {
 // pyrDown for the higher levels: each warp loads its 35 x 132 source tile from global memory
 // (REFLECT_101), then the same shared-memory pass.  4 warps per CTA, one tile each.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh, uint8_t* __restrict__ dst,
              size_t dst_stride, int dw, int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
     __shared__ uint32_t s_tile[4][FT_TILE_WORDS];
@@ -307,6 +390,20 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     // back to REFLECT_101 byte loads.  Aligned loads may run up to 7 bytes past the row end: into the next row,
     // or into the padding every level allocation carries (rf_frameset_alloc).
     const int xk = x0 + 4 * lane, xk32 = x0 + 128;
+    if (x0 >= 0 && x0 + FT_RW + 4 <= sw && 2 * oy1 - 2 >= 0 && 2 * oy1 - 2 + FT_RH <= sh) {
+        // interior tile: no reflection, no edge words; the row pointer advances by the pitch.  Rows are only
+        // byte-aligned (odd widths at the higher levels), so each region word is cut out of two aligned loads.
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3u);
+        const uint32_t* __restrict__ s4 = reinterpret_cast<const uint32_t*>(s - mis) + lane;   // aligned frame base
+        unsigned off = mis + (unsigned)(2 * oy1 - 2) * (unsigned)sw + (unsigned)x0;             // byte offset of the row's region
+#pragma unroll 5
+        for (int r = 0; r < FT_RH; ++r, off += sw) {
+            const uint32_t* ap = s4 + (off >> 2);
+            const unsigned sh8 = 8u * (off & 3u);
+            tw[r * FT_RWW + lane] = __funnelshift_r(__ldg(ap), __ldg(ap + 1), sh8);
+            if (lane == 0) tw[r * FT_RWW + 32] = __funnelshift_r(__ldg(ap + 32), __ldg(ap + 33), sh8);
+        }
+    } else {
     const bool in_k = xk >= 0 && xk + 3 < sw, in_32 = xk32 + 3 < sw;
 #pragma unroll 5
     for (int r = 0; r < FT_RH; ++r) {
@@ -336,6 +433,7 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
             }
             tw[r * FT_RWW + 32] = v2;
         }
+    }
     }
     __syncwarp();
     warp_pyr_tile<false>(s_tile[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane, nullptr, 0);
