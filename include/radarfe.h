@@ -191,6 +191,28 @@ RF_API int rf_nms_select(rf_handle* h, const float* resp, int rows, int cols, fl
 /* polar f32 [A, W] -> out [cap,2] i64 (azimuth, range), azimuth-major order. */
 RF_API int rf_polar_peaks(rf_handle* h, const float* polar, int A, int W, int64_t* out, int64_t cap, int64_t* n);
 
+/* ---- N1  Fourier-Mellin rotation prior                   FMT.py:13-90 --------------- */
+/* FMT.getRotationUsingFMT for n_pairs pairs drawn from n_frames f32 polar images [n_frames, A, W] (host):
+ * clip to clip_px range bins (<= 0: none; FMT.py:55-58), cv2.resize to clip_px / downsample bins, log-polar
+ * resampling (parseData.convertPolarImgToLogPolar, parseData.py:138-157), Hann-windowed phase correlation.
+ * Outputs per pair: angle_rad (normalised, R(angle) @ src = target), scale, response (NULL to skip) and the raw
+ * phaseCorrelate shift (dx, dy) in shift_xy [n_pairs, 2] (NULL to skip). */
+RF_API int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W, const int32_t* pair_idx,
+                    int n_pairs, int downsample, int clip_px, double* angle_rad, double* scale, double* response,
+                    double* shift_xy);
+/* The log-polar image itself (stage-level parity): out [h_lp, w_lp] f32; out == NULL only queries the size. */
+RF_API int rf_fmt_log_polar(rf_handle* h, const float* polar, int A, int W, int downsample, int clip_px, float* out,
+                     int64_t out_cap, int* h_lp, int* w_lp);
+/* cv2.phaseCorrelate(a, b, cv2.createHanningWindow((cols, rows), CV_32F))   FMT.py:13-33
+ * a, b [rows, cols] f32 (host) -> (dx, dy), response. */
+RF_API int rf_phase_correlate(rf_handle* h, const float* a, const float* b, int rows, int cols, double* dx, double* dy,
+                       double* response);
+
+/* The same for every pair of an uploaded batch, from the scans already resident on the device (u8 power bins,
+ * decoded as parseData.py:43 does): Tracker.py:62-63 without a second upload.  Synchronous on return. */
+RF_API int rf_batch_fmt(rf_handle* h, rf_batch* b, int downsample, int clip_px, double* angle_rad, double* scale,
+                 double* response, double* shift_xy);
+
 /* ---- a11 fused pair / batch: Tracker.track + getTransform (+ MDS)  Tracker.py:35-127 */
 RF_API int rf_batch_create(rf_handle* h, rf_batch** out);
 RF_API void rf_batch_destroy(rf_handle* h, rf_batch* b);

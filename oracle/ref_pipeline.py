@@ -121,3 +121,26 @@ def track_pair(raw_prev, raw_next, feats_xy, prev_pose=None, with_mds=False, ran
         T_wj = T0 @ np.block([[out["R"], out["h"].reshape(2, 1)], [np.zeros((2,)), 1]])   # :201
         out["mds_x"] = mds_solve(T0, p_w, p_jt, T_wj)
     return out
+
+
+def rotation_fmt(src_polar, tgt_polar, downsample=10, max_range_clip_m=87.5, range_res_cart_m=0.0432 * 2):
+    """FMT.py:36-90 getRotationUsingFMT as the cv2 calls the reference makes (resize, warpPolar x 2,
+    createHanningWindow, phaseCorrelate) -> (angle rad, scale, response)."""
+    import cv2
+    if max_range_clip_m > 0:
+        clip = int(max_range_clip_m / range_res_cart_m)
+        src_polar, tgt_polar = src_polar[:, :clip], tgt_polar[:, :clip]
+    H, W = src_polar.shape
+
+    def log_polar(p):
+        small = cv2.resize(p, (int(W // downsample), H))
+        cart = polar_to_cart(small, downsample=1)                               # parseData.py:148-151
+        h, w = cart.shape
+        return cv2.warpPolar(cart, None, (h / 2, w / 2), w / 2, cv2.WARP_POLAR_LOG + cv2.INTER_LINEAR + cv2.WARP_FILL_OUTLIERS)
+
+    a, b = log_polar(src_polar), log_polar(tgt_polar)
+    h_lp, w_lp = a.shape
+    (scale, angle), response = cv2.phaseCorrelate(a, b, cv2.createHanningWindow((w_lp, h_lp), cv2.CV_32F))
+    sz = max(h_lp, w_lp)
+    angle = (-float(angle) * 2 * np.pi / sz + np.pi) % (2 * np.pi) - np.pi        # utils.normalize_angles
+    return angle, np.exp(np.log(h_lp / 2) / sz) ** scale, response

@@ -1,0 +1,29 @@
+"""Drop-in for the reference's FMT.py: Fourier-Mellin rotation prior on libradarfe.so.
+Same names, arguments and return values as FMT.py:13-90; the arithmetic runs in
+rf_fmt_rotation / rf_phase_correlate (csrc/k_fmt.cu).  Plotting helpers are out of scope."""
+from typing import Tuple
+
+import numpy as np
+
+from . import _engine
+from .parseData import RANGE_RESOLUTION_CART_M
+
+FMT_DOWNSAMPLE_FACTOR = 10   # FMT.py:10
+FMT_RANGE_CLIP_M = 87.5      # FMT.py:11
+
+
+def getTranslationUsingPhaseCorrelation(srcImg: np.ndarray, targetImg: np.ndarray) -> Tuple[Tuple[float, float], float]:
+    """FMT.py:13-33: Hann-windowed cv2.phaseCorrelate -> ((dx, dy), response)."""
+    fe = _engine.engine()
+    return fe.phase_correlate(srcImg, targetImg)
+
+
+def getRotationUsingFMT(srcPolarImg: np.ndarray, targetPolarImg: np.ndarray, downsampleFactor: int = FMT_DOWNSAMPLE_FACTOR,
+                        maxRangeClipM=FMT_RANGE_CLIP_M) -> Tuple[float, float, float]:
+    """FMT.py:36-90 -> (angleRad with R(angleRad) @ src = target, scale, response)."""
+    assert srcPolarImg.shape == targetPolarImg.shape, "Images need to have the same shape!"
+    clip_px = int(maxRangeClipM / RANGE_RESOLUTION_CART_M) if maxRangeClipM > 0 else 0   # FMT.py:55-58
+    fe = _engine.engine()
+    polar = np.stack([np.asarray(srcPolarImg, np.float32), np.asarray(targetPolarImg, np.float32)])
+    ang, sc, resp, _ = fe.fmt_rotation(polar, ((0, 1),), downsample=int(downsampleFactor), clip_px=clip_px)
+    return float(ang[0]), float(sc[0]), float(resp[0])

@@ -4,6 +4,7 @@ from typing import Tuple
 
 import numpy as np
 
+from .FMT import getRotationUsingFMT
 from .getTransformKLT import calculateTransformSVD, getTrackedPointsKLT
 from .outlierRejection import rejectOutliers
 from .parseData import RANGE_RESOLUTION_CART_M
@@ -28,9 +29,9 @@ class Tracker():
               currImgPolar: np.ndarray, featureCoord: np.ndarray, seqInd: int
               ) -> Tuple[np.ndarray, np.ndarray, float, np.ndarray]:
         """Tracker.py:35-106 -> (good_old, good_new, angleRotRad, corrStatus u8 [K,1]).
-        The FMT rotation prior (Tracker.py:62-63) is computed-but-unused in the reference and is
-        not part of this front end: angleRotRad is returned as 0.0."""
-        angleRotRad = 0.0
+        angleRotRad is the FMT rotation prior (Tracker.py:62-63, rf_fmt_rotation); like the reference, the
+        images are not pre-rotated by it (the `useFMT` branch is a no-op there, Tracker.py:66-72)."""
+        angleRotRad, _, _ = getRotationUsingFMT(prevImgPolar, currImgPolar)
         good_new, good_old, bad_new, bad_old, corrStatus = getTrackedPointsKLT(prevImgCart, currImgCart, featureCoord)
         nFeatures = good_new.shape[0] + bad_new.shape[0]
         if self.paramFlags.get("rejectOutliers", True):

@@ -50,7 +50,8 @@ SYMBOLS = [
     "rf_detect", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
-    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait",
+    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_log_polar",
+    "rf_phase_correlate", "rf_batch_fmt",
 ]
 STAGES = ("polar2cart", "scan_to_l0l1", "pyr_down", "klt", "compact", "reject", "kabsch", "mds", "finish")
 
@@ -209,6 +210,14 @@ class Batch:
         err = np.zeros((max(P, 1), K), np.float32)
         fe._check(fe.lib.rf_batch_klt_status(fe.h, self.p, _ptr(st), _ptr(err)))
         return st[:P], err[:P]
+
+    def fmt_rotation(self, downsample=10, clip_px=0):
+        """FMT rotation prior (Tracker.py:62-63) of every pair of the uploaded batch, from the resident scans
+        -> (angle_rad [P], scale [P], response [P], shift_xy [P, 2])."""
+        fe, P = self.fe, self.n_pairs
+        ang, sc, resp, sh = np.zeros(P), np.zeros(P), np.zeros(P), np.zeros((P, 2))
+        fe._check(fe.lib.rf_batch_fmt(fe.h, self.p, int(downsample), int(clip_px), _ptr(ang), _ptr(sc), _ptr(resp), _ptr(sh)))
+        return ang, sc, resp, sh
 
     def frame(self, idx, what=1):
         fe = self.fe
@@ -481,6 +490,43 @@ class RadarFE:
         n = C.c_int64(0)
         self._check(self.lib.rf_polar_peaks(self.h, _ptr(polar), A, W, _ptr(out), C.c_int64(cap), C.byref(n)))
         return out[:n.value].copy()
+
+
+    # -- N1 FMT rotation prior (FMT.py:13-90) ---------------------------------------
+    def fmt_rotation(self, polar, pairs=((0, 1),), downsample=10, clip_px=0):
+        """polar [F, A, W] f32, pairs [P, 2] -> (angle_rad [P], scale [P], response [P], shift_xy [P, 2])."""
+        polar = _c(polar, np.float32)
+        if polar.ndim != 3:
+            raise ValueError(f"expected [frames, azimuths, bins], got {polar.shape}")
+        F, A, W = polar.shape
+        pairs = _c(np.asarray(pairs, np.int32).reshape(-1, 2), np.int32)
+        P = pairs.shape[0]
+        ang, sc, resp, sh = np.zeros(P), np.zeros(P), np.zeros(P), np.zeros((P, 2))
+        self._check(self.lib.rf_fmt_rotation(self.h, _ptr(polar), F, A, W, _ptr(pairs), P, int(downsample), int(clip_px),
+                                             _ptr(ang), _ptr(sc), _ptr(resp), _ptr(sh)))
+        return ang, sc, resp, sh
+
+    def fmt_log_polar(self, polar, downsample=10, clip_px=0):
+        """parseData.convertPolarImgToLogPolar(cv2.resize(polar[:, :clip_px], ...)) -> f32 [h_lp, w_lp]."""
+        polar = _c(polar, np.float32)
+        A, W = polar.shape
+        h_lp, w_lp = C.c_int(0), C.c_int(0)
+        self._check(self.lib.rf_fmt_log_polar(self.h, _ptr(polar), A, W, int(downsample), int(clip_px), None, C.c_int64(0),
+                                              C.byref(h_lp), C.byref(w_lp)))
+        out = np.empty((h_lp.value, w_lp.value), np.float32)
+        self._check(self.lib.rf_fmt_log_polar(self.h, _ptr(polar), A, W, int(downsample), int(clip_px), _ptr(out),
+                                              C.c_int64(out.size), C.byref(h_lp), C.byref(w_lp)))
+        return out
+
+    def phase_correlate(self, a, b):
+        """cv2.phaseCorrelate(a, b, hanning) -> ((dx, dy), response)."""
+        a, b = _c(a, np.float32), _c(b, np.float32)
+        if a.shape != b.shape or a.ndim != 2:
+            raise ValueError("phase_correlate: images need the same 2-D shape")
+        dx, dy, r = C.c_double(0), C.c_double(0), C.c_double(0)
+        self._check(self.lib.rf_phase_correlate(self.h, _ptr(a), _ptr(b), a.shape[0], a.shape[1], C.byref(dx), C.byref(dy),
+                                                C.byref(r)))
+        return (dx.value, dy.value), r.value
 
 
 _default = {}

@@ -123,3 +123,8 @@ int rf_launch_kabsch(rf_handle* h, const float* d_src, const float* d_tgt, const
 int rf_launch_mds_fused(rf_handle* h, const float* d_old, const float* d_new, const uint8_t* d_mask, int mask_stride,
                         const int32_t* d_counts, int Kstride, int P, const double* d_R, const double* d_h,
                         const double* d_prev_pose, double* d_scratch, double* d_x, int32_t* d_iters);
+// k_fmt.cu — Fourier-Mellin rotation prior over device-resident scans (used by rf_batch_fmt)
+int rf_fmt_resident_u8(rf_handle* h, const uint8_t* d_raw, int F, int A, int W, size_t pitch, const int32_t* d_pairs, int P,
+                       int downsample, int clip_px, double** d_out_p, int* sz_out, double* log_base_out);
+void rf_fmt_finish(const double* out3, int P, int sz, double log_base, double* angle_rad, double* scale, double* response,
+                   double* shift_xy);

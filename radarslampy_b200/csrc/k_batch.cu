@@ -406,6 +406,27 @@ int rf_batch_klt_status(rf_handle* h, rf_batch* b, uint8_t* klt_status, float* e
     return RF_OK;
 }
 
+// Tracker.py:62-63 for every pair of the batch: FMT rotation prior from the RESIDENT raw scans (no extra upload).
+// Runs on the handle's main stream after the batch's upload; synchronous on return.
+int rf_batch_fmt(rf_handle* h, rf_batch* b, int downsample, int clip_px, double* angle_rad, double* scale, double* response,
+                 double* shift_xy) {
+    if (!h || !b || !angle_rad) return rf_fail(h, RF_E_BADARG, "rf_batch_fmt: null argument");
+    const int P = b->n_pairs, F = b->n_frames;
+    if (!P) return RF_OK;
+    RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_uploaded, 0));
+    double* d_out = nullptr;
+    int sz = 0;
+    double log_base = 1.0;
+    int rc = rf_fmt_resident_u8(h, b->d_raw, F, h->cfg.azimuths, b->raw_cols, (size_t)b->raw_pitch, b->d_pair_idx, P, downsample,
+                                clip_px, &d_out, &sz, &log_base);
+    if (rc) return rc;
+    std::vector<double> out((size_t)P * 3);
+    RF_CUDA(h, cudaMemcpyAsync(out.data(), d_out, (size_t)P * 24, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    rf_fmt_finish(out.data(), P, sz, log_base, angle_rad, scale, response, shift_xy);
+    return RF_OK;
+}
+
 int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx, int n_pairs,
                    const float* feats, const int32_t* feat_counts, const double* prev_pose, int with_mds,
                    rf_pair_result* results, float* next_xy, uint8_t* status) {

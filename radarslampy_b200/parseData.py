@@ -36,8 +36,8 @@ def convertPolarImageToCartesian(imgPolar: np.ndarray, logPolarMode: bool = Fals
     """parseData.py:100-135 (cv2.warpPolar, inverse linear map) -> f32 [2R, 2R].  The returned array
     also keeps its device frame (u8 image + LK pyramid) for getTrackedPointsKLT."""
     if logPolarMode:
-        raise NotImplementedError("log-polar conversion is only used by the FMT rotation prior, which is outside "
-                                  "this front end (SURVEY.md §8f N1)")
+        raise NotImplementedError("inverse log-polar conversion is not used on the hot path (the FMT rotation prior "
+                                  "goes polar -> Cartesian -> log-polar: see convertPolarImgToLogPolar)")
     imgPolar = np.ascontiguousarray(imgPolar, dtype=np.float32)
     A, W = imgPolar.shape
     if changeGlobalRangeResolution:
@@ -46,6 +46,12 @@ def convertPolarImageToCartesian(imgPolar: np.ndarray, logPolarMode: bool = Fals
     fe = _engine.engine(range_bins=W, azimuths=A, downsample=max(int(downsampleFactor), 1))
     frame, cart = fe.polar_to_cart(polar=imgPolar)
     return _engine.wrap(cart, fe, frame)
+
+
+def convertPolarImgToLogPolar(imgPolar: np.ndarray) -> np.ndarray:
+    """parseData.py:138-157: polar -> Cartesian (no down-sampling) -> semi-log polar, f32 [round(pi W), W]."""
+    imgPolar = np.ascontiguousarray(imgPolar, dtype=np.float32)
+    return _engine.engine().fmt_log_polar(imgPolar, downsample=1, clip_px=0)
 
 
 def convertRawScanToCartesian(polarImgData: np.ndarray, maxRangeClipM: float = MAX_RANGE_CLIP_DEFAULT) -> np.ndarray:
