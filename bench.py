@@ -209,7 +209,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, rb, kmax):
@@ -222,7 +222,34 @@ def workload_config(args, rb, kmax):
 
 
 # ---------------------------------------------------------------------------------------
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout (see main)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def ncu_traffic(kernel: str, frames: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    `--set full` capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); scaled when the
+    capture used a different frame count (traffic is linear in frames).  None if there is no capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    rec = json.load(open(p)).get(kernel)
+    if not rec:
+        return None
+    return float(rec["dram_bytes_per_launch"]) * frames / float(rec["frames"])
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL's version banner, torch warnings) write to fd 1: keep the JSON line alone on stdout by
+    # pointing fd 1 at stderr for the rest of the process and writing the result to a saved copy
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -390,11 +417,11 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32/f64", "data": "synthetic", "config": dict(workload_config(args, rb, kmax), pipelining=f"{NB} batches alternate on one handle (copy / image+KLT / rejection+solve streams)"),
         "klt_tracks_per_s": world * K_total * args.steps / (ms * 1e-3),
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+                "ms_per_step": ms_e2e / args.steps, "note": "bytes are the whole job's (all ranks) per step"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(dom, S), "peak_source": peak_src,
                      "alg_bytes_per_launch": sb[dom], "ms_per_launch": stages[dom]["ms"]},
         "stages": stages,
         "clocks": clocks,
@@ -406,7 +433,7 @@ def main():
     }
     if cpu_line is not None:
         line["cpu_baseline"] = cpu_line
-    print(json.dumps(line), flush=True)
+    emit(line)
     for b in batches:
         b.close()
     fe.close()

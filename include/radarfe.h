@@ -213,6 +213,14 @@ RF_API int rf_phase_correlate(rf_handle* h, const float* a, const float* b, int 
 RF_API int rf_batch_fmt(rf_handle* h, rf_batch* b, int downsample, int clip_px, double* angle_rad, double* scale,
                  double* response, double* shift_xy);
 
+/* ---- N3  trajectory chaining                              trajectoryPlotting.py:27-60 */
+/* Poses [P+1, 3] (x, y, theta) from per-pair relative transforms R [P, 4] (row-major 2x2), h [P, 2], as a parallel
+ * prefix product over SE(2), starting at start_pose (x, y, theta; NULL = origin).
+ * left_multiply = 1: T_k = A_k T_{k-1} (Trajectory.appendRelativeTransform, trajectoryPlotting.py:54);
+ * left_multiply = 0: T_k = T_{k-1} A_k (Trajectory.appendRelativeDeltas, trajectoryPlotting.py:27-35). */
+RF_API int rf_chain_poses(rf_handle* h, const double* R, const double* hv, int P, const double* start_pose,
+                   int left_multiply, double* poses_out);
+
 /* ---- a11 fused pair / batch: Tracker.track + getTransform (+ MDS)  Tracker.py:35-127 */
 RF_API int rf_batch_create(rf_handle* h, rf_batch** out);
 RF_API void rf_batch_destroy(rf_handle* h, rf_batch* b);

@@ -51,7 +51,7 @@ SYMBOLS = [
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
     "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_log_polar",
-    "rf_phase_correlate", "rf_batch_fmt",
+    "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses",
 ]
 STAGES = ("polar2cart", "scan_to_l0l1", "pyr_down", "klt", "compact", "reject", "kabsch", "mds", "finish")
 
@@ -527,6 +527,20 @@ class RadarFE:
         self._check(self.lib.rf_phase_correlate(self.h, _ptr(a), _ptr(b), a.shape[0], a.shape[1], C.byref(dx), C.byref(dy),
                                                 C.byref(r)))
         return (dx.value, dy.value), r.value
+
+
+    # -- N3 trajectory chaining (trajectoryPlotting.py:27-60) -------------------------
+    def chain_poses(self, R, h, start_pose=None, left_multiply=True):
+        """R [P, 2, 2] (or [P, 4]), h [P, 2] -> poses [P + 1, 3] (x, y, theta)."""
+        R = _c(np.asarray(R, np.float64).reshape(-1, 4), np.float64)
+        h = _c(np.asarray(h, np.float64).reshape(-1, 2), np.float64)
+        if R.shape[0] != h.shape[0]:
+            raise ValueError("chain_poses: R and h need the same length")
+        P = R.shape[0]
+        sp = None if start_pose is None else _c(np.asarray(start_pose, np.float64).reshape(3), np.float64)
+        out = np.empty((P + 1, 3), np.float64)
+        self._check(self.lib.rf_chain_poses(self.h, _ptr(R), _ptr(h), P, _ptr(sp), int(bool(left_multiply)), _ptr(out)))
+        return out
 
 
 _default = {}

@@ -13,7 +13,7 @@ python bench.py --steps 10 --warmup 3 --mds 1 --no-cpu-baseline > $O/${TAG}_benc
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_launch.log 2>&1
-for k in ${NCU_KERNELS:-k_scan_to_l0l1 k_klt k_clique}; do
+for k in ${NCU_KERNELS:-k_scan16_to_l0l1 k_klt k_clique}; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $O/${TAG}_full_$k \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_$k.log 2>&1
 done

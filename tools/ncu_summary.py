@@ -1,8 +1,13 @@
 #!/usr/bin/env python
 """Condense an ncu report (.ncu-rep, `--set full`) into the small metric,unit,value CSV kept under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/X.ncu-rep profiles/X.csv
+    python tools/ncu_summary.py gpurun_out/X.ncu-rep profiles/X.csv [--traffic STAGE FRAMES]
+
+--traffic also records dram__bytes_read.sum + dram__bytes_write.sum of the (first) captured launch under
+profiles/ncu_traffic.json[STAGE], which bench.py reports as roofline.traffic.
 """
+import json
+import os
 import csv
 import io
 import subprocess
@@ -38,5 +43,30 @@ def main(rep, out):
                     f.write(f"{h},{u},{v}\n")
 
 
+def to_bytes(value, unit):
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+    return float(value.replace(",", "")) * scale
+
+
+def traffic(csv_path, stage, frames):
+    rd = wr = None
+    name = ""
+    for line in open(csv_path):
+        if line.startswith("# kernel,") and not name:
+            name = line.strip().split(",", 1)[1]
+        f = line.strip().split(",")
+        if f[0] == "dram__bytes_read.sum" and rd is None:
+            rd = to_bytes(f[2], f[1])
+        if f[0] == "dram__bytes_write.sum" and wr is None:
+            wr = to_bytes(f[2], f[1])
+    out = os.path.join(os.path.dirname(os.path.abspath(csv_path)), "ncu_traffic.json")
+    rec = json.load(open(out)) if os.path.exists(out) else {}
+    rec[stage] = {"kernel": name, "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                  "frames": int(frames), "source": os.path.basename(csv_path)}
+    json.dump(rec, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
     main(sys.argv[1], sys.argv[2])
+    if len(sys.argv) >= 6 and sys.argv[3] == "--traffic":
+        traffic(sys.argv[2], sys.argv[4], sys.argv[5])
