@@ -27,3 +27,9 @@ def getTrackedPointsKLT(srcImg: np.ndarray, targetImg: np.ndarray, blobCoordSrc:
     nextPts, status, _ = fe.klt(prev, nxt, featurePtSrc, apply_err_gate=True)
     good = (status == 1).flatten()
     return nextPts[good, :], featurePtSrc[good, :], nextPts[~good, :], featurePtSrc[~good, :], status
+
+
+def visualize_transform(*args, **kwargs):
+    """getTransformKLT.py:165-230 is a matplotlib debugging plot (imported, never called on the hot path by
+    Tracker.py:9); it is outside this front end."""
+    raise NotImplementedError("visualize_transform is a plotting helper of the reference and is not part of the drop-in")

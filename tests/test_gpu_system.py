@@ -1,0 +1,45 @@
+"""GPU: the reference's SYSTEM loop (RawROAMSystem.run, RawROAMSystem.py:104-300) on a synthetic Oxford-shaped
+sequence — sequential KLT odometry with feature carry-over, keyframes, re-detection and the motion-distortion
+solve — through the drop-in modules (radarslampy_b200/odometry.py), against the same loop made of the
+reference's third-party calls on the CPU (oracle/ref_system.py).  BASELINE.json configs[1]/[2] at test size.
+Tolerances (north_star): per-frame pose within 1e-4 m / 1e-5 rad."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL_M, TOL_RAD = 1e-4, 1e-5
+
+
+@pytest.fixture(scope="module")
+def sequence():
+    from radarslampy_b200 import synthetic as S
+    world = S.World(seed=4321)
+    raw, poses = S.make_sequence(7, res_m=0.0432, world=world, first=0)
+    return raw, poses
+
+
+def test_system_loop_matches_cpu_reference_loop(sequence):
+    from radarslampy_b200 import odometry
+    from radarslampy_b200.getFeatures import appendNewFeatures
+    from oracle import ref_system
+    raw, gt = sequence
+    got = odometry.run_odometry(raw, init_pose=(0.0, 0.0, 0.0))
+    want = ref_system.run_odometry(raw, lambda cart, old: appendNewFeatures(cart, old)[0])
+    P = len(raw) - 1
+    assert got["R"].shape == (P, 2, 2) and got["traj"].poses.shape == (P + 1, 3)
+    assert got["n_features_in"].tolist() == want["n_features_in"].tolist()
+    assert got["n_tracked"].tolist() == want["n_tracked"].tolist()
+    assert got["retrack"].tolist() == want["retrack"].tolist()
+    assert len(got["map"].keyframes) == want["n_keyframes"]
+    for k in range(P):
+        dth = np.arctan2(got["R"][k][1, 0], got["R"][k][0, 0]) - np.arctan2(want["R"][k][1, 0], want["R"][k][0, 0])
+        assert abs(dth) <= TOL_RAD, (k, dth)
+        assert np.abs(got["h"][k] - want["h"][k]).max() <= TOL_M, (k, got["h"][k].ravel(), want["h"][k].ravel())
+    # the chained absolute poses stay together too (errors accumulate over the 6 frames)
+    d = got["traj"].poses - want["poses"]
+    assert np.abs(d[:, :2]).max() <= 6 * TOL_M and np.abs(d[:, 2]).max() <= 6 * TOL_RAD
+    # and the odometry is right: 2.5 m, 0.025 rad per frame in the synthetic world
+    step = np.linalg.norm(np.diff(got["traj"].poses[:, :2], axis=0), axis=1)
+    assert np.abs(step - 2.5).max() < 0.5 and np.abs(step[3:] - 2.5).max() < 0.05      # the first MDS solves start from zero velocity
+    assert np.all(got["n_tracked"] >= 20)
+    assert np.all(np.isfinite(got["fmt_angle"]))

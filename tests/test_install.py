@@ -1,0 +1,72 @@
+"""CPU: radarslampy_b200.install() makes the reference's bare module names resolve to the drop-in, so that the
+UNMODIFIED reference driver binds to this package's functions.  The binding half needs the
+reference checkout (authoring container only); nothing here launches a kernel."""
+import importlib
+import sys
+
+import pytest
+
+import radarslampy_b200 as pkg
+from oracle import ref_import as ri
+
+ALIASES = pkg.HOT_PATH_MODULES + pkg.OPTIONAL_MODULES
+
+
+@pytest.fixture()
+def clean_modules():
+    saved = {k: v for k, v in sys.modules.items()}
+    path = list(sys.path)
+    for n in ALIASES + ("RawROAMSystem", "utils", "genFakeData", "Coord"):
+        sys.modules.pop(n, None)
+    yield
+    for k in list(sys.modules):
+        if k not in saved:
+            del sys.modules[k]
+    sys.modules.update(saved)
+    sys.path[:] = path
+
+
+def test_install_aliases_every_hot_path_module(clean_modules):
+    done = pkg.install()
+    assert tuple(done) == pkg.HOT_PATH_MODULES
+    for n in pkg.HOT_PATH_MODULES:
+        m = importlib.import_module(n)
+        assert m.__name__ == f"radarslampy_b200.{n}"
+    import parseData
+    from Tracker import Tracker
+    from Mapping import Keyframe, Map
+    from FMT import getRotationUsingFMT
+    assert parseData.convertPolarImageToCartesian.__module__ == "radarslampy_b200.parseData"
+    assert Tracker.__module__ == "radarslampy_b200.Tracker" and Keyframe.__module__ == "radarslampy_b200.Mapping"
+    assert getRotationUsingFMT.__module__ == "radarslampy_b200.FMT" and Map is not None
+    with pytest.raises(ValueError):
+        pkg.install(["utils"])
+    pkg.uninstall()
+    assert all(n not in sys.modules for n in pkg.HOT_PATH_MODULES)
+
+
+@pytest.mark.skipif(not ri.available(), reason="reference checkout not present (GPU box)")
+def test_unmodified_reference_driver_binds_to_the_dropin(clean_modules):
+    pkg.install()
+    ri.activate()                       # shims (matplotlib / tkinter / skimage stubs) + /root/reference on sys.path
+    with ri.quiet():
+        import RawROAMSystem as S       # the unmodified reference driver
+    for name in ("convertPolarImageToCartesian", "getCartImageFromImgPaths", "getPolarImageFromImgPaths", "getRadarImgPaths"):
+        assert getattr(S, name).__module__ == "radarslampy_b200.parseData", name
+    assert S.appendNewFeatures.__module__ == "radarslampy_b200.getFeatures"
+    assert S.Tracker.__module__ == "radarslampy_b200.Tracker"
+    assert S.MotionDistortionSolver.__module__ == "radarslampy_b200.motionDistortion"
+    assert S.Keyframe.__module__ == "radarslampy_b200.Mapping" and S.Map.__module__ == "radarslampy_b200.Mapping"
+    assert S.RANGE_RESOLUTION_CART_M == 0.0432 * 2 and S.N_FEATURES_BEFORE_RETRACK == 60
+    # modules the package does not replace still come from the reference
+    assert S.Trajectory.__module__ == "trajectoryPlotting" and "reference" in sys.modules["utils"].__file__
+
+
+def test_install_refuses_after_reference_import(clean_modules):
+    if not ri.available():
+        pytest.skip("reference checkout not present")
+    ri.activate()
+    with ri.quiet():
+        import parseData  # noqa: F401  (the reference's)
+    with pytest.raises(RuntimeError):
+        pkg.install()
