@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--res", type=float, default=0.0438, help="range resolution m/bin (BASELINE: 0.0438; reference: 0.0432)")
     ap.add_argument("--mds", type=int, default=0, help="1 = motion-distortion solve enabled (configs[2])")
     ap.add_argument("--write-f32", type=int, default=0, help="also materialise the f32 Cartesian image per frame")
-    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = 2 x cores)")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = 8 x cores: about 15-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batches", type=int, default=3, help="batches in flight on one handle (pipeline depth)")
     return ap.parse_args()
@@ -190,7 +190,7 @@ def run_reference(args, rank, world):
         return
     rb, kmax, raw, poses, pair_idx, feats, counts = workload(args, 0)
     cores = os.cpu_count() or 1
-    n_pairs = args.cpu_pairs or min(args.frames - 1, 2 * cores)
+    n_pairs = args.cpu_pairs or min(args.frames - 1, 8 * cores)
     times = []
     for i in range(args.warmup + args.steps):
         rate, workers, n_used, dt = cpu_reference_rate(args, raw, feats, counts, poses, n_pairs)
@@ -263,7 +263,7 @@ def main():
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         # timed BEFORE the CUDA context exists (fork-safe), on a bounded sample of the same workload
         cores = os.cpu_count() or 1
-        n_pairs = args.cpu_pairs or min(args.frames - 1, 2 * cores)
+        n_pairs = args.cpu_pairs or min(args.frames - 1, 8 * cores)
         rate, workers, n_used, dt = cpu_reference_rate(args, raw_np, feats, counts, poses, n_pairs, repeats=2)
         cpu_line = {"value": rate, "unit": "frames/s", "cores": workers, "kind": "port",
                     "sample": f"first {n_used} pairs of the same sequence through oracle/ref_pipeline.py (the reference's own "

@@ -221,6 +221,14 @@ RF_API int rf_batch_fmt(rf_handle* h, rf_batch* b, int downsample, int clip_px, 
 RF_API int rf_chain_poses(rf_handle* h, const double* R, const double* hv, int P, const double* start_pose,
                    int left_multiply, double* poses_out);
 
+/* ---- N4  raw-scan ingest                                  parseData.py:160-179 ------ */
+/* Parallel host-side decode of the radar scan container (8-bit grayscale non-interlaced PNG) — what
+ * cv2.imread(path, cv2.IMREAD_GRAYSCALE) does one file at a time.  n files -> out [n, rows, cols] u8 (typically a
+ * pinned rf_host_alloc buffer handed to rf_batch_upload_async); threads <= 0 uses every host core.  No handle:
+ * errors are reported through rf_last_error(NULL). */
+RF_API int rf_png_info(const char* path, int* rows, int* cols);
+RF_API int rf_ingest_png(const char* const* paths, int n, int rows, int cols, int threads, uint8_t* out);
+
 /* ---- a11 fused pair / batch: Tracker.track + getTransform (+ MDS)  Tracker.py:35-127 */
 RF_API int rf_batch_create(rf_handle* h, rf_batch** out);
 RF_API void rf_batch_destroy(rf_handle* h, rf_batch* b);

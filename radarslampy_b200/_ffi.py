@@ -51,7 +51,7 @@ SYMBOLS = [
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
     "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_log_polar",
-    "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses",
+    "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses", "rf_png_info", "rf_ingest_png",
 ]
 STAGES = ("polar2cart", "scan_to_l0l1", "pyr_down", "klt", "compact", "reject", "kabsch", "mds", "finish")
 
@@ -101,6 +101,35 @@ def _ptr(a):
 
 def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def png_info(path):
+    """(rows, cols) of one scan file (rf_png_info)."""
+    L = load_library()
+    r, c = C.c_int(0), C.c_int(0)
+    rc = L.rf_png_info(os.fsencode(path), C.byref(r), C.byref(c))
+    if rc:
+        raise ValueError(L.rf_last_error(None).decode())
+    return r.value, c.value
+
+
+def ingest_png(paths, threads=0, out=None, pinned=False):
+    """Decode scan files in parallel (rf_ingest_png) -> u8 [n, rows, cols]; `out` may be a pinned staging array."""
+    L = load_library()
+    paths = [os.fsencode(p) for p in paths]
+    n = len(paths)
+    if n == 0:
+        return np.empty((0, 0, 0), np.uint8)
+    if out is None:
+        rows, cols = png_info(paths[0])
+        out = pinned_empty((n, rows, cols), np.uint8) if pinned else np.empty((n, rows, cols), np.uint8)
+    if out.dtype != np.uint8 or out.ndim != 3 or out.shape[0] < n or not out.flags.c_contiguous:
+        raise ValueError("ingest_png: `out` must be a C-contiguous u8 [>= n, rows, cols] array")
+    arr = (C.c_char_p * n)(*paths)
+    rc = L.rf_ingest_png(arr, n, out.shape[1], out.shape[2], int(threads), _ptr(out))
+    if rc:
+        raise ValueError(L.rf_last_error(None).decode())
+    return out[:n]
 
 
 class _PinnedOwner:

@@ -22,6 +22,9 @@
 #define KLT_WIN 15
 #define KLT_NPIX 225
 #define KLT_PER_LANE 8
+#ifndef KLT_MIN_BLOCKS
+#define KLT_MIN_BLOCKS 4   // resident CTAs per SM the register allocation is capped for; 4, 5 (96 regs) and 6 (80 regs, spills) measured equal
+#endif
 
 struct KltArgs {
     FrameSet prev, next;
@@ -38,8 +41,9 @@ struct KltArgs {
     int gate;
 };
 
-struct WarpSmem {
-    uint8_t I[18][20];   // previous-image neighbourhood, origin (ip.x-1, ip.y-1)
+struct __align__(16) WarpSmem {
+    uint8_t I[18][20];   // previous-image neighbourhood, origin (ip.x-1, ip.y-1); rows are 5 aligned words
+    uint8_t pad_[8];     // keeps D and J 16-byte aligned (vector stores in the staging fast paths)
     short2 D[16][16];    // Scharr (dx, dy) at (ip.x + c, ip.y + r)
     uint8_t J[16][16];   // next-image window, origin (in.x, in.y)
 };
@@ -60,11 +64,24 @@ __device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01
     w11 = 16384 - w00 - w01 - w10;
 }
 
+// Stage the 16x16 next-image window at (ox, oy).  Interior windows (the common case) are read as aligned 32-bit
+// words: lane = 2 * row + half moves 8 consecutive bytes (three aligned loads, two funnel shifts, one 64-bit
+// shared store).  The third word may reach 3 bytes past the window: into the same row, the next row, or the slack
+// every level allocation carries.  Windows that touch the border take the REFLECT_101 byte path.
 __device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ J, int w, int h, int ox, int oy, int lane) {
+    if (ox >= 0 && oy >= 0 && ox + 16 <= w && oy + 16 <= h) {
+        const int r = lane >> 1, c0 = (lane & 1) * 8;
+        const uint8_t* p = J + (size_t)(oy + r) * w + ox + c0;
+        const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
+        const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
+        *reinterpret_cast<uint2*>(&s.J[r][c0]) = make_uint2(__funnelshift_r(w0, w1, 8 * m), __funnelshift_r(w1, w2, 8 * m));
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int idx = lane + 32 * k, r = idx >> 4, c = idx & 15;
-        s.J[r][c] = __ldg(J + (size_t)reflect101(oy + r, h) * w + reflect101(ox + c, w));
+        for (int k = 0; k < 8; ++k) {
+            const int idx = lane + 32 * k, r = idx >> 4, c = idx & 15;
+            s.J[r][c] = __ldg(J + (size_t)reflect101(oy + r, h) * w + reflect101(ox + c, w));
+        }
     }
     __syncwarp();
 }
@@ -74,7 +91,7 @@ __device__ __forceinline__ int j_sample(const WarpSmem& s, int y, int x, int w00
     return (v + (1 << 8)) >> 9;
 }
 
-__global__ void __launch_bounds__(KLT_WARPS * 32) k_klt(const KltArgs a) {
+__global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const KltArgs a) {
     __shared__ WarpSmem smem[KLT_WARPS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * KLT_WARPS + wib;
@@ -122,9 +139,24 @@ __global__ void __launch_bounds__(KLT_WARPS * 32) k_klt(const KltArgs a) {
 
         __syncwarp();
         // 1. 18x18 neighbourhood (324 bytes)
-        for (int idx = lane; idx < 18 * 18; idx += 32) {
-            const int r = idx / 18, c = idx - r * 18;
-            s.I[r][c] = __ldg(I + (size_t)reflect101(ipy - 1 + r, h) * w + reflect101(ipx - 1 + c, w));
+        if (ipx >= 1 && ipy >= 1 && ipx + 17 <= w && ipy + 17 <= h) {
+            // interior: lane r < 18 moves row r (18 bytes -> five words of the 20-byte shared row) from aligned loads
+            if (lane < 18) {
+                const uint8_t* p = I + (size_t)(ipy - 1 + lane) * w + (ipx - 1);
+                const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
+                const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
+                uint32_t q[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) q[i] = __ldg(ap + i);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&s.I[lane][0]);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) dst[i] = __funnelshift_r(q[i], q[i + 1], 8 * m);
+            }
+        } else {
+            for (int idx = lane; idx < 18 * 18; idx += 32) {
+                const int r = idx / 18, c = idx - r * 18;
+                s.I[r][c] = __ldg(I + (size_t)reflect101(ipy - 1 + r, h) * w + reflect101(ipx - 1 + c, w));
+            }
         }
         __syncwarp();
         // 2. Scharr at the 16x16 positions (cv::calcSharrDeriv; zero outside the image)

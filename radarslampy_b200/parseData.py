@@ -67,13 +67,19 @@ def convertRawScanToCartesian(polarImgData: np.ndarray, maxRangeClipM: float = M
     return _engine.wrap(cart, fe, frame)
 
 
-# ---- file access (parseData.py:160-226): PNG decode stays on the host ---------------------------
+# ---- file access (parseData.py:160-226): PNG decode on the host cores (csrc/ingest.cu) -----------
+def readRadarScans(imgPathArr: List[str], threads: int = 0, pinned: bool = False) -> np.ndarray:
+    """All the scans of a sequence at once, decoded in parallel on the host cores (rf_ingest_png): u8 [n, A, 3779]."""
+    from . import _ffi
+    return _ffi.ingest_png(imgPathArr, threads=threads, pinned=pinned)
+
+
 def getDataFromImgPathsByIndex(imgPathArr: List[str], index: int):
-    import cv2
-    imgPolarData = cv2.imread(imgPathArr[index], cv2.IMREAD_GRAYSCALE)
-    if imgPolarData is None:
+    """parseData.py:160-179 (cv2.imread(..., IMREAD_GRAYSCALE) replaced by the library's own decoder)."""
+    from . import _ffi
+    if not os.path.exists(imgPathArr[index]):
         raise FileNotFoundError(imgPathArr[index])
-    return extractDataFromRadarImage(imgPolarData)
+    return extractDataFromRadarImage(_ffi.ingest_png([imgPathArr[index]], threads=1)[0])
 
 
 def getPolarImageFromImgPaths(imgPathArr: List[str], index: int) -> np.ndarray:
