@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = 8 x cores: about 15-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batches", type=int, default=3, help="batches in flight on one handle (pipeline depth)")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (multi-GPU runs)")
+    ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the per-step NCCL pose gather")
     return ap.parse_args()
 
 
@@ -222,6 +224,31 @@ def workload_config(args, rb, kmax):
 
 
 # ---------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index: int):
+    """Pin this process (and so the pinned staging buffers it allocates next: first touch) to the host cores of the
+    NUMA node GPU `index` hangs off.  With several ranks on one box every rank otherwise stages through whichever
+    socket the launcher left it on, and the H2D streams of the far-socket GPUs cross the inter-socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        dev = f"{int(dom, 16):04x}:{rest.lower()}"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{dev}/local_cpulist").read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read().strip())
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "pci": dev}
+    except Exception as e:      # no NVML / sysfs (containers): leave the affinity alone
+        return {"node": None, "cpus": None, "error": type(e).__name__}
+
+
 def emit(line: dict):
     """The ONE JSON line goes to the process's original stdout (see main)."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -258,6 +285,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa) else {"node": None, "cpus": None}
     rb, kmax, raw_np, poses, pair_idx, feats, counts = workload(args, rank)
     cpu_line = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
@@ -316,7 +344,7 @@ def main():
 
     def gather_poses(res_host):
         """trajectory concatenation: poses of every rank to rank 0 over NCCL"""
-        if world > 1:
+        if world > 1 and not args.no_gather:
             gatherer.gather(_shard.pack_records(res_host))
 
     def upload(b):
@@ -425,6 +453,7 @@ def main():
                      "alg_bytes_per_launch": sb[dom], "ms_per_launch": stages[dom]["ms"]},
         "stages": stages,
         "clocks": clocks,
+        "numa": numa,
         "pose_check": {"median_dtheta_rad": float(np.median(np.arctan2(res["R"][:, 2], res["R"][:, 0]))),
                        "expected_dtheta_rad": 0.025, "median_inliers": float(np.median(res["n_inliers"])),
                        "worklimit_pairs": int((res["status"] != 0).sum())},
