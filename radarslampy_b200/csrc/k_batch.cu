@@ -32,6 +32,8 @@
 // overwrites the track buffers.  rf_sync / the timers join all three.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define RF_PROFILE_RING 64
@@ -58,6 +60,11 @@ struct rf_batch {
     cudaStream_t tail;
     cudaEvent_t ev_uploaded, ev_main_done, ev_tail_done;
 };
+
+// RADARFE_KLT_ON_TAIL=1 moves KLT from the handle's main stream to the batch's tail stream.  Measured on B200 (r01g):
+// +2.5 % with >= 4 batches in flight, -4.5 % with 3 — the scan kernel's CTAs fill the shared memory of every SM, so the
+// two kernels take turns rather than co-run; the default keeps KLT on the main stream.
+static const bool g_klt_on_tail = []() { const char* e = getenv("RADARFE_KLT_ON_TAIL"); return e && e[0] == '1'; }();
 
 // Launchers take their stream from the handle: run a scope on another stream.
 struct StreamScope {
@@ -206,7 +213,9 @@ int rf_batch_create(rf_handle* h, rf_batch** out) {
     RF_BALLOC(b->d_mds_scratch, P * K * 5 * sizeof(double));
     RF_BALLOC(b->d_corr, P * K);
     RF_BALLOC(b->d_results, P * sizeof(rf_pair_result));
-    if (cudaStreamCreateWithFlags(&b->tail, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // tail streams run above the image kernels of later batches
+    if (cudaStreamCreateWithPriority(&b->tail, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_tail_done, cudaEventDisableTiming) != cudaSuccess) {
@@ -290,6 +299,8 @@ int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
     auto mark = [&]() { if (ev) cudaEventRecord(ev[stage], h->stream); ++stage; };
     int rc;
     RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_uploaded, 0));
+    // with KLT on the tail stream the previous run's tail still reads this batch's pyramid: wait before rebuilding it
+    if (g_klt_on_tail && P) RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_tail_done, 0));
     mark();
     const bool fused = b->fs.cart == nullptr && b->fs.n_levels >= 2;
     if (F && fused) {
@@ -310,17 +321,28 @@ int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
         mark();
     }
     if (P) {
-        // the tail of this batch's previous run still reads the track buffers KLT is about to overwrite
-        RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_tail_done, 0));
+        // KLT either closes the main-stream part (klt_on_tail = 0) or opens the tail-stream part: on the (high-priority)
+        // tail stream it co-runs with the image kernels of the NEXT batch instead of queueing behind/before them
+        const bool klt_on_tail = g_klt_on_tail;
+        if (klt_on_tail) {
+            RF_CUDA(h, cudaEventRecord(b->ev_main_done, h->stream));
+            RF_CUDA(h, cudaStreamWaitEvent(b->tail, b->ev_main_done, 0));
+        } else {
+            // the tail of this batch's previous run still reads the track buffers KLT is about to overwrite
+            RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_tail_done, 0));
+        }
+        StreamScope on_tail(h, klt_on_tail ? b->tail : h->stream);
         if ((rc = rf_launch_klt(h, b->fs, b->fs, b->d_pair_idx, b->d_feats, b->d_counts, K, P, b->d_next, b->d_status,
                                 b->d_err, 1))) return rc;
         mark();
         k_compact_good<<<(P + 3) / 4, 128, 0, h->stream>>>(b->d_feats, b->d_next, b->d_status, b->d_counts, K, P,
                                                            b->d_good_old, b->d_good_new, b->d_good_src, b->d_ngood);
         RF_CHECK_LAUNCH(h);
-        RF_CUDA(h, cudaEventRecord(b->ev_main_done, h->stream));
-        RF_CUDA(h, cudaStreamWaitEvent(b->tail, b->ev_main_done, 0));
-        StreamScope on_tail(h, b->tail);     // everything below runs on the batch's tail stream
+        if (!klt_on_tail) {
+            RF_CUDA(h, cudaEventRecord(b->ev_main_done, h->stream));
+            RF_CUDA(h, cudaStreamWaitEvent(b->tail, b->ev_main_done, 0));
+            h->stream = b->tail;             // everything below runs on the batch's tail stream (restored by on_tail)
+        }
         mark();
         uint8_t* d_mask; int mask_stride; int32_t *d_ninl, *d_nodes, *d_cstatus;
         if ((rc = rf_launch_reject(h, b->d_clique_ws, b->d_good_old, b->d_good_new, b->d_ngood, K, P, &d_mask, &mask_stride,
