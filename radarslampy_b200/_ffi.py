@@ -281,15 +281,26 @@ class Batch:
 class Frame:
     """Device-resident scan (f32 Cartesian image + u8 LK pyramid)."""
 
+    POOL_MAX = 8    # released frames kept per handle: a sequential caller allocates device memory only for the first few scans
+
     def __init__(self, fe):
         self.fe = fe
+        pool = fe._frame_pool
+        if pool:
+            self.p = pool.pop()          # every frame of a handle has the same geometry
+            return
         p = C.c_void_p()
         fe._check(fe.lib.rf_frame_create(fe.h, C.byref(p)))
         self.p = p
 
     def close(self):
+        """Release the frame: back to the handle's pool (cudaMalloc / cudaFree cost milliseconds per frame), or
+        destroyed when the pool is full.  Every entry point that touches a frame is synchronous, so no work is pending."""
         if self.p and self.fe.h:
-            self.fe.lib.rf_frame_destroy(self.fe.h, self.p)
+            if len(self.fe._frame_pool) < self.POOL_MAX:
+                self.fe._frame_pool.append(self.p)
+            else:
+                self.fe.lib.rf_frame_destroy(self.fe.h, self.p)
         self.p = None
 
     def __del__(self):
@@ -311,6 +322,7 @@ class RadarFE:
     """One rf_handle: a CUDA stream, the geometry table and the workspaces on one GPU."""
 
     def __init__(self, cfg: RfConfig = None, device: int = 0, stream: int = None):
+        self._frame_pool = []
         self.lib = load_library()
         self.cfg = cfg if cfg is not None else default_config()
         h = C.c_void_p()
@@ -325,6 +337,9 @@ class RadarFE:
     # -- plumbing ---------------------------------------------------------------
     def close(self):
         if getattr(self, "h", None):
+            for p in self._frame_pool:
+                self.lib.rf_frame_destroy(self.h, p)
+            self._frame_pool = []
             self.lib.rf_destroy(self.h)
             self.h = None
 
@@ -515,7 +530,7 @@ class RadarFE:
         polar = _c(polar, np.float32)
         A, W = polar.shape
         cap = A * (W // 2 + 1)
-        out = np.zeros((cap, 2), np.int64)
+        out = np.empty((cap, 2), np.int64)
         n = C.c_int64(0)
         self._check(self.lib.rf_polar_peaks(self.h, _ptr(polar), A, W, _ptr(out), C.c_int64(cap), C.byref(n)))
         return out[:n.value].copy()

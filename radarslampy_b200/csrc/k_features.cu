@@ -144,10 +144,10 @@ extern "C" int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double
     size_t need = kp_bytes + sel_bytes + 256;
     int rc = rf_ensure_scratch(h, need);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per device: the attribute belongs to the device's context
+    if (!attr_set[h->device & 63]) {
         RF_CUDA(h, cudaFuncSetAttribute(k_ssc_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, SSC_SMEM_MAX));
-        attr_set = true;
+        attr_set[h->device & 63] = true;
     }
     if (n) RF_CUDA(h, cudaMemcpyAsync(h->d_scratch, kp, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     int nres = 0;           // len(result) of the most recent pass
@@ -599,10 +599,10 @@ extern "C" int rf_polar_peaks(rf_handle* h, const float* polar, int A, int W, in
     int32_t* d_cnt = (int32_t*)(base + polar_b + rows_b);
     int64_t* d_out = (int64_t*)(base + polar_b + rows_b + cnt_b);
     long long* d_n = (long long*)(base + polar_b + rows_b + cnt_b + out_b);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per device: the attribute belongs to the device's context
+    if (!attr_set[h->device & 63]) {
         RF_CUDA(h, cudaFuncSetAttribute(k_peaks_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set[h->device & 63] = true;
     }
     RF_CUDA(h, cudaMemcpyAsync(d_polar, polar, (size_t)A * W * 4, cudaMemcpyHostToDevice, h->stream));
     k_peaks_rows<<<A, 256, smem, h->stream>>>(d_polar, W, d_rows, row_cap, d_cnt);

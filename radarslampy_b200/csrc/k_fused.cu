@@ -472,10 +472,10 @@ size_t rf_interleave_words(const rf_handle* h, int max_frames) {
 int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames) {
     if (h->n % 4) return rf_fail(h, RF_E_BADARG, "cartesian size %d is not a multiple of 4", h->n);
     if (fs.n_levels < 2) return rf_fail(h, RF_E_BADARG, "fused image path needs at least two pyramid levels");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per device: the attribute belongs to the device's context
+    if (!attr_set[h->device & 63]) {
         RF_CUDA(h, cudaFuncSetAttribute(k_scan16_to_l0l1, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
-        attr_set = true;
+        attr_set[h->device & 63] = true;
     }
     FusedArgs a;
     a.rawi = reinterpret_cast<const uint4*>(d_rawi); a.Wp = rf_fused_wp(h); a.A = h->cfg.azimuths; a.group_stride = (size_t)a.A * a.Wp;
