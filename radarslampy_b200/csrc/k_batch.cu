@@ -213,6 +213,14 @@ int rf_batch_create(rf_handle* h, rf_batch** out) {
     RF_BALLOC(b->d_mds_scratch, P * K * 5 * sizeof(double));
     RF_BALLOC(b->d_corr, P * K);
     RF_BALLOC(b->d_results, P * sizeof(rf_pair_result));
+    // slots k >= feat_counts[p] are never written by the kernels: define them (0) instead of leaving whatever the
+    // allocator recycled, so that the [P][Kmax] outputs are reproducible bit for bit (found under compute-sanitizer)
+    if (cudaMemset(b->d_next, 0, P * K * 2 * sizeof(float)) != cudaSuccess || cudaMemset(b->d_status, 0, P * K) != cudaSuccess ||
+        cudaMemset(b->d_err, 0, P * K * sizeof(float)) != cudaSuccess || cudaMemset(b->d_corr, 0, P * K) != cudaSuccess ||
+        cudaMemset(b->d_feats, 0, P * K * 2 * sizeof(float)) != cudaSuccess) {
+        batch_free(b);
+        return rf_fail(h, RF_E_CUDA, "rf_batch_create: cudaMemset failed");
+    }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // tail streams run above the image kernels of later batches
     if (cudaStreamCreateWithPriority(&b->tail, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||

@@ -429,8 +429,10 @@ __device__ __noinline__ int set_pop(const SetRef& s, int K, int NWe, int lane) {
                 }
             }
         }
+        __syncwarp();                               // every lane has read the table before lane 0 rewrites a slot
         if (lane == 0) s.tab()[slot] = DUMMY_SLOT;
     }
+    __syncwarp();                                   // ... and the bit set (racecheck: explicit read -> write order)
     if (lane == 0) {
         s.bits()[found >> 5] &= ~(1u << (found & 31));
         s.used() -= 1;
@@ -608,6 +610,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                 if (fast) {
                     const unsigned bm = __ballot_sync(FULL, univ);
                     n_univ += __popc(bm);
+                    __syncwarp();
                     if (ident && lane == 0) D[i0 >> 5] = bm;
                 }
             }
