@@ -157,3 +157,31 @@ def test_mds_undistort_matches_reference_formula(fe):
     ex = np.cos(th) * pts[:, 0] - np.sin(th) * pts[:, 1] + v[0] * t
     ey = np.sin(th) * pts[:, 0] + np.cos(th) * pts[:, 1] + v[1] * t
     assert np.abs(out - np.column_stack([ex, ey])).max() < 1e-12
+
+
+def test_mds_recovers_known_motion(fe):
+    """Property (the recipe of the reference's testMotionDistortion.py: distort <-> undistort round trip): observations
+    made consistent with a known velocity and pose have zero residual there, and the solve returns that motion from a
+    perturbed start."""
+    rng = np.random.default_rng(11)
+    period = 0.25
+    v = np.array([9.0, -0.6, 0.09])                                   # m/s, m/s, rad/s
+    pose = np.array([35.0, -12.0, 0.8])
+    p_jt = rng.uniform(-80, 80, (120, 2))                             # observed (distorted) points, sensor frame
+    t = period * np.arctan2(-p_jt[:, 1], -p_jt[:, 0]) / (2 * np.pi)   # motionDistortion.py:107-124
+    th = v[2] * t
+    q = np.column_stack([np.cos(th) * p_jt[:, 0] - np.sin(th) * p_jt[:, 1] + v[0] * t,
+                         np.sin(th) * p_jt[:, 0] + np.cos(th) * p_jt[:, 1] + v[1] * t])   # undistorted, frame j
+
+    def T(p):
+        c, s = np.cos(p[2]), np.sin(p[2])
+        return np.array([[c, -s, p[0]], [s, c, p[1]], [0, 0, 1.0]])
+
+    T_wj = T(pose)
+    p_w = (T_wj[:2, :2] @ q.T).T + T_wj[:2, 2]
+    T_wj0 = T_wj @ np.linalg.inv(T(v * period))                       # previous pose consistent with the velocity prior
+    start = T(pose + [0.4, -0.3, 0.01])
+    x, iters, cost = fe.mds_solve(T_wj0, p_w, p_jt, start, period=period)
+    assert cost < 1e-12
+    assert np.abs(x[:2] - v[:2]).max() < 1e-4 and abs(x[2] - v[2]) < 1e-5
+    assert np.abs(x[3:5] - pose[:2]).max() < 1e-4 and abs(x[5] - pose[2]) < 1e-5
