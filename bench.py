@@ -110,7 +110,8 @@ def workload(args, rank):
     from radarslampy_b200 import synthetic as S
     rb = int(87.5 / args.res)
     world = S.World(seed=1234 + rank)
-    raw, poses = S.make_sequence(args.frames, res_m=args.res, world=world, first=0)
+    # configs[2] (--mds 1): the same sequence rendered with intra-scan motion distortion
+    raw, poses = S.make_sequence(args.frames, res_m=args.res, world=world, first=0, distort=bool(args.mds))
     kmax = max(64, (args.features + 63) // 64 * 64)
     pair_idx, feats, counts = S.sequence_pairs(args.frames, world, poses, args.res, rb, k=args.features, max_features=kmax)
     return rb, kmax, raw, poses, pair_idx, feats, counts
@@ -217,7 +218,7 @@ def run_reference(args, rank, world):
 def workload_config(args, rb, kmax):
     return {"workload": f"synthetic Oxford-shaped sequence, {args.frames} scans/GPU/step (400x3768 u8 + 11 metadata bytes, "
                         f"{args.res} m/bin -> {rb} used bins, {2 * (rb // 2)}^2 Cartesian), {args.features} features/pair given, "
-                        f"KLT 15x15 x 4 levels, clique rejection, Kabsch" + (", motion-distortion LM" if args.mds else ""),
+                        f"KLT 15x15 x 4 levels, clique rejection, Kabsch" + (", scans rendered with intra-scan motion distortion, motion-distortion LM" if args.mds else ""),
             "frames_per_step_per_gpu": args.frames, "pairs_per_step_per_gpu": args.frames - 1, "features_per_pair": args.features,
             "range_res_m": args.res, "mds": bool(args.mds), "write_cart_f32": bool(args.write_f32),
             "l2": "inputs larger than L2: each step streams >= 1.3 GB of scans + pyramids per GPU (L2 = 126 MB)"}

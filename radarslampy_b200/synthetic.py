@@ -39,10 +39,33 @@ def sensor_points(world_xy, pose):
     return np.column_stack([c * d[:, 0] + s * d[:, 1], -s * d[:, 0] + c * d[:, 1]])
 
 
+def twist_poses(k, v=10.0, w=0.10, hz=4.0):
+    """twist_pose for an array of (fractional) frame indices -> [n, 3]."""
+    t = np.asarray(k, np.float64) / hz
+    th = w * t
+    if abs(w) < 1e-12:
+        return np.column_stack([v * t, np.zeros_like(t), np.zeros_like(t)])
+    return np.column_stack([v / w * np.sin(th), v / w * (1 - np.cos(th)), th])
+
+
+def distorted_sensor_points(world_xy, frame_idx, v, w):
+    """Intra-scan motion distortion (BASELINE configs[2]): every scatterer is seen from the pose the sensor has when the
+    beam sweeps over it.  Timing follows the model the reference's solver assumes (motionDistortion.py:107-124):
+    the frame's pose is the mid-scan pose and the beam at azimuth row a fires (a / 400 - 0.5) scan periods later."""
+    ps = sensor_points(world_xy, twist_pose(frame_idx, v, w))
+    for _ in range(3):                                  # fixed point: the firing time depends on the observed azimuth
+        frac = (np.arctan2(ps[:, 1], ps[:, 0]) % (2 * np.pi)) / (2 * np.pi) - 0.5
+        pose = twist_poses(frame_idx + frac, v, w)
+        c, s = np.cos(pose[:, 2]), np.sin(pose[:, 2])
+        d = world_xy - pose[:, :2]
+        ps = np.column_stack([c * d[:, 0] + s * d[:, 1], -s * d[:, 0] + c * d[:, 1]])
+    return ps
+
+
 def render_scan(world: World, pose, frame_idx, res_m=0.0438, t0_us=1_547_131_046_000_000, speckle_mean=8.0,
-                sigma_r=2.5, sigma_a=0.6, seed=5678):
-    """One raw scan uint8 [400, 3779]."""
-    ps = sensor_points(world.xy, pose)
+                sigma_r=2.5, sigma_a=0.6, seed=5678, distort=None):
+    """One raw scan uint8 [400, 3779].  distort = (v, w) renders intra-scan motion distortion for that twist."""
+    ps = sensor_points(world.xy, pose) if distort is None else distorted_sensor_points(world.xy, frame_idx, *distort)
     rb = np.hypot(ps[:, 0], ps[:, 1]) / res_m                       # range in bins
     az = (np.arctan2(ps[:, 1], ps[:, 0]) % (2 * np.pi)) / (2 * np.pi) * A   # azimuth in rows
     keep = rb < BINS + 8
@@ -72,14 +95,14 @@ def render_scan(world: World, pose, frame_idx, res_m=0.0438, t0_us=1_547_131_046
     return raw
 
 
-def make_sequence(n_frames, res_m=0.0438, world: World = None, v=10.0, w=0.10, first=0, out=None):
-    """raw [n_frames, 400, 3779] uint8 and the ground-truth poses [n_frames, 3]."""
+def make_sequence(n_frames, res_m=0.0438, world: World = None, v=10.0, w=0.10, first=0, out=None, distort=False):
+    """raw [n_frames, 400, 3779] uint8 and the ground-truth (mid-scan) poses [n_frames, 3]."""
     world = world or World()
     raw = out if out is not None else np.empty((n_frames, A, RAW_WIDTH), np.uint8)
     poses = np.zeros((n_frames, 3))
     for k in range(n_frames):
         poses[k] = twist_pose(first + k, v, w)
-        raw[k] = render_scan(world, poses[k], first + k, res_m=res_m)
+        raw[k] = render_scan(world, poses[k], first + k, res_m=res_m, distort=(v, w) if distort else None)
     return raw, poses
 
 
