@@ -68,21 +68,31 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, disabled=False, n_gpus=1):
         self.index = index
+        self.disabled = disabled
+        self.n_gpus = n_gpus
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
     def start(self):
+        if self.disabled:
+            return
+        self._start()
+
+    def _start(self):
+        """index = None samples every GPU of the box from ONE nvidia-smi process (multi-GPU runs: rank 0 only, so that
+        eight samplers do not poll the driver while eight ranks are being timed)."""
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            sel = [] if self.index is None else ["-i", str(self.index)]
+            self.p = subprocess.Popen(["nvidia-smi"] + sel + [f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                                               "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable" if not self.disabled else "sampled by rank 0"]}
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -94,6 +104,8 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
+                if self.index is None and int(r[0]) >= self.n_gpus:
+                    continue                      # a GPU of the box this job does not use
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except ValueError:
                 continue
@@ -361,7 +373,8 @@ def main():
     fe.sync()
     for b in batches:
         b.stage_times()
-    sampler = ClockSampler(local_rank)
+    # one GPU: sample it; several: rank 0 samples all of them (the GPUs the job's ranks run on)
+    sampler = ClockSampler(local_rank if world == 1 else None, disabled=(world > 1 and rank != 0), n_gpus=world)
     barrier()
     sampler.start()
     n0 = fe.launch_count()
