@@ -381,7 +381,10 @@ __global__ void __launch_bounds__(256, FT_SCAN_MIN_BLOCKS) k_scan16_to_l0l1(cons
 // pyrDown for the higher levels: each warp loads its FT_RH x 132 source tile from global memory
 // (REFLECT_101), then the same shared-memory pass.  4 warps per CTA, one tile each.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8)
+#ifndef FT_PYR_MIN_BLOCKS
+#define FT_PYR_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, FT_PYR_MIN_BLOCKS)
 k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh, uint8_t* __restrict__ dst,
              size_t dst_stride, int dw, int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
     __shared__ uint32_t s_tile[4][FT_TILE_WORDS];

@@ -18,7 +18,9 @@
 // to ~5e-4 px (tolerance in north_star: 0.02 px) and status/err gating is identical.
 #include "common.cuh"
 
+#ifndef KLT_WARPS
 #define KLT_WARPS 4
+#endif
 #define KLT_WIN 15
 #define KLT_NPIX 225
 #define KLT_PER_LANE 8
