@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--write-f32", type=int, default=0, help="also materialise the f32 Cartesian image per frame")
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = 8 x cores: about 15-20 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batches", type=int, default=3, help="batches in flight on one handle (pipeline depth)")
+    ap.add_argument("--batches", type=int, default=5, help="batches in flight on one handle (pipeline depth; the clique + MDS tail of a batch lasts about three steps)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (multi-GPU runs)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the per-step NCCL pose gather")
     return ap.parse_args()
