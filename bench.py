@@ -450,6 +450,10 @@ def main():
     streaming = [k for k in ("polar2cart", "scan_to_l0l1", "pyr_down", "klt") if stages[k]["ms"] > 0]
     dom = max(streaming, key=lambda k: stages[k]["ms"])
     achieved = stages[dom]["gbs"] or 0.0
+    lv = [fe.n]
+    for _ in range(3):
+        lv.append((lv[-1] + 1) // 2)
+    survey_bytes = S * (cfg.azimuths * rb + 4 * fe.n * fe.n + sum(v * v for v in lv))      # per launch of the conversion
     value = world * P * args.steps / (ms * 1e-3)
     e2e = world * P * args.steps / (ms_e2e * 1e-3)
     h2d = S * cfg.azimuths * (cfg.meta_bytes + rb) + P * (8 + kmax * 8 + 4 + 24)
@@ -464,7 +468,12 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(dom, S), "peak_source": peak_src,
-                     "alg_bytes_per_launch": sb[dom], "ms_per_launch": stages[dom]["ms"]},
+                     "alg_bytes_per_launch": sb[dom], "ms_per_launch": stages[dom]["ms"],
+                     # SURVEY.md §8(d) counts the reference's materialised f32 Cartesian image (4 n^2 per frame) plus the
+                     # whole u8 pyramid as mandated outputs of the conversion; this kernel never writes the f32 image and
+                     # produces levels 0-1 only, so `achieved` / `frac` above use the smaller, actual figure
+                     "survey_8d_bytes_per_launch": survey_bytes, "survey_8d_frac": (survey_bytes / (stages[dom]["ms"] * 1e-3) / 1e9 / peak)
+                     if dom == "scan_to_l0l1" and stages[dom]["ms"] > 0 else None},
         "stages": stages,
         "clocks": clocks,
         "numa": numa,

@@ -55,16 +55,19 @@ class Keyframe():
         # the reference omits the velocity argument here (Mapping.py:69-71, a TypeError if ever called)
         self.updateInfo(keyframe.pose, keyframe.featurePointsLocal, keyframe.radarPolarImg, keyframe.velocity)
 
+    def _sensor_to_global(self, pts_m: np.ndarray) -> np.ndarray:
+        """Rigid transform of metric sensor-frame points by this keyframe's pose (x, y, theta)."""
+        c, s = np.cos(self.pose[2]), np.sin(self.pose[2])
+        pts_m = np.asarray(pts_m, np.float64)
+        return np.column_stack((c * pts_m[:, 0] - s * pts_m[:, 1] + self.pose[0], s * pts_m[:, 0] + c * pts_m[:, 1] + self.pose[1]))
+
     def convertFeaturesLocalToGlobal(self, featurePointsLocal: np.ndarray) -> np.ndarray:
         """Mapping.py:73-99: pixels -> metres about the image centre -> global frame of this keyframe's pose."""
-        x, y, th = self.pose
-        pts = (np.asarray(featurePointsLocal, np.float64) - RADAR_CART_CENTER) * parseData.RANGE_RESOLUTION_CART_M
-        return (getRotationMatrix(th) @ pts.T + np.array([x, y]).reshape(2, 1)).T
+        return self._sensor_to_global((np.asarray(featurePointsLocal, np.float64) - RADAR_CART_CENTER) * parseData.RANGE_RESOLUTION_CART_M)
 
     def getPrunedFeaturesGlobalPosition(self) -> np.ndarray:
         """Mapping.py:101-120: the pruned, undistorted local points (already metres) in the global frame."""
-        x, y, th = self.pose
-        return (getRotationMatrix(th) @ self.prunedUndistortedLocals.T + np.array([x, y]).reshape(2, 1)).T
+        return self._sensor_to_global(self.prunedUndistortedLocals)
 
     def pruneFeaturePoints(self, corrStatus: np.ndarray) -> None:
         keep = np.asarray(corrStatus).flatten().astype(bool)
