@@ -12,7 +12,7 @@
 //   k_fmt_cart       cv::warpPolar inverse linear map, 2Wd x 2Wd (same roundings as k_build_map + k_polar2cart)
 //   k_fmt_logpolar   cv::warpPolar forward semi-log map (double exp/cos/sin -> f32 map -> 5-bit fixed point ->
 //                    f32 bilinear, BORDER_CONSTANT 0), times the Hann window, zero-padded to the DFT size
-//   k_fmt_dft_rows / k_fmt_dft_cols   2-D real-to-half-complex DFT as two dense passes with shared-memory
+//   k_fmt_dft_rows / k_fmt_dft_cols   2-D real-to-half-complex DFT: direct row sums, Cooley-Tukey split columns, shared-memory
 //                    twiddle tables (sizes are 2^a 3^b 5^c, e.g. 320 x 108: direct sums in f32, tables from f64)
 //   k_fmt_cross      R = F1 conj(F2) |F1 conj(F2)| / (|.|^2 + FLT_EPSILON)   (mulSpectrums / magSpectrums / divSpectrums)
 //   k_fmt_idft_cols / k_fmt_idft_rows  unnormalised inverse, Hermitian rows -> real
@@ -204,15 +204,21 @@ k_fmt_dft_rows(const float* __restrict__ x, int M, int N, int rows, int cols, co
     }
 }
 
-// columns: Zt[f][k][j] = sum_{m < rows} Yt[f][k][m] w_M^{sign j m}.   grid (Nh, F), block <= 256 (loops over j)
+// columns: Zt[f][k][j] = sum_{m < rows} Yt[f][k][m] w_M^{sign j m}.   grid (Nh, F), block <= 256 (loops over outputs)
+// One Cooley-Tukey split M = L1 * L2 (L1 ~ sqrt(M); 320 = 16 * 20): with m = L2 m1 + m2 and j = j1 + L1 j2,
+//   Z[j1 + L1 j2] = sum_{m2} w_M^{m2 j1} ( sum_{m1} y[L2 m1 + m2] w_M^{L2 m1 j1} ) w_M^{L1 m2 j2}
+// i.e. L2 DFTs of length L1, a twiddle, L1 DFTs of length L2: M (L1 + L2) complex MACs per column instead of M^2
+// (8.9x fewer at M = 320).  L1 = 1 degenerates to the direct sum (prime lengths).  All twiddles come from the one
+// table w_M^i (f32 from f64), so every product uses an exactly tabulated root of unity.
 template <int SIGN>
 __global__ void __launch_bounds__(256)
-k_fmt_dft_cols(const float2* __restrict__ Yt, int M, int Nh, int rows, const float2* __restrict__ twM,
+k_fmt_dft_cols(const float2* __restrict__ Yt, int M, int Nh, int rows, int L1, const float2* __restrict__ twM,
                float2* __restrict__ Zt) {
     extern __shared__ float sm[];
-    float2* ys = reinterpret_cast<float2*>(sm);   // [M]
-    float2* tw = ys + M;                          // [M]
-    const int k = blockIdx.x, f = blockIdx.y;
+    float2* ys = reinterpret_cast<float2*>(sm);   // [M] input column (zero beyond `rows`)
+    float2* tw = ys + M;                          // [M] w_M^{sign i}
+    float2* as = tw + M;                          // [M] stage-1 results A[j1][m2] at j1 * L2 + m2
+    const int k = blockIdx.x, f = blockIdx.y, L2 = M / L1;
     const float2* col = Yt + ((size_t)f * Nh + k) * M;
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         ys[i] = i < rows ? col[i] : make_float2(0.0f, 0.0f);
@@ -221,17 +227,36 @@ k_fmt_dft_cols(const float2* __restrict__ Yt, int M, int Nh, int rows, const flo
         tw[i] = w;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    for (int t = threadIdx.x; t < M; t += blockDim.x) {       // A[j1][m2] = w^{m2 j1} sum_{m1} y[L2 m1 + m2] w^{L2 m1 j1}
+        const int j1 = t / L2, m2 = t - j1 * L2;
         float re = 0.0f, im = 0.0f;
         int idx = 0;
-        for (int m = 0; m < rows; ++m) {
-            const float2 w = tw[idx], y = ys[m];
+        const int step = (L2 * j1) % M;
+        for (int m1 = 0; m1 < L1; ++m1) {
+            const float2 w = tw[idx], y = ys[L2 * m1 + m2];
             re = fmaf(y.x, w.x, fmaf(-y.y, w.y, re));
             im = fmaf(y.x, w.y, fmaf(y.y, w.x, im));
-            idx += j;
+            idx += step;
             if (idx >= M) idx -= M;
         }
-        Zt[((size_t)f * Nh + k) * M + j] = make_float2(re, im);
+        const float2 w = tw[(m2 * j1) % M];
+        as[t] = make_float2(re * w.x - im * w.y, re * w.y + im * w.x);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < M; t += blockDim.x) {       // Z[j1 + L1 j2] = sum_{m2} A[j1][m2] w^{L1 m2 j2}
+        const int j2 = t / L1, j1 = t - j2 * L1;
+        float re = 0.0f, im = 0.0f;
+        int idx = 0;
+        const int step = (L1 * j2) % M;
+        const float2* arow = as + j1 * L2;
+        for (int m2 = 0; m2 < L2; ++m2) {
+            const float2 w = tw[idx], y = arow[m2];
+            re = fmaf(y.x, w.x, fmaf(-y.y, w.y, re));
+            im = fmaf(y.x, w.y, fmaf(y.y, w.x, im));
+            idx += step;
+            if (idx >= M) idx -= M;
+        }
+        Zt[((size_t)f * Nh + k) * M + j1 + L1 * j2] = make_float2(re, im);
     }
 }
 
@@ -347,11 +372,13 @@ int fmt_correlate(rf_handle* h, char* ws, const float* d_pad, int F, const int32
     k_fmt_dft_rows<<<dim3(rows, F), 64, (size_t)N * 12, h->stream>>>(d_pad, M, N, rows, cols, twN, Yt);
     RF_CHECK_LAUNCH(h);
     const int passes = (M + 255) / 256, ct = ((M + passes - 1) / passes + 31) / 32 * 32;   // threads per column block
-    k_fmt_dft_cols<-1><<<dim3(Nh, F), ct, (size_t)M * 16, h->stream>>>(Yt, M, Nh, rows, twM, Zt);
+    int L1 = 1;                                    // the divisor of M closest to sqrt(M) from below (320 -> 16)
+    for (int d = 1; d * d <= M; ++d) if (M % d == 0) L1 = d;
+    k_fmt_dft_cols<-1><<<dim3(Nh, F), ct, (size_t)M * 24, h->stream>>>(Yt, M, Nh, rows, L1, twM, Zt);
     RF_CHECK_LAUNCH(h);
     k_fmt_cross<<<dim3((unsigned)((plane + 255) / 256), P), 256, 0, h->stream>>>(Zt, d_pairs, plane, Ct);
     RF_CHECK_LAUNCH(h);
-    k_fmt_dft_cols<1><<<dim3(Nh, P), ct, (size_t)M * 16, h->stream>>>(Ct, M, Nh, M, twM, Dt);
+    k_fmt_dft_cols<1><<<dim3(Nh, P), ct, (size_t)M * 24, h->stream>>>(Ct, M, Nh, M, L1, twM, Dt);
     RF_CHECK_LAUNCH(h);
     k_fmt_idft_rows<<<dim3(M, P), 128, (size_t)(Nh + N) * 8, h->stream>>>(Dt, M, N, twN, c);
     RF_CHECK_LAUNCH(h);
@@ -379,7 +406,7 @@ int fmt_dims(rf_handle* h, int A, int W, int downsample, int clip_px, FmtDims* d
     d->N = optimal_dft_size(d->w_lp);
     if (d->N & 1) d->N = optimal_dft_size(d->N + 1);                // keep the Nyquist column (sizes here are even anyway)
     d->Nh = d->N / 2 + 1;
-    if ((size_t)d->M * 16 > 48 * 1024) return rf_fail(h, RF_E_CAPACITY, "rf_fmt: DFT size %d exceeds shared memory", d->M);
+    if ((size_t)d->M * 24 > 48 * 1024) return rf_fail(h, RF_E_CAPACITY, "rf_fmt: DFT size %d exceeds shared memory", d->M);
     return RF_OK;
 }
 
@@ -509,7 +536,7 @@ int rf_phase_correlate(rf_handle* h, const float* a, const float* b, int rows, i
     const int M = optimal_dft_size(rows);
     int N = optimal_dft_size(cols);
     if (N & 1) N = optimal_dft_size(N + 1);
-    if ((size_t)M * 16 > 48 * 1024 || (size_t)N * 12 > 48 * 1024) return rf_fail(h, RF_E_CAPACITY, "rf_phase_correlate: image too large");
+    if ((size_t)M * 24 > 48 * 1024 || (size_t)N * 12 > 48 * 1024) return rf_fail(h, RF_E_CAPACITY, "rf_phase_correlate: image too large");
     const size_t b_img = al256((size_t)2 * rows * cols * 4), b_pad = al256((size_t)2 * M * N * 4);
     int rc = rf_ensure_scratch(h, b_img + b_pad + 512 + fmt_correlate_ws(2, 1, M, N));
     if (rc) return rc;
