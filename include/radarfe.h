@@ -200,6 +200,10 @@ RF_API int rf_polar_peaks(rf_handle* h, const float* polar, int A, int W, int64_
 RF_API int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W, const int32_t* pair_idx,
                     int n_pairs, int downsample, int clip_px, double* angle_rad, double* scale, double* response,
                     double* shift_xy);
+/* The same with one pointer per image ([A, W] f32 each): the reference passes two separately allocated arrays. */
+RF_API int rf_fmt_rotation_frames(rf_handle* h, const float* const* frames, int n_frames, int A, int W,
+                           const int32_t* pair_idx, int n_pairs, int downsample, int clip_px, double* angle_rad,
+                           double* scale, double* response, double* shift_xy);
 /* The log-polar image itself (stage-level parity): out [h_lp, w_lp] f32; out == NULL only queries the size. */
 RF_API int rf_fmt_log_polar(rf_handle* h, const float* polar, int A, int W, int downsample, int clip_px, float* out,
                      int64_t out_cap, int* h_lp, int* w_lp);

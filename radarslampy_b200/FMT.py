@@ -24,6 +24,5 @@ def getRotationUsingFMT(srcPolarImg: np.ndarray, targetPolarImg: np.ndarray, dow
     assert srcPolarImg.shape == targetPolarImg.shape, "Images need to have the same shape!"
     clip_px = int(maxRangeClipM / RANGE_RESOLUTION_CART_M) if maxRangeClipM > 0 else 0   # FMT.py:55-58
     fe = _engine.engine()
-    polar = np.stack([np.asarray(srcPolarImg, np.float32), np.asarray(targetPolarImg, np.float32)])
-    ang, sc, resp, _ = fe.fmt_rotation(polar, ((0, 1),), downsample=int(downsampleFactor), clip_px=clip_px)
+    ang, sc, resp, _ = fe.fmt_rotation([srcPolarImg, targetPolarImg], ((0, 1),), downsample=int(downsampleFactor), clip_px=clip_px)
     return float(ang[0]), float(sc[0]), float(resp[0])

@@ -50,7 +50,7 @@ SYMBOLS = [
     "rf_detect", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
-    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_log_polar",
+    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_rotation_frames", "rf_fmt_log_polar",
     "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses", "rf_png_info", "rf_ingest_png",
 ]
 STAGES = ("polar2cart", "scan_to_l0l1", "pyr_down", "klt", "compact", "reject", "kabsch", "mds", "finish")
@@ -539,13 +539,22 @@ class RadarFE:
     # -- N1 FMT rotation prior (FMT.py:13-90) ---------------------------------------
     def fmt_rotation(self, polar, pairs=((0, 1),), downsample=10, clip_px=0):
         """polar [F, A, W] f32, pairs [P, 2] -> (angle_rad [P], scale [P], response [P], shift_xy [P, 2])."""
+        pairs = _c(np.asarray(pairs, np.int32).reshape(-1, 2), np.int32)
+        P = pairs.shape[0]
+        ang, sc, resp, sh = np.zeros(P), np.zeros(P), np.zeros(P), np.zeros((P, 2))
+        if isinstance(polar, (list, tuple)):          # separately allocated images: one pointer each, no stacking
+            frames = [_c(f, np.float32) for f in polar]
+            if not frames or any(f.ndim != 2 or f.shape != frames[0].shape for f in frames):
+                raise ValueError("fmt_rotation: the images need the same 2-D shape")
+            A, W = frames[0].shape
+            ptrs = (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+            self._check(self.lib.rf_fmt_rotation_frames(self.h, ptrs, len(frames), A, W, _ptr(pairs), P, int(downsample),
+                                                        int(clip_px), _ptr(ang), _ptr(sc), _ptr(resp), _ptr(sh)))
+            return ang, sc, resp, sh
         polar = _c(polar, np.float32)
         if polar.ndim != 3:
             raise ValueError(f"expected [frames, azimuths, bins], got {polar.shape}")
         F, A, W = polar.shape
-        pairs = _c(np.asarray(pairs, np.int32).reshape(-1, 2), np.int32)
-        P = pairs.shape[0]
-        ang, sc, resp, sh = np.zeros(P), np.zeros(P), np.zeros(P), np.zeros((P, 2))
         self._check(self.lib.rf_fmt_rotation(self.h, _ptr(polar), F, A, W, _ptr(pairs), P, int(downsample), int(clip_px),
                                              _ptr(ang), _ptr(sc), _ptr(resp), _ptr(sh)))
         return ang, sc, resp, sh

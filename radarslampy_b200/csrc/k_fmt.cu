@@ -459,10 +459,14 @@ void rf_fmt_finish(const double* out3, int P, int sz, double log_base, double* a
 extern "C" {
 
 // polar [n_frames][A][W] f32 (host) -> per pair: angle (rad), scale, response, shift (dx, dy)
-int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W, const int32_t* pair_idx, int n_pairs,
-                    int downsample, int clip_px, double* angle_rad, double* scale, double* response, double* shift_xy) {
-    if (!h || !polar || !pair_idx || n_frames < 1 || n_pairs < 1 || !angle_rad)
+static int fmt_rotation_impl(rf_handle* h, const float* polar, const float* const* frames, int n_frames, int A, int W,
+                             const int32_t* pair_idx, int n_pairs, int downsample, int clip_px, double* angle_rad, double* scale,
+                             double* response, double* shift_xy) {
+    if (!h || (!polar && !frames) || !pair_idx || n_frames < 1 || n_pairs < 1 || !angle_rad)
         return rf_fail(h, RF_E_BADARG, "rf_fmt_rotation: bad argument");
+    if (frames)
+        for (int i = 0; i < n_frames; ++i)
+            if (!frames[i]) return rf_fail(h, RF_E_BADARG, "rf_fmt_rotation: null frame pointer");
     for (int i = 0; i < 2 * n_pairs; ++i)
         if (pair_idx[i] < 0 || pair_idx[i] >= n_frames) return rf_fail(h, RF_E_BADARG, "rf_fmt_rotation: pair index out of range");
     FmtDims d;
@@ -480,7 +484,10 @@ int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W
     float* d_pad = (float*)ws;        ws += b_pad;
     int32_t* d_pairs = (int32_t*)ws;  ws += b_pairs;
     double* d_out = (double*)ws;      ws += b_out;
-    RF_CUDA(h, cudaMemcpyAsync(d_polar, polar, (size_t)F * A * W * 4, cudaMemcpyHostToDevice, h->stream));
+    if (polar) RF_CUDA(h, cudaMemcpyAsync(d_polar, polar, (size_t)F * A * W * 4, cudaMemcpyHostToDevice, h->stream));
+    else
+        for (int i = 0; i < F; ++i)   // separately allocated images (the reference's call passes two arrays): no host-side stacking
+            RF_CUDA(h, cudaMemcpyAsync(d_polar + (size_t)i * A * W, frames[i], (size_t)A * W * 4, cudaMemcpyHostToDevice, h->stream));
     RF_CUDA(h, cudaMemcpyAsync(d_pairs, pair_idx, (size_t)P * 8, cudaMemcpyHostToDevice, h->stream));
     k_fmt_resize<float><<<dim3((d.Wd + 127) / 128, A, F), 128, 0, h->stream>>>(d_polar, A, (size_t)W, d.clip, d.Wd, d_rs);
     RF_CHECK_LAUNCH(h);
@@ -496,6 +503,20 @@ int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W
     const int sz = d.h_lp > d.w_lp ? d.h_lp : d.w_lp;                    // FMT.py:79-80
     rf_fmt_finish(out.data(), P, sz, exp(log((double)d.h_lp / 2.0) / sz), angle_rad, scale, response, shift_xy);
     return RF_OK;
+}
+
+int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W, const int32_t* pair_idx, int n_pairs,
+                    int downsample, int clip_px, double* angle_rad, double* scale, double* response, double* shift_xy) {
+    return fmt_rotation_impl(h, polar, nullptr, n_frames, A, W, pair_idx, n_pairs, downsample, clip_px, angle_rad, scale, response,
+                             shift_xy);
+}
+
+// the same with one pointer per image ([A, W] f32 each) instead of one stacked array
+int rf_fmt_rotation_frames(rf_handle* h, const float* const* frames, int n_frames, int A, int W, const int32_t* pair_idx,
+                           int n_pairs, int downsample, int clip_px, double* angle_rad, double* scale, double* response,
+                           double* shift_xy) {
+    return fmt_rotation_impl(h, nullptr, frames, n_frames, A, W, pair_idx, n_pairs, downsample, clip_px, angle_rad, scale, response,
+                             shift_xy);
 }
 
 // parseData.convertPolarImgToLogPolar(cv2.resize(polar[:, :clip_px], (clip_px // downsample, A)))
