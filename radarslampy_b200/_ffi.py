@@ -163,6 +163,51 @@ def pinned_empty(shape, dtype):
     return arr
 
 
+class _PinnedImagePool:
+    """Recycled page-locked host buffers for the images the drop-in API hands back as NumPy arrays (16 MB per
+    Cartesian image): a fresh np.empty pays page faults and a pageable D2H every frame.  A buffer returns to the pool
+    when the last array referring to it is garbage-collected (arrays keep their base alive, so a live view can never
+    see recycled memory).  At most MAX_OUT buffers are handed out at a time; callers that hoard images beyond that get
+    ordinary pageable arrays, so pinned memory stays bounded."""
+    MAX_OUT = 6
+
+    def __init__(self):
+        self.free = {}          # nbytes -> [pointer values]
+        self.out = 0
+        self.lock = threading.Lock()
+
+    def empty(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = max(count * dtype.itemsize, 1)
+        with self.lock:
+            if self.out >= self.MAX_OUT:
+                return np.empty(shape, dtype)
+            lst = self.free.get(nbytes)
+            ptr = lst.pop() if lst else None
+            self.out += 1
+        if ptr is None:
+            lib = load_library()
+            p = C.c_void_p()
+            if lib.rf_host_alloc(C.c_size_t(nbytes), C.byref(p)) != RF_OK:
+                with self.lock:
+                    self.out -= 1
+                return np.empty(shape, dtype)
+            ptr = p.value
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, nbytes, ptr)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _release(self, nbytes, ptr):
+        with self.lock:
+            self.out -= 1
+            self.free.setdefault(nbytes, []).append(ptr)
+
+
+_image_pool = _PinnedImagePool()
+
+
 class Batch:
     """Device-resident batch of independent frame pairs (rf_batch)."""
 
@@ -394,7 +439,7 @@ class RadarFE:
     # -- a2 / a3 ----------------------------------------------------------------
     def polar_to_cart(self, raw=None, polar=None, frame: Frame = None, want_host=True):
         frame = frame or self.new_frame()
-        out = np.empty((self.n, self.n), np.float32) if want_host else None
+        out = _image_pool.empty((self.n, self.n), np.float32) if want_host else None
         if raw is not None:
             raw = _c(raw, np.uint8)
             if raw.shape != (self.cfg.azimuths, self.cfg.raw_width):
