@@ -9,7 +9,7 @@ from . import Mapping
 from .getFeatures import N_FEATURES_BEFORE_RETRACK, appendNewFeatures
 from .Mapping import Keyframe, Map
 from .motionDistortion import MotionDistortionSolver
-from .parseData import RANGE_RESOLUTION_CART_M, convertPolarImageToCartesian, extractDataFromRadarImage
+from .parseData import RANGE_RESOLUTION_CART_M, convertRawScanToCartesian, extractDataFromRadarImage
 from .Tracker import Tracker
 from .trajectoryPlotting import Trajectory, convertPoseToTransform
 
@@ -33,7 +33,7 @@ def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_fl
     mds = MotionDistortionSolver(cov_p, cov_v)
     prev_pose = convertPoseToTransform(init_pose)
     prev_polar = extractDataFromRadarImage(scans[0])[0]              # RawROAMSystem.py:145-146
-    prev_cart = convertPolarImageToCartesian(prev_polar)
+    prev_cart = convertRawScanToCartesian(scans[0])                  # = convertPolarImageToCartesian(prev_polar), bit for bit, without re-uploading the f32 polar image
     blob, _ = appendNewFeatures(prev_cart, np.empty((0, 2)))         # RawROAMSystem.py:149-150
     center = Mapping.cartCenter(prev_polar)
     metric = (blob - center) * RANGE_RESOLUTION_CART_M               # RawROAMSystem.py:153
@@ -44,7 +44,7 @@ def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_fl
     out = {"R": [], "h": [], "mds_x": [], "n_tracked": [], "n_features_in": [], "fmt_angle": [], "retrack": []}
     for k in range(1, n):
         curr_polar = extractDataFromRadarImage(scans[k])[0]
-        curr_cart = convertPolarImageToCartesian(curr_polar)
+        curr_cart = convertRawScanToCartesian(scans[k])
         out["n_features_in"].append(len(blob))
         if use_fmt_prior:
             # NB the reference never advances prevImgPolar (RawROAMSystem.py:296-298): the prior is always taken
