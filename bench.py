@@ -472,6 +472,9 @@ def main():
                      # SURVEY.md §8(d) counts the reference's materialised f32 Cartesian image (4 n^2 per frame) plus the
                      # whole u8 pyramid as mandated outputs of the conversion; this kernel never writes the f32 image and
                      # produces levels 0-1 only, so `achieved` / `frac` above use the smaller, actual figure
+                     "note": "dominant = largest main-stream (step-time-determining) kernel; k_clique has longer launches "
+                             "(stages.reject) but is one warp per pair on ~2 % of the machine, latency-bound with ~3 KB of traffic "
+                             "per pair, and runs on per-batch tail streams underneath the image kernels of the following batches",
                      "survey_8d_bytes_per_launch": survey_bytes, "survey_8d_frac": (survey_bytes / (stages[dom]["ms"] * 1e-3) / 1e9 / peak)
                      if dom == "scan_to_l0l1" and stages[dom]["ms"] > 0 else None},
         "stages": stages,
