@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """FMT rotation prior throughput on the resident scans of a batch, next to the CPU path.
 
-    python tools/fmt_bench.py [--frames 256] [--reps 5]
+    python tests/perf/fmt_bench.py [--frames 256] [--reps 5]
 
 Prints one JSON line: pairs/s on the GPU (rf_batch_fmt over the batch's u8 scans, synchronous call incl. the
 D2H of the results), pairs/s of the reference's cv2 calls (oracle/ref_pipeline.rotation_fmt) on one core, and
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -4,7 +4,7 @@
 each frame, FMT prior, point cloud, keyframes, MDS) next to the same loop made of the reference's library calls on
 the CPU (oracle/ref_system.py; + FMT and point-cloud extraction per frame, as RawROAMSystem.run does).
 
-    python tools/sequential_bench.py [--frames 24]
+    python tests/perf/sequential_bench.py [--frames 24]
 
 One JSON line with frames/s of both and the largest per-frame pose difference.  This is BASELINE configs[0]/[1]
 as a latency-bound sequential run (pose chaining does not shard); the batch path in bench.py is the throughput mode."""
@@ -16,7 +16,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

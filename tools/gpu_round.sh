@@ -17,8 +17,8 @@ for k in ${NCU_KERNELS:-k_scan16_to_l0l1 k_klt k_clique}; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o $O/${TAG}_full_$k \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_$k.log 2>&1
 done
-python tools/fmt_bench.py > $O/${TAG}_fmt_bench.json 2>> $O/${TAG}_bench.err
+python tests/perf/fmt_bench.py > $O/${TAG}_fmt_bench.json 2>> $O/${TAG}_bench.err
 python tools/klt_stress.py > $O/${TAG}_klt_stress.json 2>> $O/${TAG}_bench.err
 python tools/ingest_bench.py > $O/${TAG}_ingest.json 2>> $O/${TAG}_bench.err
-python tools/sequential_bench.py > $O/${TAG}_sequential.json 2>> $O/${TAG}_bench.err
+python tests/perf/sequential_bench.py > $O/${TAG}_sequential.json 2>> $O/${TAG}_bench.err
 cat $O/${TAG}_bench.json
