@@ -85,7 +85,7 @@ std::string decode_one(const char* path, int rows, int cols, uint8_t* out) {
         if (pos + 12 + (size_t)len > b.size()) { inflateEnd(&zs); return std::string(path) + ": truncated chunk"; }
         const uint32_t crc = be32(&b[pos + 8 + len]);
         if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), type, len + 4) != crc) { inflateEnd(&zs); return std::string(path) + ": chunk CRC mismatch"; }
-        if (memcmp(type, "IDAT", 4) == 0) {
+        if (memcmp(type, "IDAT", 4) == 0 && !done) {   // (IDAT chunks after the end of the deflate stream carry nothing)
             seen_idat = true;
             zs.next_in = const_cast<uint8_t*>(&b[pos + 8]);
             zs.avail_in = len;
