@@ -234,6 +234,11 @@ RF_API int rf_png_info(const char* path, int* rows, int* cols);
 RF_API int rf_ingest_png(const char* const* paths, int n, int rows, int cols, int threads, uint8_t* out);
 
 /* ---- a11 fused pair / batch: Tracker.track + getTransform (+ MDS)  Tracker.py:35-127 */
+/* One pair from two separately held raw scans [A, raw_width] u8: the fused path above on a two-frame batch the
+ * handle owns.  feats_xy [K, 2] f32 (K <= max_features); prev_pose (x, y, theta) or NULL; next_xy [K, 2] and
+ * corr_status [K] (Tracker.track's corrStatus) may be NULL.  Synchronous on return. */
+RF_API int rf_track_pair(rf_handle* h, const uint8_t* raw_prev, const uint8_t* raw_next, const float* feats_xy, int K,
+                  const double* prev_pose, int with_mds, rf_pair_result* result, float* next_xy, uint8_t* corr_status);
 RF_API int rf_batch_create(rf_handle* h, rf_batch** out);
 RF_API void rf_batch_destroy(rf_handle* h, rf_batch* b);
 /* Host -> device staging.  raw: [n_frames, A, raw_width] u8; pair_idx: [n_pairs,2]

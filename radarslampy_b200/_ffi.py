@@ -48,7 +48,7 @@ SYMBOLS = [
     "rf_frame_destroy", "rf_polar_to_cart", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
     "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
     "rf_detect", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
-    "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_batch_upload_async",
+    "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_track_pair", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
     "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_rotation_frames", "rf_fmt_log_polar",
     "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses", "rf_png_info", "rf_ingest_png",
@@ -580,6 +580,22 @@ class RadarFE:
         self._check(self.lib.rf_polar_peaks(self.h, _ptr(polar), A, W, _ptr(out), C.c_int64(cap), C.byref(n)))
         return out[:n.value].copy()
 
+
+    # -- a11 one pair (rf_track_pair) ----------------------------------------------
+    def track_pair(self, raw_prev, raw_next, feats_xy, prev_pose=None, with_mds=False):
+        """Two raw scans + features on the first -> (rf_pair_result record, next_xy [K, 2], corrStatus u8 [K])."""
+        a, b = _c(raw_prev, np.uint8), _c(raw_next, np.uint8)
+        want = (self.cfg.azimuths, self.cfg.raw_width)
+        if a.shape != want or b.shape != want:
+            raise ValueError(f"raw scans must be {want}")
+        f = _c(np.asarray(feats_xy, np.float32).reshape(-1, 2), np.float32)
+        K = f.shape[0]
+        pose = None if prev_pose is None else _c(np.asarray(prev_pose, np.float64).reshape(3), np.float64)
+        res = np.zeros(1, PAIR_RESULT_DTYPE)
+        nxt, st = np.zeros((K, 2), np.float32), np.zeros(K, np.uint8)
+        self._check(self.lib.rf_track_pair(self.h, _ptr(a), _ptr(b), _ptr(f), K, _ptr(pose), int(with_mds), _ptr(res),
+                                           _ptr(nxt), _ptr(st)))
+        return res[0], nxt, st
 
     # -- N1 FMT rotation prior (FMT.py:13-90) ---------------------------------------
     def fmt_rotation(self, polar, pairs=((0, 1),), downsample=10, clip_px=0):

@@ -97,6 +97,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
     h->map = nullptr; h->map2 = nullptr; h->d_raw = nullptr; h->d_polar = nullptr; h->d_polar_u8 = nullptr;
     h->d_scratch = nullptr; h->scratch_bytes = 0; h->scratch_gen = 0; h->h_pinned = nullptr; h->pinned_bytes = 0;
     h->launches = 0;
+    h->pair_batch = nullptr;
     h->ev0 = h->ev1 = nullptr; h->stream_copy = nullptr; h->ev_copy = nullptr; h->stream = nullptr; h->owns_stream = false;
     int rc = RF_OK;
     auto bail = [&](int code) { rf_destroy(h); return code; };
@@ -127,6 +128,7 @@ void rf_destroy(rf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     rf_sync_all(h);
+    if (h->pair_batch) { rf_batch_destroy(h, h->pair_batch); h->pair_batch = nullptr; }
     if (h->map) cudaFree(h->map);
     if (h->map2) cudaFree(h->map2);
     if (h->d_raw) cudaFree(h->d_raw);

@@ -35,6 +35,7 @@ struct rf_handle {
     cudaStream_t stream_copy;  // H2D staging of the batch path (overlaps the kernels of the previous batch)
     cudaEvent_t ev_copy;       // join point of stream_copy for the timers / rf_sync
     std::vector<rf_batch*> batches;   // live batches (each owns a tail stream for rejection + solves)
+    rf_batch* pair_batch;             // two-frame / one-pair batch behind rf_track_pair (created on first use)
     int n;          // cartesian size 2R
     int R;
     int sm_count;

@@ -180,13 +180,19 @@ static void batch_free(rf_batch* b) {
 
 extern "C" {
 
+static int batch_create_sized(rf_handle* h, int max_frames, int max_pairs, rf_batch** out);
+
 int rf_batch_create(rf_handle* h, rf_batch** out) {
     if (!h || !out) return rf_fail(h, RF_E_BADARG, "rf_batch_create: null argument");
+    return batch_create_sized(h, h->cfg.max_frames, h->cfg.max_pairs, out);
+}
+
+static int batch_create_sized(rf_handle* h, int max_frames, int max_pairs, rf_batch** out) {
     *out = nullptr;
     const rf_config& c = h->cfg;
     rf_batch* b = new rf_batch();
     memset(b, 0, sizeof(*b));
-    b->max_frames = c.max_frames; b->max_pairs = c.max_pairs; b->Kmax = c.max_features;
+    b->max_frames = max_frames; b->max_pairs = max_pairs; b->Kmax = c.max_features;
     b->raw_cols = c.range_bins;                 // power bins only: the 11 metadata bytes are decoded on the host
     b->raw_pitch = (b->raw_cols + 15) & ~15;
     const size_t P = b->max_pairs, K = b->Kmax;
@@ -464,6 +470,39 @@ int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, 
     if (rc) return rc;
     if ((rc = rf_batch_run_async(h, b, with_mds))) return rc;
     return rf_batch_download(h, b, results, next_xy, status);
+}
+
+// Tracker.track + getTransform (+ MDS) for ONE pair given as two separate raw scans (SURVEY.md 8b rf_track_pair): a
+// two-frame, one-pair batch owned by the handle, created on first use.  feats_xy [K, 2] f32, K <= max_features;
+// next_xy [K, 2] / corr_status [K] may be NULL.  Synchronous on return.
+int rf_track_pair(rf_handle* h, const uint8_t* raw_prev, const uint8_t* raw_next, const float* feats_xy, int K,
+                  const double* prev_pose, int with_mds, rf_pair_result* result, float* next_xy, uint8_t* corr_status) {
+    if (!h || !raw_prev || !raw_next || !result || K < 0 || (K > 0 && !feats_xy))
+        return rf_fail(h, RF_E_BADARG, "rf_track_pair: bad argument");
+    const rf_config& c = h->cfg;
+    if (K > c.max_features) return rf_fail(h, RF_E_CAPACITY, "rf_track_pair: %d features exceed max_features = %d", K, c.max_features);
+    int rc;
+    if (!h->pair_batch && (rc = batch_create_sized(h, 2, 1, &h->pair_batch))) return rc;
+    rf_batch* b = h->pair_batch;
+    const size_t scan = (size_t)c.azimuths * c.raw_width, kmax = (size_t)c.max_features;
+    const size_t off_feats = (2 * scan + 255) & ~(size_t)255, off_next = off_feats + ((kmax * 8 + 255) & ~(size_t)255);
+    const size_t off_st = off_next + ((kmax * 8 + 255) & ~(size_t)255);
+    if ((rc = rf_ensure_pinned(h, off_st + kmax + 256))) return rc;
+    uint8_t* hp = (uint8_t*)h->h_pinned;
+    memcpy(hp, raw_prev, scan);
+    memcpy(hp + scan, raw_next, scan);
+    float* hf = (float*)(hp + off_feats);
+    memset(hf, 0, kmax * 8);
+    if (K) memcpy(hf, feats_xy, (size_t)K * 8);
+    const int32_t pair[2] = {0, 1}, count = K;
+    if ((rc = rf_batch_upload_async(h, b, hp, 2, pair, 1, hf, &count, prev_pose))) return rc;
+    if ((rc = rf_batch_run_async(h, b, with_mds))) return rc;
+    float* hn = (float*)(hp + off_next);
+    uint8_t* hs = hp + off_st;
+    if ((rc = rf_batch_download(h, b, result, next_xy ? hn : nullptr, corr_status ? hs : nullptr))) return rc;
+    if (next_xy && K) memcpy(next_xy, hn, (size_t)K * 8);
+    if (corr_status && K) memcpy(corr_status, hs, (size_t)K);
+    return RF_OK;
 }
 
 int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, int what, void* out, int* rows, int* cols) {

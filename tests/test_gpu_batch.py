@@ -239,3 +239,32 @@ def test_two_batches_pipelined_equal_serial():
             b.close()
     finally:
         fe.close()
+
+
+def test_track_pair_equals_batch_path(golden):
+    """rf_track_pair (two separately held scans, handle-owned two-frame batch) returns what rf_track_batch returns."""
+    fr, st = golden["tiny_frames"], golden["tiny_stages"]
+    fe = _engine(max_pairs=2, max_frames=3, max_features=256)
+    try:
+        pts = st["feat_in_0"]
+        K = pts.shape[0]
+        raw = np.stack([fr["raw_0"], fr["raw_1"]])
+        feats = np.zeros((1, 256, 2), np.float32)
+        feats[0, :K] = pts
+        b = fe.new_batch()
+        res_b, nxt_b, corr_b = b.track(raw, [[0, 1]], feats, [K], with_mds=True)
+        for _ in range(2):                                   # the handle-owned batch is reused call after call
+            res, nxt, corr = fe.track_pair(fr["raw_0"], fr["raw_1"], pts, with_mds=True)
+            for name in ("R", "h", "mds_x", "n_features", "n_good", "n_inliers", "status", "clique_nodes"):
+                assert np.array_equal(res[name], res_b[0][name]), name
+            assert np.array_equal(nxt, nxt_b[0, :K]) and np.array_equal(corr, corr_b[0, :K])
+        want = st["klt_status_0"].copy()
+        want[want.flatten().astype(bool)] &= st["rej_mask_0"][:, None].astype(np.uint8)
+        assert np.array_equal(corr, want.ravel())
+        res0, nxt0, corr0 = fe.track_pair(fr["raw_0"], fr["raw_1"], np.zeros((0, 2), np.float32))
+        assert int(res0["n_features"]) == 0 and nxt0.shape == (0, 2)
+        with pytest.raises((ValueError, RuntimeError)):
+            fe.track_pair(fr["raw_0"], fr["raw_1"], np.zeros((300, 2), np.float32))
+        b.close()
+    finally:
+        fe.close()
