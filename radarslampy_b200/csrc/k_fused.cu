@@ -123,22 +123,22 @@ k_build_map2(const uint32_t* __restrict__ map, size_t count, int A, int W, int W
 // ------------------------------------------------------------------------------------
 // INTERIOR: the whole tile lies inside both images and the destination pitch is even — no per-row or per-lane
 // bounds checks; addresses advance by pointer increments either way.
-template <bool L0, bool INTERIOR>
+template <bool L0, bool INTERIOR, int TH1>
 __device__ __forceinline__ void warp_pyr_tile_impl(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
                                                    int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
     const int x = ox1 + 2 * lane;
     const bool even_pitch = INTERIOR || (dw & 1) == 0;
     const bool x_ok = INTERIOR || x < dw, x0_ok = INTERIOR || 2 * ox1 + 4 * lane < n;
-    const int rows0 = INTERIOR ? 2 * FT_TH1 : min(2 * FT_TH1, n - 2 * oy1);   // level-0 rows of this tile inside the image
-    const int rows1 = INTERIOR ? FT_TH1 : min(FT_TH1, dh - oy1);
+    const int rows0 = INTERIOR ? 2 * TH1 : min(2 * TH1, n - 2 * oy1);   // level-0 rows of this tile inside the image
+    const int rows1 = INTERIOR ? TH1 : min(TH1, dh - oy1);
     uint8_t* q0 = L0 ? l0 + (size_t)(2 * oy1) * n + 2 * ox1 + 4 * lane : nullptr;
     uint8_t* q1 = dst + (size_t)oy1 * dw + x;
     const uint32_t* tp = tile + lane;
     uint32_t h[5];
 #pragma unroll
-    for (int r = 0; r < FT_RH; ++r) {
+    for (int r = 0; r < 2 * TH1 + 3; ++r) {
         const uint32_t w0 = tp[r * FT_RWW], w1 = tp[r * FT_RWW + 1];
-        if (L0 && r >= 2 && r < 2 + 2 * FT_TH1) {
+        if (L0 && r >= 2 && r < 2 + 2 * TH1) {
             if (INTERIOR || (r - 2 < rows0 && x0_ok)) *reinterpret_cast<uint32_t*>(q0) = __funnelshift_r(w0, w1, 16);
             q0 += n;
         }
@@ -158,13 +158,13 @@ __device__ __forceinline__ void warp_pyr_tile_impl(const uint32_t* __restrict__ 
     }
 }
 
-template <bool L0>
+template <bool L0, int TH1>
 __device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
                                               int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
-    const bool interior = (dw & 1) == 0 && ox1 + FT_TW1 <= dw && oy1 + FT_TH1 <= dh &&
-                          (!L0 || (2 * ox1 + 2 * FT_TW1 <= n && 2 * oy1 + 2 * FT_TH1 <= n));
-    if (interior) warp_pyr_tile_impl<L0, true>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
-    else warp_pyr_tile_impl<L0, false>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
+    const bool interior = (dw & 1) == 0 && ox1 + FT_TW1 <= dw && oy1 + TH1 <= dh &&
+                          (!L0 || (2 * ox1 + 2 * FT_TW1 <= n && 2 * oy1 + 2 * TH1 <= n));
+    if (interior) warp_pyr_tile_impl<L0, true, TH1>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
+    else warp_pyr_tile_impl<L0, false, TH1>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
 }
 
 // ------------------------------------------------------------------------------------
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256, FT_SCAN_MIN_BLOCKS) k_scan16_to_l0l1(cons
     for (int fw = warp; fw < FT_FR; fw += 8) {
         const int frame = f0 + fw;
         if (frame >= a.n_frames) break;
-        warp_pyr_tile<true>(tiles + fw * FT_TILE_WORDS, a.l1 + (size_t)frame * a.l1_stride, a.w1, a.h1, ox1, oy1, lane,
+        warp_pyr_tile<true, FT_TH1>(tiles + fw * FT_TILE_WORDS, a.l1 + (size_t)frame * a.l1_stride, a.w1, a.h1, ox1, oy1, lane,
                             a.l0 + (size_t)frame * a.l0_stride, a.n);
     }
 }
@@ -381,19 +381,26 @@ __global__ void __launch_bounds__(256, FT_SCAN_MIN_BLOCKS) k_scan16_to_l0l1(cons
 // pyrDown for the higher levels: each warp loads its FT_RH x 132 source tile from global memory
 // (REFLECT_101), then the same shared-memory pass.  4 warps per CTA, one tile each.
 // ------------------------------------------------------------------------------------
+// tile height of the upper-level pyrDown kernel (destination rows per warp tile).  Measured (256 frames, levels 2 + 3):
+// 16 rows 0.417 ms, 8 rows 0.383 ms, 4 rows 0.406 ms (0.369 ms with 12 CTAs/SM and spills): 8 is the default
+#ifndef FT_PYR_TH1
+#define FT_PYR_TH1 8
+#endif
+#define FT_PYR_RH (2 * FT_PYR_TH1 + 3)
+#define FT_PYR_TILE_WORDS (FT_PYR_RH * FT_RWW)
 #ifndef FT_PYR_MIN_BLOCKS
 #define FT_PYR_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(128, FT_PYR_MIN_BLOCKS)
 k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh, uint8_t* __restrict__ dst,
              size_t dst_stride, int dw, int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
-    __shared__ uint32_t s_tile[4][FT_TILE_WORDS];
+    __shared__ uint32_t s_tile[4][FT_PYR_TILE_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 4 + warp;
     if (t >= n_tiles) return;
     const int frame = t / tiles_per_frame, tt = t - frame * tiles_per_frame;
     const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
-    const int ox1 = tx * FT_TW1, oy1 = ty * FT_TH1;
+    const int ox1 = tx * FT_TW1, oy1 = ty * FT_PYR_TH1;
     const uint8_t* __restrict__ s = src + (size_t)frame * src_stride;
     uint32_t* tw = s_tile[warp];
     const int x0 = 2 * ox1 - 2;
@@ -403,14 +410,14 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     // back to REFLECT_101 byte loads.  Aligned loads may run up to 7 bytes past the row end: into the next row,
     // or into the padding every level allocation carries (rf_frameset_alloc).
     const int xk = x0 + 4 * lane, xk32 = x0 + 128;
-    if (x0 >= 0 && x0 + FT_RW + 4 <= sw && 2 * oy1 - 2 >= 0 && 2 * oy1 - 2 + FT_RH <= sh) {
+    if (x0 >= 0 && x0 + FT_RW + 4 <= sw && 2 * oy1 - 2 >= 0 && 2 * oy1 - 2 + FT_PYR_RH <= sh) {
         // interior tile: no reflection, no edge words; the row pointer advances by the pitch.  Rows are only
         // byte-aligned (odd widths at the higher levels), so each region word is cut out of two aligned loads.
         const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3u);
         const uint32_t* __restrict__ s4 = reinterpret_cast<const uint32_t*>(s - mis) + lane;   // aligned frame base
         unsigned off = mis + (unsigned)(2 * oy1 - 2) * (unsigned)sw + (unsigned)x0;             // byte offset of the row's region
 #pragma unroll 5
-        for (int r = 0; r < FT_RH; ++r, off += sw) {
+        for (int r = 0; r < FT_PYR_RH; ++r, off += sw) {
             const uint32_t* ap = s4 + (off >> 2);
             const unsigned sh8 = 8u * (off & 3u);
             tw[r * FT_RWW + lane] = __funnelshift_r(__ldg(ap), __ldg(ap + 1), sh8);
@@ -419,7 +426,7 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     } else {
     const bool in_k = xk >= 0 && xk + 3 < sw, in_32 = xk32 + 3 < sw;
 #pragma unroll 5
-    for (int r = 0; r < FT_RH; ++r) {
+    for (int r = 0; r < FT_PYR_RH; ++r) {
         const uint8_t* row = s + (size_t)reflect101_safe(2 * oy1 - 2 + r, sh) * sw;
         const uint8_t* p = row + x0;
         const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
@@ -449,7 +456,7 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     }
     }
     __syncwarp();
-    warp_pyr_tile<false>(s_tile[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane, nullptr, 0);
+    warp_pyr_tile<false, FT_PYR_TH1>(s_tile[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------
@@ -505,7 +512,7 @@ int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet&
 // levels first_level .. n_levels-1 from their predecessors
 int rf_launch_pyr_levels(rf_handle* h, const FrameSet& fs, int first_level, int n_frames) {
     for (int l = first_level; l < fs.n_levels; ++l) {
-        const int tiles_x = (fs.w[l] + FT_TW1 - 1) / FT_TW1, tiles_y = (fs.h[l] + FT_TH1 - 1) / FT_TH1;
+        const int tiles_x = (fs.w[l] + FT_TW1 - 1) / FT_TW1, tiles_y = (fs.h[l] + FT_PYR_TH1 - 1) / FT_PYR_TH1;
         const int n_tiles = tiles_x * tiles_y * n_frames;
         k_pyr_down_w<<<(n_tiles + 3) / 4, 128, 0, h->stream>>>(fs.lvl[l - 1], fs.lvl_stride[l - 1], fs.w[l - 1], fs.h[l - 1],
                                                                fs.lvl[l], fs.lvl_stride[l], fs.w[l], fs.h[l], tiles_x,
