@@ -8,8 +8,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 python -m pytest tests -m gpu -x -q > $O/${TAG}_gpu_tests.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_gpu_tests.log
 tail -3 $O/${TAG}_gpu_tests.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -2 $O/${TAG}_smoke.log
-python bench.py --steps 20 --warmup 3 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.err
-python bench.py --steps 10 --warmup 3 --mds 1 --no-cpu-baseline > $O/${TAG}_bench_mds.json 2>> $O/${TAG}_bench.err
+python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.err
+python bench.py --steps 100 --warmup 5 --mds 1 --no-cpu-baseline > $O/${TAG}_bench_mds.json 2>> $O/${TAG}_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_launch.log 2>&1
