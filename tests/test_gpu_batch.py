@@ -268,3 +268,38 @@ def test_track_pair_equals_batch_path(golden):
         b.close()
     finally:
         fe.close()
+
+
+@pytest.mark.parametrize("A,bins,n_frames", [(200, 501, 5), (360, 1205, 17)])
+def test_other_scan_geometries_bit_exact(A, bins, n_frames):
+    """Nothing is specialised to 400 x 2025: other azimuth counts / range clips (small, odd pyramid sizes, tiles that are
+    all border) give the oracle's images at every level through the batch path and the single-frame path."""
+    from oracle import restate as R
+    from radarslampy_b200 import _ffi
+    rng = np.random.default_rng(5)
+    cfg = _ffi.default_config()
+    cfg.azimuths, cfg.range_bins, cfg.raw_width = A, bins, 11 + bins + 37
+    cfg.max_frames, cfg.max_pairs, cfg.max_features, cfg.write_cart_f32 = n_frames, 2, 64, 0
+    raw = rng.integers(0, 256, (n_frames, A, cfg.raw_width), dtype=np.uint8)
+    fe = _ffi.RadarFE(cfg)
+    try:
+        n = 2 * (bins // 2)
+        assert fe.n == n
+        b = fe.new_batch()
+        b.upload(raw, np.zeros((0, 2), np.int32), np.zeros((0, 64, 2), np.float32), np.zeros(0, np.int32))
+        b.run_async()
+        fe.sync()
+        for f in (0, n_frames - 1):
+            polar = (raw[f][:, 11:11 + bins].astype(np.float32) / np.float32(255))
+            want = R.to_u8(R.warp_polar(polar))
+            frame, cart = fe.polar_to_cart(raw=raw[f])
+            assert np.array_equal(cart, R.warp_polar(polar))
+            for lvl in range(4):
+                got = b.frame(f, 1 + lvl)
+                assert got.shape == want.shape and np.array_equal(got, want), (f, lvl)
+                assert np.array_equal(frame.download(1 + lvl), want), (f, lvl, "single-frame path")
+                want = R.pyr_down(want)
+            frame.close()
+        b.close()
+    finally:
+        fe.close()
