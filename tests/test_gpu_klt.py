@@ -62,3 +62,35 @@ def test_klt_identity_and_shift(fe):
     assert g.mean() > 0.9
     assert np.abs(nxt[g] - pts[g]).max() <= 1e-3
     assert err.ravel()[g].max() == 0.0
+
+
+def test_klt_small_images_every_window_near_a_border():
+    """500 x 500 frames (pyramid 500 / 250 / 125 / 63): at the upper levels almost every 16 x 16 / 18 x 18 window touches
+    the image border, so the staging switches between the aligned-word fast path and the REFLECT_101 path all the time.
+    Status identical and positions within 2e-3 px of the C restatement (same integer arithmetic)."""
+    from oracle import restate as R
+    from radarslampy_b200 import _ffi
+    from scipy.ndimage import gaussian_filter, shift as nd_shift
+    rng = np.random.default_rng(21)
+    cfg = _ffi.default_config()
+    cfg.azimuths, cfg.range_bins, cfg.raw_width = 200, 501, 11 + 501
+    cfg.max_frames, cfg.max_pairs, cfg.max_features = 2, 1, 64
+    fe = _ffi.RadarFE(cfg)
+    try:
+        a = gaussian_filter(rng.random((500, 500)).astype(np.float32), 1.5)
+        a = ((a - a.min()) / (a.max() - a.min())).astype(np.float32)
+        b = np.clip(nd_shift(a, (0.8, -1.3), order=1, mode="nearest"), 0, 1).astype(np.float32)
+        fa, fb = fe.frame_from_cart(a), fe.frame_from_cart(b)
+        pts = np.vstack([rng.uniform(-2, 502, (400, 2)), rng.uniform(0, 20, (60, 2)), rng.uniform(480, 500, (60, 2)),
+                         [[0, 0], [499, 499], [7.5, 250.25], [492.4, 8.6], [250, 250]]]).astype(np.float32)
+        nxt, st, err = fe.klt(fa, fb, pts, apply_err_gate=False)
+        o_nxt, o_st, o_err = R.pyr_lk(fa.download(1), fb.download(1), pts)
+        assert np.array_equal(st.ravel(), o_st)
+        g = o_st.astype(bool)
+        assert g.sum() > 300
+        assert np.abs(nxt[g] - o_nxt[g]).max() <= 2e-3
+        assert np.abs(err.ravel()[g] - o_err[g]).max() <= 1e-3
+        if (~g).any():
+            assert np.abs(nxt[~g] - o_nxt[~g]).max() <= TOL_PX
+    finally:
+        fe.close()
