@@ -101,3 +101,20 @@ def test_bad_arguments(fe, polar):
         fe.fmt_rotation(np.stack(polar[:2]), [[0, 2]])
     with pytest.raises((ValueError, RuntimeError)):
         fe.phase_correlate(np.zeros((4, 4), np.float32), np.zeros((4, 5), np.float32))
+
+
+def test_fmt_other_geometry(fe):
+    """200 azimuths x 400 bins, down-sampling 5, no clipping: log-polar 251 x 80, DFT 256 x 80 (column split 16 x 16)."""
+    rng = np.random.default_rng(8)
+    base = rng.random((200, 400)).astype(np.float32)
+    k = np.array([0.25, 0.5, 0.25])
+    img = np.apply_along_axis(lambda r: np.convolve(r, k, "same"), 1, base).astype(np.float32)
+    rolled = np.roll(img, 7, axis=0)
+    lp = [F.polar_to_log_polar(F.resize_cols_linear(p, 80)) for p in (img, rolled)]
+    assert lp[0].shape == (251, 80)
+    assert np.array_equal(fe.fmt_log_polar(img, downsample=5, clip_px=0), lp[0])
+    (ox, oy), oresp = F.phase_correlate(lp[0], lp[1], F.hanning_window(251, 80))
+    ang, sc, resp, sh = fe.fmt_rotation([img, rolled], [[0, 1]], downsample=5, clip_px=0)
+    assert abs(sh[0, 0] - ox) <= TOL_SHIFT_PX and abs(sh[0, 1] - oy) <= TOL_SHIFT_PX and abs(resp[0] - oresp) <= 1e-4
+    want = (-oy * 2 * np.pi / 251 + np.pi) % (2 * np.pi) - np.pi
+    assert abs(ang[0] - want) <= TOL_ANGLE_RAD
