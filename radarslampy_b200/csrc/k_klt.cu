@@ -16,6 +16,8 @@
 //      and solves the 2x2 system in f32.
 // All integer sums are exact; cv2 accumulates the same products in f32, so positions agree
 // to ~5e-4 px (tolerance in north_star: 0.02 px) and status/err gating is identical.
+#include <limits.h>
+
 #include "common.cuh"
 
 #ifndef KLT_WARPS
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
         D = __fdiv_rn(1.f, D);
         float qx = __fsub_rn(nx, half), qy = __fsub_rn(ny, half);  // nextPt -= halfWin
         float pdx = 0.f, pdy = 0.f;
+        int jx = INT_MIN, jy = INT_MIN;          // origin of the next-image window currently staged in s.J (none yet at this level)
         // 4. iterations
         for (int it = 0; it < a.max_iters; ++it) {
             const int inx = cv_floor(qx), iny = cv_floor(qy);
@@ -217,8 +220,12 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                 break;
             }
             q14_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
-            __syncwarp();
-            load_J(s, J, w, h, inx, iny, lane);
+            // sub-pixel updates usually keep the integer window origin: the staged window is still the right one
+            if (inx != jx || iny != jy) {
+                __syncwarp();
+                load_J(s, J, w, h, inx, iny, lane);
+                jx = inx; jy = iny;
+            }
             int b1 = 0, b2 = 0;
 #pragma unroll
             for (int j = 0; j < KLT_PER_LANE; ++j) {
@@ -248,8 +255,10 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                 status = 0;
             } else {
                 q14_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
-                __syncwarp();
-                load_J(s, J, w, h, iex, iey, lane);
+                if (iex != jx || iey != jy) {
+                    __syncwarp();
+                    load_J(s, J, w, h, iex, iey, lane);
+                }
                 int e = 0;
 #pragma unroll
                 for (int j = 0; j < KLT_PER_LANE; ++j)
