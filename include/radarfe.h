@@ -68,7 +68,16 @@ typedef struct rf_config {
     double  mds_sigma_v[3];    /* (1, 1, (5 deg)^2)                                            */
     int64_t clique_node_limit; /* per-pair bound on search-tree descents (RF_E_WORKLIMIT)      */
     int32_t write_cart_f32;    /* batch path: also materialise the f32 Cartesian image         */
-    int32_t reserved;
+    int32_t retrack_threshold; /* 60    N_FEATURES_BEFORE_RETRACK getFeatures.py:57, RawROAMSystem.py:250 */
+    int32_t ssc_num_ret;       /* 200   adaptiveNMS ret_points        getFeatures.py:66             */
+    int32_t doh_num_sigma;     /* 3     DEFAULT_FEATURE_PARAMS        getFeatures.py:13-18          */
+    double  ssc_tolerance;     /* 0.1                                                               */
+    double  kf_rot_thr;        /* 0.2 rad  ROT_THRESHOLD              Mapping.py:13-15              */
+    double  kf_trans_thr;      /* 2.0 m    TRANS_THRESHOLD                                          */
+    double  detect_quality;    /* mode 0: candidates above this fraction of the strongest response (0.01) */
+    double  doh_min_sigma;     /* 0.01                                getFeatures.py:13-18          */
+    double  doh_max_sigma;     /* 10                                                                */
+    double  doh_threshold;     /* 0.0005                                                            */
 } rf_config;
 
 typedef struct rf_handle rf_handle; /* stream + workspaces + geometry tables            */
@@ -286,6 +295,71 @@ RF_API void rf_host_free(void* p);
 RF_API int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
                    int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose,
                    int with_mds, rf_pair_result* results, float* next_xy, uint8_t* status);
+
+/* ---- N2  chained odometry on the device: RawROAMSystem.run          RawROAMSystem.py:141-300
+ *          + Keyframe / Map bookkeeping                               Mapping.py:37-66,97-125,149-174
+ *          + appendNewFeatures / adaptiveNMS                          getFeatures.py:66-118
+ * n_seq independent sequences advance one frame per step in lock step.  Everything the reference's loop carries
+ * from frame k-1 to frame k stays on the device: the tracked features (blobCoord), the previous image pyramid,
+ * prev_pose, the keyframe the features belong to (pose + undistorted local points, pruned with corrStatus), the
+ * keyframe count.  A step is: scan -> Cartesian u8 pyramid, KLT from the previous frame, err gating, clique
+ * rejection, Kabsch, motion-distortion solve (world points from the keyframe), pose / keyframe update, and — for
+ * exactly the sequences whose feature count fell to <= 60 (RawROAMSystem.py:250-271) — re-detection on the device:
+ * detector response, 3x3 NMS, candidate sort, the whole SSC bisection, append + order-preserving de-duplication.
+ * No host synchronisation inside a step; with RF_SEQ_GRAPH the step is one CUDA graph launch.
+ *
+ * Scans live in an arena of `arena_frames` device-resident scans; a step reads scan (base + s * stride) for
+ * sequence s, so both "one long drive, sequence s starts at frame s" (stride 1) and "one slot of n_seq fresh scans
+ * per step" layouts work without copies. */
+typedef struct rf_seq rf_seq;
+typedef struct rf_seq_result {
+    double pose[3];        /* absolute pose (x, y, theta) after this frame      RawROAMSystem.py:212,237           */
+    double R[4];           /* relative transform T_wj0^-1 T(pose), row-major     RawROAMSystem.py:214               */
+    double h[2];           /* metres                                                                                */
+    double mds_x[6];       /* [vx, vy, vtheta, Tx, Ty, Ttheta]                   motionDistortion.py:295-325        */
+    double kab_R[4];       /* Tracker.getTransform(good_old, good_new)           Tracker.py:108-127 (h in metres)   */
+    double kab_h[2];
+    int32_t n_features_in; /* len(blobCoord) handed to Tracker.track                                                */
+    int32_t n_good;        /* after KLT status & (err < thr)                                                        */
+    int32_t n_tracked;     /* clique size = good_new.shape[0]                    RawROAMSystem.py:249               */
+    int32_t retrack;       /* n_tracked <= 60 -> appendNewFeatures               RawROAMSystem.py:250,264           */
+    int32_t keyframe_added;/* retrack or Map.isGoodKeyframe                      RawROAMSystem.py:251-271           */
+    int32_t n_keyframes;   /* len(map.keyframes) after this frame                                                   */
+    int32_t n_features_out;/* len(blobCoord) carried to the next frame                                              */
+    int32_t n_candidates;  /* detector candidates of this frame's re-detection (0 if none)                          */
+    int32_t mds_iters;
+    int32_t clique_nodes;
+    int32_t status;        /* RF_OK, RF_E_WORKLIMIT (clique), RF_E_CAPACITY (features / candidates truncated)       */
+    int32_t reserved;
+} rf_seq_result;
+
+#define RF_SEQ_MDS 1      /* pose from the motion-distortion solve (configs[2], what the reference always does);
+                             without it the pose is T_wj = prev_pose @ [R, h] (configs[1]) and velocity = 0        */
+#define RF_SEQ_GRAPH 2    /* replay the step as a CUDA graph (captured on first use per step shape)               */
+
+/* detector_mode: 0 = structure-tensor min eigenvalue, 1 = determinant of Hessian (rf_detect).  The runner owns a
+ * CUDA stream: several runners on one handle overlap (the latency-bound clique / solve tail of one under the image
+ * kernels of another). */
+RF_API int rf_seq_create(rf_handle* h, int n_seq, int arena_frames, int detector_mode, rf_seq** out);
+RF_API void rf_seq_destroy(rf_handle* h, rf_seq* s);
+/* raw [n_frames][A][raw_width] u8 (host; pinned for a truly asynchronous copy) -> arena frames [first, first + n_frames).
+ * Waits (on the device) for queued steps that still read those arena frames. */
+RF_API int rf_seq_upload_async(rf_handle* h, rf_seq* s, int first_frame, int n_frames, const uint8_t* raw);
+/* Frame 0 of every sequence: pyramid, feature detection, first keyframe.  init_pose [n_seq][3] or NULL (origin). */
+RF_API int rf_seq_reset_async(rf_handle* h, rf_seq* s, int base, int stride, const double* init_pose);
+/* One frame for every sequence.  Asynchronous; results land in a device ring (rf_seq_results). */
+RF_API int rf_seq_step_async(rf_handle* h, rf_seq* s, int base, int stride, int flags);
+/* Results of step `step` (1 = first step after the reset; 0 = the reset itself: feature counts only), which must be
+ * one of the last rf_seq_ring() steps.  Synchronises the runner's stream.  out [n_seq]. */
+RF_API int rf_seq_results(rf_handle* h, rf_seq* s, int step, rf_seq_result* out);
+RF_API int rf_seq_results_async(rf_handle* h, rf_seq* s, int step, rf_seq_result* out_pinned);
+RF_API int rf_seq_ring(const rf_seq* s);
+RF_API int rf_seq_steps_done(const rf_seq* s);
+/* Current blobCoord of every sequence: feats [n_seq][max_features][2] f32, counts [n_seq].  Synchronises. */
+RF_API int rf_seq_features(rf_handle* h, rf_seq* s, float* feats, int32_t* counts);
+RF_API int rf_seq_sync(rf_handle* h, rf_seq* s);
+/* Number of kernels one step launches (eager or inside the graph). */
+RF_API int rf_seq_launches_per_step(const rf_seq* s);
 
 #ifdef __cplusplus
 }

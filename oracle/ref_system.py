@@ -42,7 +42,9 @@ class _KF:
         return (T[:2, :2] @ self.pruned_und.T + T[:2, 2:]).T
 
 
-def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0)):
+def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0), with_mds=True):
+    """with_mds=False: the pose chain without motion compensation, T_wj = prev_pose @ [R, h] (RawROAMSystem.py:201,
+    BASELINE configs[1]); the keyframe points are then undistorted with zero velocity."""
     scans = list(raw_scans)
     init_pose = np.asarray(init_pose, np.float64)
     prev_pose = _pose_T(init_pose)
@@ -67,7 +69,10 @@ def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0)):
         p_w = old_kf.global_pts()
         centered_new = (good_new - center) * RES
         T_wj = prev_pose @ np.block([[R, h], [np.zeros((2,)), 1]])
-        sol = P.mds_solve(prev_pose, p_w, centered_new, T_wj)
+        if with_mds:
+            sol = P.mds_solve(prev_pose, p_w, centered_new, T_wj)
+        else:
+            sol = np.array([0.0, 0.0, 0.0, T_wj[0, 2], T_wj[1, 2], np.arctan2(T_wj[1, 0], T_wj[0, 0])])
         pose_vector = sol[3:]
         rel = np.linalg.inv(prev_pose) @ _pose_T(pose_vector)
         velocity = sol[:3]
@@ -91,4 +96,5 @@ def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0)):
         prev_pose = _pose_T(pose_vector)
     res = {k: np.array(v) for k, v in out.items()}
     res["n_keyframes"] = len(kfs)
+    res["features"] = blob
     return res

@@ -23,7 +23,10 @@ class RfConfig(C.Structure):
         ("klt_eps", C.c_float), ("klt_min_eig", C.c_float), ("klt_err_thr", C.c_float),
         ("dist_thr_px", C.c_double), ("cart_res_m", C.c_double), ("mds_period", C.c_double),
         ("mds_sigma_p", C.c_double * 2), ("mds_sigma_v", C.c_double * 3),
-        ("clique_node_limit", C.c_int64), ("write_cart_f32", C.c_int32), ("reserved", C.c_int32),
+        ("clique_node_limit", C.c_int64), ("write_cart_f32", C.c_int32), ("retrack_threshold", C.c_int32),
+        ("ssc_num_ret", C.c_int32), ("doh_num_sigma", C.c_int32), ("ssc_tolerance", C.c_double),
+        ("kf_rot_thr", C.c_double), ("kf_trans_thr", C.c_double), ("detect_quality", C.c_double),
+        ("doh_min_sigma", C.c_double), ("doh_max_sigma", C.c_double), ("doh_threshold", C.c_double),
     ]
 
 
@@ -41,6 +44,15 @@ PAIR_RESULT_DTYPE = np.dtype([
     ("status", np.int32), ("clique_nodes", np.int32)], align=True)
 assert PAIR_RESULT_DTYPE.itemsize == C.sizeof(RfPairResult)
 
+SEQ_RESULT_DTYPE = np.dtype([
+    ("pose", np.float64, (3,)), ("R", np.float64, (4,)), ("h", np.float64, (2,)), ("mds_x", np.float64, (6,)),
+    ("kab_R", np.float64, (4,)), ("kab_h", np.float64, (2,)),
+    ("n_features_in", np.int32), ("n_good", np.int32), ("n_tracked", np.int32), ("retrack", np.int32),
+    ("keyframe_added", np.int32), ("n_keyframes", np.int32), ("n_features_out", np.int32), ("n_candidates", np.int32),
+    ("mds_iters", np.int32), ("clique_nodes", np.int32), ("status", np.int32), ("reserved", np.int32)], align=True)
+assert SEQ_RESULT_DTYPE.itemsize == 21 * 8 + 12 * 4
+RF_SEQ_MDS, RF_SEQ_GRAPH = 1, 2
+
 # every symbol include/radarfe.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "rf_default_config", "rf_create", "rf_destroy", "rf_last_error", "rf_version", "rf_cart_size", "rf_stream",
@@ -52,6 +64,8 @@ SYMBOLS = [
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
     "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_rotation_frames", "rf_fmt_log_polar",
     "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses", "rf_png_info", "rf_ingest_png",
+    "rf_seq_create", "rf_seq_destroy", "rf_seq_upload_async", "rf_seq_reset_async", "rf_seq_step_async", "rf_seq_results",
+    "rf_seq_results_async", "rf_seq_ring", "rf_seq_steps_done", "rf_seq_features", "rf_seq_sync", "rf_seq_launches_per_step",
 ]
 STAGES = ("polar2cart", "scan_to_l0l1", "pyr_down", "klt", "compact", "reject", "kabsch", "mds", "finish")
 
@@ -85,6 +99,18 @@ def load_library():
             L.rf_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
             L.rf_host_free.restype = None
             L.rf_host_free.argtypes = [C.c_void_p]
+            L.rf_seq_destroy.restype = None
+            L.rf_seq_destroy.argtypes = [C.c_void_p, C.c_void_p]
+            L.rf_seq_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+            L.rf_seq_upload_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            L.rf_seq_reset_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            L.rf_seq_step_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+            L.rf_seq_results.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.rf_seq_results_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.rf_seq_features.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.rf_seq_sync.argtypes = [C.c_void_p, C.c_void_p]
+            for fn in (L.rf_seq_ring, L.rf_seq_steps_done, L.rf_seq_launches_per_step):
+                fn.argtypes = [C.c_void_p]
             _lib = L
     return _lib
 
@@ -323,6 +349,75 @@ class Batch:
         return res[:P], nxt[:P], st[:P]
 
 
+class Sequences:
+    """Lock-step runner of n_seq device-resident odometry chains (rf_seq, include/radarfe.h)."""
+
+    def __init__(self, fe, n_seq, arena_frames, detector_mode=0):
+        self.fe, self.n_seq, self.arena_frames = fe, int(n_seq), int(arena_frames)
+        p = C.c_void_p()
+        fe._check(fe.lib.rf_seq_create(fe.h, self.n_seq, self.arena_frames, int(detector_mode), C.byref(p)))
+        self.p = p
+        self._keep = []
+
+    def close(self):
+        if self.p and self.fe.h:
+            self.fe.lib.rf_seq_destroy(self.fe.h, self.p)
+        self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, first_frame, raw):
+        """raw u8 [n_frames, A, raw_width] -> arena frames [first_frame, first_frame + n_frames) (asynchronous: `raw` is
+        kept alive until the next sync())."""
+        cfg = self.fe.cfg
+        raw = np.ascontiguousarray(raw, np.uint8)
+        if raw.ndim != 3 or raw.shape[1:] != (cfg.azimuths, cfg.raw_width):
+            raise ValueError(f"raw scans must be [n_frames, {cfg.azimuths}, {cfg.raw_width}] uint8, got {raw.shape}")
+        self.fe._check(self.fe.lib.rf_seq_upload_async(self.fe.h, self.p, int(first_frame), raw.shape[0], _ptr(raw)))
+        self._keep.append(raw)
+
+    def reset(self, base=0, stride=1, init_pose=None):
+        ip = None if init_pose is None else _c(np.asarray(init_pose, np.float64).reshape(self.n_seq, 3), np.float64)
+        self.fe._check(self.fe.lib.rf_seq_reset_async(self.fe.h, self.p, int(base), int(stride), _ptr(ip)))
+
+    def step(self, base, stride=1, with_mds=True, graph=True):
+        flags = (RF_SEQ_MDS if with_mds else 0) | (RF_SEQ_GRAPH if graph else 0)
+        self.fe._check(self.fe.lib.rf_seq_step_async(self.fe.h, self.p, int(base), int(stride), flags))
+
+    @property
+    def steps_done(self):
+        return int(self.fe.lib.rf_seq_steps_done(self.p))
+
+    @property
+    def ring(self):
+        return int(self.fe.lib.rf_seq_ring(self.p))
+
+    @property
+    def launches_per_step(self):
+        return int(self.fe.lib.rf_seq_launches_per_step(self.p))
+
+    def results(self, step, out=None, sync=True):
+        out = np.zeros(self.n_seq, SEQ_RESULT_DTYPE) if out is None else out
+        fn = self.fe.lib.rf_seq_results if sync else self.fe.lib.rf_seq_results_async
+        self.fe._check(fn(self.fe.h, self.p, int(step), _ptr(out)))
+        return out
+
+    def features(self):
+        K = self.fe.cfg.max_features
+        feats = np.zeros((self.n_seq, K, 2), np.float32)
+        counts = np.zeros(self.n_seq, np.int32)
+        self.fe._check(self.fe.lib.rf_seq_features(self.fe.h, self.p, _ptr(feats), _ptr(counts)))
+        return feats, counts
+
+    def sync(self):
+        self.fe._check(self.fe.lib.rf_seq_sync(self.fe.h, self.p))
+        self._keep = []
+
+
 class Frame:
     """Device-resident scan (f32 Cartesian image + u8 LK pyramid)."""
 
@@ -422,6 +517,9 @@ class RadarFE:
 
     def new_batch(self) -> Batch:
         return Batch(self)
+
+    def new_sequences(self, n_seq, arena_frames, detector_mode=0) -> Sequences:
+        return Sequences(self, n_seq, arena_frames, detector_mode)
 
     # -- a1 ---------------------------------------------------------------------
     def extract_polar(self, raw):

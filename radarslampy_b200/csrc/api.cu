@@ -63,6 +63,11 @@ void rf_default_config(rf_config* c) {
     c->mds_sigma_v[2] = (5 * M_PI / 180) * (5 * M_PI / 180);
     c->clique_node_limit = 4000000;
     c->write_cart_f32 = 1;
+    c->retrack_threshold = 60;                  // getFeatures.py:57
+    c->ssc_num_ret = 200; c->ssc_tolerance = 0.1;   // getFeatures.py:66
+    c->kf_rot_thr = 0.2; c->kf_trans_thr = 2.0;     // Mapping.py:13-15
+    c->detect_quality = 0.01;
+    c->doh_min_sigma = 0.01; c->doh_max_sigma = 10; c->doh_num_sigma = 3; c->doh_threshold = 0.0005;   // getFeatures.py:13-18
 }
 
 int rf_version(void) { return RADARFE_VERSION; }

@@ -27,6 +27,7 @@ struct rf_frame {
 };
 
 struct rf_batch;
+struct rf_seq;
 struct rf_handle {
     rf_config cfg;
     int device;
@@ -36,6 +37,7 @@ struct rf_handle {
     cudaEvent_t ev_copy;       // join point of stream_copy for the timers / rf_sync
     std::vector<rf_batch*> batches;   // live batches (each owns a tail stream for rejection + solves)
     rf_batch* pair_batch;             // two-frame / one-pair batch behind rf_track_pair (created on first use)
+    std::vector<rf_seq*> seqs;        // live lock-step sequence runners (each owns a stream)
     int n;          // cartesian size 2R
     int R;
     int sm_count;
@@ -107,12 +109,17 @@ int rf_launch_extract(rf_handle* h, const uint8_t* d_raw, float* d_polar);
 int rf_fused_wp(const rf_handle* h);
 size_t rf_interleave_words(const rf_handle* h, int max_frames);
 int rf_launch_build_map2(rf_handle* h);
-int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out);
+// frame_sel: optional device pointer to {base, stride}: frame f of the group is read from source frame base + f * stride
+int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out,
+                         const int32_t* d_frame_sel = nullptr);
 int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames);
 int rf_launch_pyr_levels(rf_handle* h, const FrameSet& fs, int first_level, int n_frames);
 // k_klt.cu
 int rf_launch_klt(rf_handle* h, const FrameSet& prev, const FrameSet& next, const int32_t* d_pair_idx, const float* d_pts,
                   const int32_t* d_counts, int Kmax, int P, float* d_next, uint8_t* d_status, float* d_err, int gate);
+// k_batch.cu
+int rf_launch_compact_good(rf_handle* h, const float* d_feats, const float* d_next, const uint8_t* d_status, const int32_t* d_counts,
+                           int Kmax, int P, float* d_good_old, float* d_good_new, int32_t* d_good_src, int32_t* d_ngood);
 // k_clique.cu
 size_t rf_clique_ws_total(int Kmax, int P);
 int rf_launch_reject(rf_handle* h, void* ws_base, const float* d_prev, const float* d_new, const int32_t* d_counts,
@@ -124,6 +131,10 @@ int rf_launch_kabsch(rf_handle* h, const float* d_src, const float* d_tgt, const
 int rf_launch_mds_fused(rf_handle* h, const float* d_old, const float* d_new, const uint8_t* d_mask, int mask_stride,
                         const int32_t* d_counts, int Kstride, int P, const double* d_R, const double* d_h,
                         const double* d_prev_pose, double* d_scratch, double* d_x, int32_t* d_iters);
+int rf_launch_mds_chain(rf_handle* h, const float* d_old, const float* d_new, const uint8_t* d_mask, int mask_stride,
+                        const int32_t* d_counts, int Kstride, int P, const double* d_R, const double* d_h,
+                        const double* d_prev_pose, const double* d_kf_und, const double* d_kf_pose, const int32_t* d_good_src,
+                        double* d_scratch, double* d_x, int32_t* d_iters);
 // k_fmt.cu — Fourier-Mellin rotation prior over device-resident scans (used by rf_batch_fmt)
 int rf_fmt_resident_u8(rf_handle* h, const uint8_t* d_raw, int F, int A, int W, size_t pitch, const int32_t* d_pairs, int P,
                        int downsample, int clip_px, double** d_out_p, int* sz_out, double* log_base_out);

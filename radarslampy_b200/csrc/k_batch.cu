@@ -73,6 +73,12 @@ struct StreamScope {
     ~StreamScope() { h->stream = saved; }
 };
 
+int rf_seq_join_all(rf_handle* h);   // k_seq.cu
+int rf_seq_sync_all(rf_handle* h);
+
+int rf_launch_compact_good(rf_handle* h, const float* d_feats, const float* d_next, const uint8_t* d_status, const int32_t* d_counts,
+                           int Kmax, int P, float* d_good_old, float* d_good_new, int32_t* d_good_src, int32_t* d_ngood);
+
 int rf_join_streams(rf_handle* h) {
     if (h->stream_copy) {
         RF_CUDA(h, cudaEventRecord(h->ev_copy, h->stream_copy));
@@ -82,14 +88,14 @@ int rf_join_streams(rf_handle* h) {
         RF_CUDA(h, cudaEventRecord(b->ev_tail_done, b->tail));
         RF_CUDA(h, cudaStreamWaitEvent(h->stream, b->ev_tail_done, 0));
     }
-    return RF_OK;
+    return rf_seq_join_all(h);
 }
 
 int rf_sync_all(rf_handle* h) {
     if (h->stream_copy) RF_CUDA(h, cudaStreamSynchronize(h->stream_copy));
     if (h->stream) RF_CUDA(h, cudaStreamSynchronize(h->stream));
     for (rf_batch* b : h->batches) RF_CUDA(h, cudaStreamSynchronize(b->tail));
-    return RF_OK;
+    return rf_seq_sync_all(h);
 }
 
 // ------------------------------------------------------------------------------------
@@ -119,6 +125,13 @@ k_compact_good(const float* __restrict__ feats, const float* __restrict__ next, 
         n += __popc(bm);
     }
     if (lane == 0) n_good[p] = n;
+}
+
+int rf_launch_compact_good(rf_handle* h, const float* d_feats, const float* d_next, const uint8_t* d_status, const int32_t* d_counts,
+                           int Kmax, int P, float* d_good_old, float* d_good_new, int32_t* d_good_src, int32_t* d_ngood) {
+    k_compact_good<<<(P + 3) / 4, 128, 0, h->stream>>>(d_feats, d_next, d_status, d_counts, Kmax, P, d_good_old, d_good_new, d_good_src, d_ngood);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
 }
 
 // Assemble rf_pair_result and the caller-facing corrStatus (Tracker.py:98-104).

@@ -60,10 +60,11 @@ __device__ __forceinline__ int reflect101_safe(int p, int len) {
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_interleave16(const uint8_t* __restrict__ raw, size_t frame_stride, int pitch, int A, int W, int n_frames,
-               uint4* __restrict__ out, int Wp) {
+               uint4* __restrict__ out, int Wp, const int32_t* __restrict__ frame_sel) {
     const int x4 = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 samples
     const int a = blockIdx.y, g = blockIdx.z;
     if (x4 * 4 >= Wp) return;
+    const int sel_base = frame_sel ? frame_sel[0] : 0, sel_stride = frame_sel ? frame_sel[1] : 1;
     uint32_t o[4][4];   // o[k][c] = sample 4*x4 + k, frames 4c .. 4c+3
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -73,7 +74,7 @@ k_interleave16(const uint8_t* __restrict__ raw, size_t frame_stride, int pitch, 
             const int fr = FT_FR * g + 4 * c + f;
             // raw rows are 16-byte aligned and hold only the power bins; columns >= W are padding
             w[f] = (fr < n_frames && x4 * 4 < pitch)
-                       ? __ldg(reinterpret_cast<const uint32_t*>(raw + (size_t)fr * frame_stride + (size_t)a * pitch) + x4) : 0u;
+                       ? __ldg(reinterpret_cast<const uint32_t*>(raw + (size_t)(sel_base + fr * sel_stride) * frame_stride + (size_t)a * pitch) + x4) : 0u;
         }
         // 4x4 byte transpose: t[k] = (w0.bk, w1.bk, w2.bk, w3.bk)
         const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140), t1 = __byte_perm(w[0], w[1], 0x7362);
@@ -475,12 +476,13 @@ int rf_launch_build_map2(rf_handle* h) {
 }
 
 // d_raw: frames of [A][pitch] power bins (no metadata), pitch a multiple of 16 and >= Wp
-int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out) {
+int rf_launch_interleave(rf_handle* h, const uint8_t* d_raw, size_t frame_stride, int pitch, int n_frames, uint32_t* d_out,
+                         const int32_t* d_frame_sel) {
     const int Wp = rf_fused_wp(h);
     const int groups = (n_frames + FT_FR - 1) / FT_FR;   // zero-filled up to a multiple of 16 frames
     dim3 grd((Wp / 4 + 255) / 256, h->cfg.azimuths, groups);
     k_interleave16<<<grd, 256, 0, h->stream>>>(d_raw, frame_stride, pitch, h->cfg.azimuths, h->cfg.range_bins, n_frames,
-                                               reinterpret_cast<uint4*>(d_out), Wp);
+                                               reinterpret_cast<uint4*>(d_out), Wp, d_frame_sel);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }

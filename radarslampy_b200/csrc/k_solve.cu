@@ -96,6 +96,11 @@ struct MdsArgs {
     // fused mode: correspondences in pixels + inlier mask + Kabsch result + previous pose
     const float* px_old; const float* px_new; const uint8_t* mask; int mask_stride; int Kstride;
     const double* kab_R; const double* kab_h; const double* prev_pose;  // [P][3] or nullptr (identity)
+    // chained mode (k_seq.cu, RawROAMSystem.py:185-209): world points come from the keyframe the features belong to
+    // (Keyframe.getPrunedFeaturesGlobalPosition, Mapping.py:101-120) instead of the previous frame
+    const double* kf_und;      // [P][Kstride][2] undistorted keyframe-local feature points (metres), row = original feature row
+    const double* kf_pose;     // [P][3]
+    const int32_t* good_src;   // [P][Kstride] original feature row of every compacted correspondence
     double center, res;
     double period, sig_p0, sig_p1, sig_v0, sig_v1, sig_v2;
     int max_iters;
@@ -242,6 +247,12 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
         const float* po = a.px_old + (size_t)p * a.Kstride * 2;
         const float* pn = a.px_new + (size_t)p * a.Kstride * 2;
         const uint8_t* m = a.mask + (size_t)p * a.mask_stride;
+        double kx = 0, ky = 0, kc = 1, ks = 0;
+        const double* und = nullptr; const int32_t* gsrc = nullptr;
+        if (a.kf_und) {
+            und = a.kf_und + (size_t)p * a.Kstride * 2; gsrc = a.good_src + (size_t)p * a.Kstride;
+            kx = a.kf_pose[3 * p]; ky = a.kf_pose[3 * p + 1]; kc = cos(a.kf_pose[3 * p + 2]); ks = sin(a.kf_pose[3 * p + 2]);
+        }
         // order-preserving compaction of the inliers
         for (int i0 = 0; i0 < K; i0 += 32) {
             const int i = i0 + lane;
@@ -251,7 +262,12 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
                 const int j = N + __popc(bm & ((1u << lane) - 1));
                 const double ox = ((double)po[2 * i] - a.center) * a.res, oy = ((double)po[2 * i + 1] - a.center) * a.res;
                 const double x = ((double)pn[2 * i] - a.center) * a.res, y = ((double)pn[2 * i + 1] - a.center) * a.res;
-                pts[5 * j] = c0 * ox - s0 * oy + x0; pts[5 * j + 1] = s0 * ox + c0 * oy + y0;
+                if (und) {   // p_w = R(theta_kf) u + t_kf
+                    const double ux = und[2 * gsrc[i]], uy = und[2 * gsrc[i] + 1];
+                    pts[5 * j] = kc * ux - ks * uy + kx; pts[5 * j + 1] = ks * ux + kc * uy + ky;
+                } else {
+                    pts[5 * j] = c0 * ox - s0 * oy + x0; pts[5 * j + 1] = s0 * ox + c0 * oy + y0;
+                }
                 pts[5 * j + 2] = x; pts[5 * j + 3] = y;
                 pts[5 * j + 4] = a.period * atan2(-y, -x) / (2.0 * M_PI);
             }
@@ -348,6 +364,21 @@ int rf_launch_mds_fused(rf_handle* h, const float* d_old, const float* d_new, co
     fill_mds_cfg(h, a);
     a.P = P; a.counts = d_counts; a.Nstride = Kstride; a.px_old = d_old; a.px_new = d_new; a.mask = d_mask;
     a.mask_stride = mask_stride; a.Kstride = Kstride; a.kab_R = d_R; a.kab_h = d_h; a.prev_pose = d_prev_pose;
+    a.x_out = d_x; a.iters = d_iters; a.cost = nullptr; a.scratch = d_scratch;
+    k_mds<<<P, 32, 0, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+int rf_launch_mds_chain(rf_handle* h, const float* d_old, const float* d_new, const uint8_t* d_mask, int mask_stride,
+                        const int32_t* d_counts, int Kstride, int P, const double* d_R, const double* d_h,
+                        const double* d_prev_pose, const double* d_kf_und, const double* d_kf_pose, const int32_t* d_good_src,
+                        double* d_scratch, double* d_x, int32_t* d_iters) {
+    MdsArgs a; memset(&a, 0, sizeof(a));
+    fill_mds_cfg(h, a);
+    a.P = P; a.counts = d_counts; a.Nstride = Kstride; a.px_old = d_old; a.px_new = d_new; a.mask = d_mask;
+    a.mask_stride = mask_stride; a.Kstride = Kstride; a.kab_R = d_R; a.kab_h = d_h; a.prev_pose = d_prev_pose;
+    a.kf_und = d_kf_und; a.kf_pose = d_kf_pose; a.good_src = d_good_src;
     a.x_out = d_x; a.iters = d_iters; a.cost = nullptr; a.scratch = d_scratch;
     k_mds<<<P, 32, 0, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);

@@ -88,3 +88,41 @@ def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_fl
     res = {k: np.array(v) for k, v in out.items()}
     res["traj"], res["map"] = est, mp
     return res
+
+
+def run_odometry_device(sequences, init_pose=None, with_mds=True, graph=True, detector_mode=0, device=None, fe=None):
+    """The same loop for several independent sequences at once, entirely on the device (rf_seq, csrc/k_seq.cu):
+    features, keyframe state and poses never leave HBM between frames, re-detection (response, NMS, SSC bisection,
+    append) runs on the device for exactly the sequences that need it, and a step is one CUDA-graph launch.
+
+    sequences: [S][T] raw scans (u8 [A, 11 + bins] each; every sequence has T frames).  with_mds=False gives the pose
+    chain without motion compensation (T_wj = prev_pose @ [R, h], RawROAMSystem.py:201; BASELINE configs[1]).
+    Returns per-sequence arrays: poses [S, T, 3], R [S, T-1, 2, 2], h [S, T-1, 2, 1], mds_x [S, T-1, 6], n_tracked,
+    n_features_in, retrack [S, T-1], n_keyframes [S], and the raw per-step records (`steps`)."""
+    from . import _engine, _ffi
+    seqs = [list(s) for s in sequences]
+    S, T = len(seqs), len(seqs[0])
+    if any(len(s) != T for s in seqs):
+        raise ValueError("every sequence needs the same number of frames")
+    if fe is None:
+        if device is not None:
+            _engine.set_device(device)
+        fe = _engine.engine(raw_width=seqs[0][0].shape[1])
+    runner = fe.new_sequences(S, S * T, detector_mode=detector_mode)
+    try:
+        # arena layout: frame t of sequence s at index t * S + s  (one slot of S fresh scans per step)
+        for t in range(T):
+            runner.upload(t * S, np.stack([seqs[s][t] for s in range(S)]))
+        runner.reset(0, 1, init_pose)
+        for t in range(1, T):
+            runner.step(t * S, 1, with_mds=with_mds, graph=graph)
+        steps = [runner.results(t) for t in range(0, T)]
+        runner.sync()
+    finally:
+        runner.close()
+    rec = np.stack(steps, axis=1)                                   # [S, T]
+    return {"poses": rec["pose"], "R": rec["R"][:, 1:].reshape(S, T - 1, 2, 2), "h": rec["h"][:, 1:].reshape(S, T - 1, 2, 1),
+            "mds_x": rec["mds_x"][:, 1:], "kab_R": rec["kab_R"][:, 1:].reshape(S, T - 1, 2, 2), "kab_h": rec["kab_h"][:, 1:],
+            "n_tracked": rec["n_tracked"][:, 1:], "n_features_in": rec["n_features_in"][:, 1:],
+            "n_features_out": rec["n_features_out"], "retrack": rec["retrack"][:, 1:].astype(bool),
+            "n_keyframes": rec["n_keyframes"][:, -1], "status": rec["status"], "steps": rec}
