@@ -302,6 +302,7 @@ struct CliqueArgs {
     int16_t* adjseq;           // [P][Kpad][SEQCAP] slot-ordered neighbours of small-table nodes
     uint32_t* stack;           // [P][Kpad + 1][3 * SW + 1]  (subg | cand | ext | qn)
     int prune;
+    const int32_t* max_size;   // [P] exact maximum clique size from k_maxclique (0 = unknown) or nullptr
     int adj_in_smem;           // adjacency rows staged in shared memory (row stride g.RS words)
     long long node_limit;
     // outputs
@@ -470,6 +471,29 @@ __device__ __forceinline__ void set_copy(uint32_t* dst, const SetRef& s, int K, 
     for (int i = lane; i < n; i += 32) dst[i] = s.w[i];
 }
 
+// Greedy sequential colouring of a vertex set (lane w holds word w of the bitset; NWe <= 32): an upper bound on the
+// size of a clique inside the set.  Stops as soon as `need` colour classes are required (returns need): the caller
+// only asks whether fewer than `need` vertices can be pairwise adjacent.
+__device__ __forceinline__ int colour_bound(uint32_t Q, const uint32_t* __restrict__ adj, int RS, int NWe, int need, int lane) {
+    int k = 0;
+    while (__any_sync(FULL, Q != 0u)) {
+        if (++k >= need) return need;
+        uint32_t Qk = Q;
+        for (;;) {
+            const unsigned bm = __ballot_sync(FULL, Qk != 0u);
+            if (!bm) break;
+            const int src = __ffs(bm) - 1;
+            const uint32_t w = __shfl_sync(FULL, Qk, src);
+            const int b = __ffs(w) - 1;
+            const int v = src * 32 + b;
+            const uint32_t row = lane < NWe ? adj[(size_t)v * RS + lane] : 0u;
+            Qk &= ~row;
+            if (lane == src) { Qk &= ~(1u << b); Q &= ~(1u << b); }
+        }
+    }
+    return k;
+}
+
 #define PROF_MARK(slot) do { if (a.prof) { const long long _t = clock64(); pc[slot] += _t - tprev; tprev = _t; } } while (0)
 __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -585,6 +609,11 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         }
         best = ns - 1;
     }
+    // (1b) The exact maximum M (k_maxclique: order-free colouring branch-and-bound over several warps): the answer is the
+    // FIRST clique of size M in networkx order, so only subtrees that can still hold M vertices are walked, with the
+    // colouring bound instead of |cand|, and the search stops at the first clique of size M.
+    const int Mmax = (fast && a.prune && a.max_size && NWe <= 32) ? a.max_size[p] : 0;
+    if (Mmax > 0) best = Mmax - 1;
     PROF_MARK(2);   // greedy bound
 
     auto enter_node = [&]() {
@@ -701,6 +730,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     enter_node();
 
     for (;;) {
+        if (Mmax > 0 && nbest >= Mmax) break;
         if (ext.used() > 0) {
             if (pops >= a.node_limit) { status = RF_E_WORKLIMIT; break; }
             ++pops;
@@ -718,12 +748,18 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     best = qn; nbest = qn;
                     for (int i = lane; i < qn; i += 32) bestQ[i] = Q[i];
                     __syncwarp();
+                    if (Mmax > 0 && best >= Mmax) break;      // the first maximum clique: nothing later can be strictly larger
                 }
             } else {
                 const int ncand = bits_count2(cand.bits(), adjq, false, NWe, lane);
                 // a child is descended only if it can still beat the best clique so far; the parent's
                 // sets do not depend on that decision, so the order of later yields is unchanged
-                if (ncand > 0 && !(a.prune && qn + ncand <= best)) {
+                bool descend = ncand > 0 && !(a.prune && qn + ncand <= best);
+                if (descend && Mmax > 0) {
+                    const uint32_t cw = lane < NWe ? (cand.bits()[lane] & adjq[lane]) : 0u;
+                    descend = qn + colour_bound(cw, adjbits, RS, NWe, best - qn + 1, lane) > best;
+                }
+                if (descend) {
                     const int degq = deg[q];
                     const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
                     build_and_adj(chs, subg, nsub, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
@@ -745,6 +781,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     __syncwarp();
                     PROF_MARK(7);   // frame push
                     enter_node();
+                    if (Mmax > 0 && nbest >= Mmax) break;     // found by the cand-is-a-clique shortcut
                 }
             }
         } else {
@@ -770,6 +807,196 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         if (a.order_hash) a.order_hash[p] = hsh;
         if (a.prof) for (int k = 0; k < 8; ++k) a.prof[(size_t)p * 8 + k] = pc[k];
     }
+}
+
+
+// ------------------------------------------------------------------------------------
+// Exact maximum clique SIZE, order-free: bitset branch and bound with greedy colouring bounds
+// (Tomita & Seki's MCQ on bitsets, as in San Segundo's BBMC).  It only has to answer "how large", so it is
+// free of the set-order emulation above and can use several warps per problem: the root level is coloured
+// once, its branches (vertex i of the colouring order + its earlier neighbours) are handed out to the warps
+// from the most promising end, and the incumbent size is shared through shared memory.
+// Vertices are relabelled by descending degree first (better colourings, smaller trees).
+// One CTA of MC_WARPS warps per problem; K <= 1024 (32 words per bitset: one word per lane).
+// ------------------------------------------------------------------------------------
+#define MC_WARPS 4
+#define MC_ARENA 4096          // colouring entries per warp (vertex | colour << 16); overflow -> size unknown (0)
+
+struct MaxCliqueArgs {
+    int P, Kpad, NW;
+    const int32_t* counts;
+    const uint32_t* adjbits;   // [P][Kpad][NW]
+    int32_t* max_size;         // [P]
+    uint32_t* levels;          // [P][MC_WARPS][Kpad][NW]   candidate set of every DFS level
+    uint32_t* arena;           // [P][MC_WARPS][MC_ARENA]
+    int32_t* lvl_meta;         // [P][MC_WARPS][Kpad][2]     (arena base, entries left)
+};
+
+// colour the set held one word per lane; entries with colour >= kmin are appended to out[] (vertex | colour << 16) in
+// colouring order; returns the number of entries written (or -1 if more than cap), *ncol = colour classes used
+__device__ __forceinline__ int mc_colour(uint32_t Q, const uint32_t* __restrict__ adj, int RSa, int NWe, int kmin, uint32_t* out,
+                                         int cap, int lane, int* ncol) {
+    int k = 0, idx = 0;
+    while (__any_sync(FULL, Q != 0u)) {
+        ++k;
+        uint32_t Qk = Q;
+        for (;;) {
+            const unsigned bm = __ballot_sync(FULL, Qk != 0u);
+            if (!bm) break;
+            const int src = __ffs(bm) - 1;
+            const uint32_t w = __shfl_sync(FULL, Qk, src);
+            const int b = __ffs(w) - 1;
+            const int v = src * 32 + b;
+            const uint32_t row = lane < NWe ? adj[(size_t)v * RSa + lane] : 0u;
+            Qk &= ~row;
+            if (lane == src) { Qk &= ~(1u << b); Q &= ~(1u << b); }
+            if (k >= kmin) {
+                if (idx >= cap) { *ncol = k; return -1; }
+                if (lane == 0) out[idx] = (uint32_t)v | ((uint32_t)k << 16);
+                ++idx;
+            }
+        }
+    }
+    *ncol = k;
+    return idx;
+}
+
+__global__ void __launch_bounds__(32 * MC_WARPS) k_maxclique(const MaxCliqueArgs a) {
+    extern __shared__ uint32_t msm[];
+    __shared__ int s_best, s_next, s_fail, s_nroot;
+    const int p = blockIdx.x;
+    const int K = a.counts[p];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (K <= 1 || K > 1024) { if (tid == 0) a.max_size[p] = K <= 1 ? max(K, 0) : 0; return; }
+    const int NWe = (K + 31) >> 5, RSa = NWe | 1;
+    uint32_t* adj = msm;                                   // [K][RSa] relabelled adjacency
+    uint16_t* rank = (uint16_t*)(adj + (size_t)K * RSa);   // [K] new label of every vertex
+    uint16_t* deg = rank + K;
+    uint32_t* root = (uint32_t*)(deg + K);                 // [K] root colouring entries (rank + deg = K words: aligned)
+    const uint32_t* g = a.adjbits + (size_t)p * a.Kpad * a.NW;
+    if (tid == 0) { s_best = 0; s_fail = 0; }
+    for (int v = tid; v < K; v += blockDim.x) {
+        int c = 0;
+        for (int w = 0; w < NWe; ++w) c += __popc(g[(size_t)v * a.NW + w]);
+        deg[v] = (uint16_t)c;
+    }
+    for (int i = tid; i < K * RSa; i += blockDim.x) adj[i] = 0u;
+    __syncthreads();
+    for (int v = tid; v < K; v += blockDim.x) {            // rank by (degree desc, index asc)
+        const int dv = deg[v];
+        int r = 0;
+        for (int u = 0; u < K; ++u) { const int du = deg[u]; r += (du > dv) || (du == dv && u < v); }
+        rank[v] = (uint16_t)r;
+    }
+    __syncthreads();
+    for (int v = tid; v < K; v += blockDim.x) {            // row rank[v] is written by this thread only
+        uint32_t* row = adj + (size_t)rank[v] * RSa;
+        for (int w = 0; w < NWe; ++w) {
+            uint32_t bits = g[(size_t)v * a.NW + w];
+            while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; const int u = rank[w * 32 + b]; row[u >> 5] |= 1u << (u & 31); }
+        }
+    }
+    __syncthreads();
+    // ---- incumbent: greedy clique (always take the candidate with most neighbours among the candidates) ----
+    if (wid == 0) {
+        uint32_t Pw = lane < NWe ? ((K >= lane * 32 + 32) ? ~0u : (K > lane * 32 ? ((1u << (K - lane * 32)) - 1u) : 0u)) : 0u;
+        int size = 0;
+        while (__any_sync(FULL, Pw != 0u)) {
+            unsigned bestkey = 0;
+            for (int v0 = 0; v0 < K; v0 += 32) {
+                const int v = v0 + lane;
+                const uint32_t pv = __shfl_sync(FULL, Pw, v0 >> 5);
+                const bool valid = v < K && ((pv >> (v & 31)) & 1u);
+                int c = 0;
+                for (int w = 0; w < NWe; ++w) {
+                    const uint32_t pw = __shfl_sync(FULL, Pw, w);
+                    if (valid) c += __popc(pw & adj[(size_t)v * RSa + w]);
+                }
+                if (valid) bestkey = max(bestkey, ((unsigned)c << 16) | (unsigned)(0xFFFF - v));
+            }
+            bestkey = __reduce_max_sync(FULL, bestkey);
+            const int v = 0xFFFF - (int)(bestkey & 0xFFFF);
+            ++size;
+            Pw &= lane < NWe ? adj[(size_t)v * RSa + lane] : 0u;
+        }
+        // ---- root colouring ----
+        uint32_t Pall = lane < NWe ? ((K >= lane * 32 + 32) ? ~0u : (K > lane * 32 ? ((1u << (K - lane * 32)) - 1u) : 0u)) : 0u;
+        int ncol = 0;
+        const int n = mc_colour(Pall, adj, RSa, NWe, 1, root, K, lane, &ncol);
+        if (lane == 0) { s_best = size; s_nroot = n; s_next = n - 1; if (ncol <= size) s_next = -1; }   // colours == incumbent: optimal
+    }
+    __syncthreads();
+    const int nroot = s_nroot;
+    uint32_t* levels = a.levels + ((size_t)p * MC_WARPS + wid) * (size_t)a.Kpad * a.NW;
+    uint32_t* arena = a.arena + ((size_t)p * MC_WARPS + wid) * MC_ARENA;
+    int32_t* meta = a.lvl_meta + ((size_t)p * MC_WARPS + wid) * (size_t)a.Kpad * 2;
+    volatile int* vbest = &s_best;
+    // position of every (relabelled) vertex in the root order, for the prefix sets of the root branches
+    uint16_t* rpos = deg;                                  // deg is no longer needed
+    for (int i = tid; i < nroot; i += blockDim.x) rpos[root[i] & 0xFFFF] = (uint16_t)i;
+    __syncthreads();
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicSub(&s_next, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i < 0 || s_fail) break;
+        const uint32_t e = root[i];
+        const int v = (int)(e & 0xFFFF), c = (int)(e >> 16);
+        if (c <= *vbest) break;                           // every remaining root branch has a colour <= c
+        // P0 = N(v) restricted to the vertices before position i of the root order
+        uint32_t P0 = lane < NWe ? adj[(size_t)v * RSa + lane] : 0u;
+        { uint32_t t = P0; while (t) { const int b = __ffs(t) - 1; t &= t - 1; if (rpos[lane * 32 + b] >= i) P0 &= ~(1u << b); } }
+        if (!__any_sync(FULL, P0 != 0u)) { if (lane == 0 && 1 > *vbest) atomicMax(&s_best, 1); continue; }
+        int d = 0;                                         // DFS level; the clique built so far has d + 1 vertices
+        if (lane < NWe) levels[lane] = P0;
+        bool enter = true;
+        int top = 0;                                       // arena entries in use
+        bool failed = false;
+        for (;;) {
+            uint32_t* Lp = levels + (size_t)d * a.NW;
+            if (enter) {
+                const uint32_t Pw = lane < NWe ? Lp[lane] : 0u;
+                int ncol = 0;
+                const int kmin = max(*vbest - (d + 1) + 1, 1);
+                const int n = mc_colour(Pw, adj, RSa, NWe, kmin, arena + top, MC_ARENA - top, lane, &ncol);
+                if (n < 0) { failed = true; break; }
+                if (lane == 0) { meta[2 * d] = top; meta[2 * d + 1] = n; }
+                top += n;
+                __syncwarp();
+                enter = false;
+            }
+            const int base = meta[2 * d];
+            int left = meta[2 * d + 1];
+            bool pop = left <= 0;
+            uint32_t en = 0;
+            if (!pop) { en = arena[base + left - 1]; pop = (d + 1) + (int)(en >> 16) <= *vbest; }
+            if (pop) {
+                if (d == 0) break;
+                top = base;
+                --d;
+                continue;
+            }
+            const int u = (int)(en & 0xFFFF);
+            __syncwarp();
+            if (lane == 0) meta[2 * d + 1] = left - 1;
+            uint32_t Pw = lane < NWe ? Lp[lane] : 0u;
+            const uint32_t row = lane < NWe ? adj[(size_t)u * RSa + lane] : 0u;
+            const uint32_t newP = Pw & row;
+            if (lane == (u >> 5)) Lp[lane] = Pw & ~(1u << (u & 31));
+            __syncwarp();
+            const int cnt = __reduce_add_sync(FULL, __popc(newP));
+            const int size = d + 2;                        // clique with u
+            if (cnt == 0) { if (lane == 0 && size > *vbest) atomicMax(&s_best, size); continue; }
+            if (size + cnt <= *vbest) continue;
+            ++d;
+            if (lane < NWe) levels[(size_t)d * a.NW + lane] = newP;
+            __syncwarp();
+            enter = true;
+        }
+        if (failed) { if (lane == 0) s_fail = 1; break; }
+    }
+    __syncthreads();
+    if (tid == 0) a.max_size[p] = s_fail ? 0 : s_best;
 }
 
 // ------------------------------------------------------------------------------------
@@ -830,6 +1057,7 @@ struct CliqueWorkspace {
     int P;
     uint32_t* adjbits; int16_t* adjseq; uint32_t* stack;
     uint8_t* mask; int32_t *n_inliers, *nodes, *status; long long* n_yields; unsigned long long* hash;
+    int32_t* max_size; uint32_t* mc_levels; uint32_t* mc_arena; int32_t* mc_meta;
 };
 
 static CliqueGeom make_geom(int Kmax) {
@@ -864,6 +1092,10 @@ static CliqueWorkspace carve(void* base, int Kmax, int P) {
     ws.status = (int32_t*)take((size_t)P * 4);
     ws.n_yields = (long long*)take((size_t)P * 8);
     ws.hash = (unsigned long long*)take((size_t)P * 8);
+    ws.max_size = (int32_t*)take((size_t)P * 4);
+    ws.mc_levels = (uint32_t*)take((size_t)P * MC_WARPS * g.Kpad * g.NW * 4);
+    ws.mc_arena = (uint32_t*)take((size_t)P * MC_WARPS * MC_ARENA * 4);
+    ws.mc_meta = (int32_t*)take((size_t)P * MC_WARPS * g.Kpad * 2 * 4);
     return ws;
 }
 
@@ -871,7 +1103,9 @@ size_t rf_clique_ws_total(int Kmax, int P) {
     CliqueGeom g = make_geom(Kmax);
     auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
     return r((size_t)P * (g.Kpad + 1) * (3 * g.SW + 1) * 4) + r((size_t)P * g.Kpad * g.NW * 4) + r((size_t)P * g.Kpad * g.SEQCAP * 2) +
-           r((size_t)P * g.Kpad) + 3 * r((size_t)P * 4) + 2 * r((size_t)P * 8);
+           r((size_t)P * g.Kpad) + 3 * r((size_t)P * 4) + 2 * r((size_t)P * 8) +
+           r((size_t)P * 4) + r((size_t)P * MC_WARPS * g.Kpad * g.NW * 4) + r((size_t)P * MC_WARPS * MC_ARENA * 4) +
+           r((size_t)P * MC_WARPS * g.Kpad * 2 * 4);
 }
 
 static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t* d_counts, int prune, bool debug) {
@@ -881,6 +1115,22 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     a.mask = ws.mask; a.n_inliers = ws.n_inliers; a.nodes = ws.nodes; a.status = ws.status;
     a.n_yields = debug ? ws.n_yields : nullptr; a.order_hash = debug ? ws.hash : nullptr;
     a.prof = nullptr;
+    a.max_size = nullptr;
+    static const bool no_mc = getenv("RF_CLIQUE_NO_MAXSIZE") != nullptr;   // diagnostic: the round-1 search (greedy bound only)
+    if (!debug && prune && ws.g.Kpad <= 1024 && !no_mc) {
+        MaxCliqueArgs m;
+        m.P = ws.P; m.Kpad = ws.g.Kpad; m.NW = ws.g.NW; m.counts = d_counts; m.adjbits = ws.adjbits; m.max_size = ws.max_size;
+        m.levels = ws.mc_levels; m.arena = ws.mc_arena; m.lvl_meta = ws.mc_meta;
+        const int Kp = ws.g.Kpad, NWp = ws.g.NW;
+        const size_t msm = (size_t)Kp * (NWp | 1) * 4 + (size_t)Kp * 2 * 2 + 8 + (size_t)Kp * 4;
+        if (msm > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_maxclique, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+            if (e != cudaSuccess) return rf_fail(h, RF_E_CUDA, "maxclique smem %zu: %s", msm, cudaGetErrorString(e));
+        }
+        k_maxclique<<<ws.P, 32 * MC_WARPS, msm, h->stream>>>(m);
+        RF_CHECK_LAUNCH(h);
+        a.max_size = ws.max_size;
+    }
     static const bool want_prof = getenv("RF_CLIQUE_PROFILE") != nullptr;
     long long* d_prof = nullptr;
     if (want_prof && cudaMalloc(&d_prof, (size_t)ws.P * 64) == cudaSuccess) a.prof = d_prof;

@@ -185,3 +185,25 @@ def test_mds_recovers_known_motion(fe):
     assert cost < 1e-12
     assert np.abs(x[:2] - v[:2]).max() < 1e-4 and abs(x[2] - v[2]) < 1e-5
     assert np.abs(x[3:5] - pose[:2]).max() < 1e-4 and abs(x[5] - pose[2]) < 1e-5
+
+
+def test_clique_real_data_density_graphs(fe):
+    """Edge density 0.38-0.55 with a planted consistent set (what data/tiny and outlier_test.npz look like: 126-8097
+    maximal cliques, 2-4 tied maxima): the production search (exact maximum size from the order-free
+    colouring branch-and-bound, then the order-exact walk pruned to that size) picks networkx's first maximum clique."""
+    from oracle import restate as R
+    rng = np.random.default_rng(23)
+    for K, p, n_in in [(83, .45, 29), (96, .50, 40), (109, .38, 35), (120, .55, 45), (139, .48, 60), (160, .42, 50),
+                       (187, .40, 67), (139, .50, 0), (100, .55, 0), (64, .45, 10)]:
+        M = rng.random((K, K)) < p
+        if n_in:
+            M[:n_in, :n_in] |= rng.random((n_in, n_in)) < 0.97      # near-clique: several tied maxima
+        M = np.triu(M, 1); M = M | M.T
+        perm = rng.permutation(K)
+        M = M[np.ix_(perm, perm)]
+        np.fill_diagonal(M, True)
+        adj = M.astype(np.uint8)
+        clique, _ = R.first_max_clique_pruned(adj)
+        ref_mask = np.zeros(K, bool); ref_mask[clique] = True
+        mask_s, size_s, _, _, nodes = fe.clique_search(adj, prune=3)
+        assert size_s == len(clique) and np.array_equal(mask_s, ref_mask), f"K={K} p={p}"
