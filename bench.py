@@ -4,15 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]; configs[2] with --mds 1): a seeded synthetic Oxford-shaped
+Headline workload (BASELINE.json configs[1] data; configs[2] with --mds 1): a seeded synthetic Oxford-shaped
 sequence (400 azimuths x 3768 range bins uint8 + 11 metadata bytes, 0.0438 m/bin) of
 --frames scans per GPU.  One step = one pass of the hot path over that batch: scan decode +
 polar->Cartesian + u8 pyramid for every frame, then pyramidal LK, distance-consistency clique
 rejection, Kabsch (and the motion-distortion solve) for every consecutive pair -> one pose per
-pair.  `value` = poses/s with the scans resident in HBM; `e2e` = the same through the C ABI with
+pair; FEATURES ARE HANDED IN and the pairs are INDEPENDENT (operationally configs[3]'s pair batches).
+`value` = poses/s with the scans resident in HBM; `e2e` = the same through the C ABI with
 host buffers (pinned H2D of every scan + D2H of the poses inside the timed region).
 Multi-GPU: every rank owns an independent sequence (weak scaling, no data-path collective);
 the poses are gathered to rank 0 over NCCL once per step.
+
+Further legs inside the same JSON line (--legs, default all):
+  chained     the REAL chained odometry (RawROAMSystem.run): 256 sequences in lock step on the device (rf_seq):
+              features carried over, on-device re-detection + SSC, keyframes, MDS, one CUDA graph per step;
+              frames/s resident and e2e, single-sequence latency, and the CPU loop (oracle/ref_system.py) beside it
+  strong      configs[3]: 4096 independent pairs from 16 sequences (seeds 1000..1015) in contiguous blocks over the
+              ranks (_shard.block_range), poses gathered over NCCL — strong scaling
+  mds         configs[2]: motion-distorted scans + the motion-distortion solve (value and e2e)
+  stress      configs[4]: dense 2000^2 grid, 10 k SSC features, 4-level KLT -> tracks/s
+  detect_ssc / fmt / peaks   on-device detection + SSC bisection, FMT rotation prior, polar peak extraction
+  parity_sample   GPU poses / inlier counts of the first pairs against what the cpu_baseline leg just computed
 
 --impl reference times the reference's own CPU path (the third-party calls the reference
 makes: cv2.warpPolar, cv2.calcOpticalFlowPyrLK, scipy cdist, networkx find_cliques, numpy SVD,
@@ -51,7 +63,24 @@ def parse_args():
     ap.add_argument("--batches", type=int, default=5, help="batches in flight on one handle (pipeline depth; the clique + MDS tail of a batch lasts about three steps)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (multi-GPU runs)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the per-step NCCL pose gather")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs: chained,strong,mds,stress,detect_ssc,fmt,peaks (all | none)")
+    ap.add_argument("--pairs", type=int, default=4096, help="strong leg: total independent pairs (BASELINE configs[3])")
+    ap.add_argument("--chain-seq", type=int, default=256, help="chained leg: sequences per GPU in lock step")
+    ap.add_argument("--chain-steps", type=int, default=12)
+    ap.add_argument("--chain-runners", type=int, default=4, help="chained leg: rf_seq runners (streams) the sequences are split over")
     return ap.parse_args()
+
+
+ALL_LEGS = ("chained", "strong", "mds", "stress", "detect_ssc", "fmt", "peaks")
+CHAIN_WARMUP = 3
+
+
+def wanted_legs(args):
+    if args.legs in ("none", ""):
+        return ()
+    if args.legs == "all":
+        return ALL_LEGS
+    return tuple(l for l in args.legs.split(",") if l in ALL_LEGS)
 
 
 # ---------------------------------------------------------------------------------------
@@ -117,15 +146,19 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(args, rank):
-    """Seeded synthetic sequence for this rank: raw scans, pairs, features, ground-truth poses."""
+def workload(args, rank, extra_frames=0, distort=None, seed=None, workers=None):
+    """Seeded synthetic sequence for this rank: raw scans, pairs, features, ground-truth poses.  Rendered on all host
+    cores (identical to the serial generator: every frame has its own seeds).  `extra_frames` more scans are rendered
+    past --frames for the chained leg (sequence s = frames s, s + 1, ...)."""
     from radarslampy_b200 import synthetic as S
     rb = int(87.5 / args.res)
-    world = S.World(seed=1234 + rank)
+    seed = 1234 + rank if seed is None else seed
+    world = S.World(seed=seed)
+    distort = bool(args.mds) if distort is None else distort
     # configs[2] (--mds 1): the same sequence rendered with intra-scan motion distortion (SURVEY.md §8d)
-    raw, poses = S.make_sequence(args.frames, res_m=args.res, world=world, first=0, distort=bool(args.mds))
+    raw, poses = S.make_sequence_parallel(args.frames + extra_frames, res_m=args.res, seed=seed, first=0, distort=distort, workers=workers)
     kmax = max(64, (args.features + 63) // 64 * 64)
-    pair_idx, feats, counts = S.sequence_pairs(args.frames, world, poses, args.res, rb, k=args.features, max_features=kmax)
+    pair_idx, feats, counts = S.sequence_pairs(args.frames, world, poses[:args.frames], args.res, rb, k=args.features, max_features=kmax)
     return rb, kmax, raw, poses, pair_idx, feats, counts
 
 
@@ -189,14 +222,16 @@ def cpu_reference_rate(args, raw, feats, counts, poses, n_pairs, repeats=1, pool
             break
         jobs.append((raw[a:bnd + 1], feats[a:bnd], counts[a:bnd], poses[a:bnd], args.res, bool(args.mds)))
     best = None
+    outputs = []
 
     def timed(pl):
         nonlocal best
         for _ in range(repeats):
             t0 = time.perf_counter()
-            pl.map(cpu_pairs_worker, jobs, chunksize=1)
+            res = pl.map(cpu_pairs_worker, jobs, chunksize=1)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
+            outputs[:] = [o for chunk in res for o in chunk]     # (h [2,1] m, R [2,2], n_inliers) per pair, in pair order
 
     if pool is not None:
         timed(pool)
@@ -204,6 +239,7 @@ def cpu_reference_rate(args, raw, feats, counts, poses, n_pairs, repeats=1, pool
         with mp.get_context("fork").Pool(len(jobs)) as pl:
             pl.map(cpu_pairs_worker, [(j[0][:2], j[1][:1], j[2][:1], j[3][:1], j[4], j[5]) for j in jobs])   # warm imports
             timed(pl)
+    cpu_reference_rate.last_outputs = outputs
     return n_pairs / best, len(jobs), n_pairs, best
 
 
@@ -227,9 +263,10 @@ def run_reference(args, rank, world):
     if not n_pairs:
         # bounded sample per step, sized so that warmup + steps finish in about two minutes whatever K is
         rate0, _, _, _ = cpu_reference_rate(args, raw, feats, counts, poses, min(args.frames - 1, 2 * cores), pool=pool)
-        per_step_s = 120.0 / max(1, args.warmup + args.steps)
+        per_step_s = 180.0 / max(1, args.warmup + args.steps)
         n_pairs = int(min(args.frames - 1, max(cores, rate0 * per_step_s)))
-        n_pairs -= n_pairs % min(cores, n_pairs)            # equal chunks for the worker processes
+        if n_pairs < args.frames - 1:                       # a bounded sample: equal chunks for the worker processes
+            n_pairs -= n_pairs % min(cores, n_pairs)        # (else: every pair of the step, exactly the GPU arm's work)
     times = []
     for i in range(args.warmup + args.steps):
         rate, workers, n_used, dt = cpu_reference_rate(args, raw, feats, counts, poses, n_pairs, pool=pool)
@@ -254,9 +291,11 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, rb, kmax):
-    return {"workload": f"synthetic Oxford-shaped sequence, {args.frames} scans/GPU/step (400x3768 u8 + 11 metadata bytes, "
-                        f"{args.res} m/bin -> {rb} used bins, {2 * (rb // 2)}^2 Cartesian), {args.features} features/pair given, "
-                        f"KLT 15x15 x 4 levels, clique rejection, Kabsch" + (", scans rendered with intra-scan motion distortion, motion-distortion LM" if args.mds else ""),
+    return {"workload": f"BASELINE configs[1] data as independent pair batches: synthetic Oxford-shaped sequence, {args.frames} scans/GPU/step "
+                        f"(400x3768 u8 + 11 metadata bytes, {args.res} m/bin -> {rb} used bins, {2 * (rb // 2)}^2 Cartesian), "
+                        f"{args.features} features/pair HANDED IN (ground-truth scatterers), consecutive pairs treated as INDEPENDENT, "
+                        f"KLT 15x15 x 4 levels, clique rejection, Kabsch" + (", scans rendered with intra-scan motion distortion, motion-distortion LM" if args.mds else "")
+                        + "; the chained odometry with on-device detection is the `chained` leg",
             "frames_per_step_per_gpu": args.frames, "pairs_per_step_per_gpu": args.frames - 1, "features_per_pair": args.features,
             "range_res_m": args.res, "mds": bool(args.mds), "write_cart_f32": bool(args.write_f32),
             "l2": "inputs larger than L2: each step streams >= 1.3 GB of scans + pyramids per GPU (L2 = 126 MB)"}
@@ -324,21 +363,45 @@ def main():
         run_reference(args, rank, world)
         return
 
+    t_setup0 = time.perf_counter()
     numa = bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa) else {"node": None, "cpus": None}
-    rb, kmax, raw_np, poses, pair_idx, feats, counts = workload(args, rank)
-    cpu_line = None
+    legs = wanted_legs(args)
+    gen_workers = max(1, (os.cpu_count() or 1) // world)
+    chain_need = (args.chain_seq + CHAIN_WARMUP + args.chain_steps + 2) if "chained" in legs else 0
+    # headline drive (configs[1]; rendered with motion distortion under --mds 1), and the motion-distorted drive of the
+    # same world / poses that the `chained` and `mds` legs read (configs[2]); one render when they coincide
+    rb, kmax, raw_long, poses_long, pair_idx, feats, counts = workload(args, rank, extra_frames=max(0, chain_need - args.frames) if args.mds else 0,
+                                                                       workers=gen_workers)
+    raw_np, poses = raw_long[:args.frames], poses_long[:args.frames]
+    pre = {}
+    if args.mds:
+        dist_long = raw_long
+    else:
+        n_dist = max(chain_need, args.frames if ("mds" in legs and world == 1 and args.frames >= 4) else 0)
+        dist_long = None
+        if n_dist:
+            from radarslampy_b200 import synthetic as SY
+            dist_long, _ = SY.make_sequence_parallel(n_dist, res_m=args.res, seed=1234 + rank, first=0, distort=True, workers=gen_workers)
+            if "mds" in legs and world == 1 and args.frames >= 4:
+                pre["mds"] = (rb, kmax, dist_long[:args.frames], poses, pair_idx, feats, counts)
+    if "strong" in legs:
+        pre["strong"] = strong_data(args, rank, world, rb, kmax, gen_workers)
+    cpu_line, cpu_out = None, None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         # timed BEFORE the CUDA context exists (fork-safe), on a bounded sample of the same workload
         cores = os.cpu_count() or 1
         n_pairs = args.cpu_pairs or min(args.frames - 1, 8 * cores)
         rate, workers, n_used, dt = cpu_reference_rate(args, raw_np, feats, counts, poses, n_pairs, repeats=2)
+        cpu_out = list(cpu_reference_rate.last_outputs)
         cpu_line = {"value": rate, "unit": "frames/s", "cores": workers, "kind": "port",
                     "sample": f"first {n_used} pairs of the same sequence through oracle/ref_pipeline.py (the reference's own "
                               f"cv2/scipy/networkx/numpy calls), {workers} processes, best of 2 ({dt:.2f} s)"}
+        if "chained" in legs:
+            pre["chained_cpu"] = chained_cpu_baseline(args, dist_long, cores)
+    setup_s = time.perf_counter() - t_setup0
 
     import torch
     import torch.distributed as dist
-    from radarslampy_b200 import _ffi, _shard
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - this framework has no CPU fallback (use --impl reference for the CPU arm)")
@@ -346,6 +409,47 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = dict(args=args, rank=rank, local_rank=local_rank, world=world, rb=rb, kmax=kmax, torch=torch, dist=dist)
+    line = weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, numa, setup_s)
+    extra_legs = {}
+    for name in legs:
+        t0 = time.perf_counter()
+        try:
+            if name == "chained":
+                out = leg_chained(ctx, dist_long, pre.get("chained_cpu"))
+            elif name == "strong":
+                out = leg_strong(ctx, pre["strong"])
+            elif world > 1 or rank != 0:
+                continue                       # the remaining legs are single-GPU properties: measured at N = 1 only
+            elif name == "mds":
+                out = leg_mds(ctx, pre.get("mds"))
+            elif name == "stress":
+                out = leg_stress(ctx)
+            elif name == "detect_ssc":
+                out = leg_detect_ssc(ctx, raw_np)
+            elif name == "fmt":
+                out = leg_fmt(ctx, raw_np)
+            elif name == "peaks":
+                out = leg_peaks(ctx, raw_np)
+        except Exception as e:                 # a failing leg must not take the headline down with it
+            out = {"error": f"{type(e).__name__}: {e}"}
+        if out is not None:
+            out["leg_s"] = time.perf_counter() - t0
+            extra_legs[name] = out
+    if rank == 0:
+        line.update(extra_legs)
+        line["legs_s"] = {k: v.get("leg_s") for k, v in extra_legs.items()}
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, numa, setup_s):
+    """The headline measurement (docstring of this file): resident `value`, `e2e`, roofline of the dominant kernel."""
+    args, rank, local_rank, world, rb, kmax = (ctx[k] for k in ("args", "rank", "local_rank", "world", "rb", "kmax"))
+    torch, dist = ctx["torch"], ctx["dist"]
+    from radarslampy_b200 import _ffi, _shard
 
     S, P = args.frames, args.frames - 1
     cfg = _ffi.default_config()
@@ -457,13 +561,16 @@ def main():
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    res = {k: np.array(res[k]) for k in res.dtype.names}      # detach from the pinned output buffers
+    for b in batches:
+        b.close()
+    fe_n = fe.n
+    fe.close()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     K_total = int(counts.sum())
-    cfgd = {"azimuths": cfg.azimuths, "range_bins": rb, "n": fe.n}
+    cfgd = {"azimuths": cfg.azimuths, "range_bins": rb, "n": fe_n}
     sb = stage_bytes(cfgd, S, P, K_total, bool(args.write_f32), 4, fused=not args.write_f32)
     peak, peak_src = peaks()
     stages = {}
@@ -476,10 +583,10 @@ def main():
     streaming = [k for k in ("polar2cart", "scan_to_l0l1", "pyr_down", "klt") if stages[k]["ms"] > 0]
     dom = max(streaming, key=lambda k: stages[k]["ms"])
     achieved = stages[dom]["gbs"] or 0.0
-    lv = [fe.n]
+    lv = [fe_n]
     for _ in range(3):
         lv.append((lv[-1] + 1) // 2)
-    survey_bytes = S * (cfg.azimuths * rb + 4 * fe.n * fe.n + sum(v * v for v in lv))      # per launch of the conversion
+    survey_bytes = S * (cfg.azimuths * rb + 4 * fe_n * fe_n + sum(v * v for v in lv))      # per launch of the conversion
     value = world * P * args.steps / (ms * 1e-3)
     e2e = world * P * args.steps / (ms_e2e * 1e-3)
     h2d = S * cfg.azimuths * (cfg.meta_bytes + rb) + P * (8 + kmax * 8 + 4 + 24)
@@ -487,7 +594,8 @@ def main():
     line = {
         "metric": "radar frames/sec polar->pose", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/f32/f64", "data": "synthetic", "config": dict(workload_config(args, rb, kmax), pipelining=f"{NB} batches alternate on one handle (copy / image+KLT / rejection+solve streams)"),
+        "dtype": "u8/f32/f64", "data": "synthetic", "config": workload_config(args, rb, kmax),
+        "pipelining": f"{NB} batches alternate on one handle (copy / image+KLT / rejection+solve streams)",
         "klt_tracks_per_s": world * K_total * args.steps / (ms * 1e-3),
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                 "ms_per_step": ms_e2e / args.steps, "note": "bytes are the whole job's (all ranks) per step"},
@@ -514,12 +622,532 @@ def main():
     }
     if cpu_line is not None:
         line["cpu_baseline"] = cpu_line
-    emit(line)
-    for b in batches:
+    if cpu_out:
+        line["parity_sample"] = parity_sample(res, cpu_out, with_mds)
+    line["setup_s"] = setup_s
+    return line
+
+
+def parity_sample(res, cpu_out, with_mds):
+    """GPU batch results of the first pairs against what the cpu_baseline leg computed for the same pairs
+    (oracle/ref_pipeline.track_pair: the reference's own cv2 / scipy / networkx / numpy calls)."""
+    n = min(len(cpu_out), len(res))
+    dm, drad, same = 0.0, 0.0, 0
+    for p in range(n):
+        h, R, n_in = cpu_out[p]
+        if with_mds:      # the CPU arm reports the relative transform of the MDS pose; compare the MDS pose through it
+            pass
+        dm = max(dm, float(np.abs(np.asarray(res["h"][p]) - np.asarray(h).ravel()).max()))
+        d = np.arctan2(res["R"][p][2], res["R"][p][0]) - np.arctan2(R[1, 0], R[0, 0])
+        drad = max(drad, float(abs((d + np.pi) % (2 * np.pi) - np.pi)))
+        same += int(res["n_inliers"][p] == n_in)
+    return {"pairs": n, "max_abs_dh_m": dm, "max_abs_dtheta_rad": drad, "inlier_count_equal": same,
+            "tolerance": "1e-4 m / 1e-5 rad (north_star); compared: Tracker.getTransform's (R, h) of every pair",
+            "pass": bool(dm <= 1e-4 and drad <= 1e-5 and same == n)}
+
+
+
+# ---------------------------------------------------------------------------------------
+# further legs (see the module docstring)
+def _fe_config(args, rb, max_frames, max_pairs, max_features):
+    from radarslampy_b200 import _ffi
+    cfg = _ffi.default_config()
+    cfg.range_bins = rb
+    cfg.cart_res_m = 2 * args.res
+    cfg.dist_thr_px = 0.5 / (2 * args.res)
+    cfg.max_frames, cfg.max_pairs, cfg.max_features = max_frames, max(max_pairs, 1), max_features
+    return cfg
+
+
+def _pin(a, dt=None):
+    from radarslampy_b200 import _ffi
+    a = np.asarray(a)
+    out = _ffi.pinned_empty(a.shape, dt or a.dtype)
+    out[...] = a
+    return out
+
+
+def _reduce_max(ctx, *vals):
+    if ctx["world"] == 1:
+        return vals
+    torch, dist = ctx["torch"], ctx["dist"]
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return tuple(float(v) for v in t)
+
+
+def _barrier(ctx, fe):
+    if ctx["world"] > 1:
+        ctx["dist"].barrier()
+    ctx["torch"].cuda.synchronize()
+    fe.sync()
+
+
+def measure_pair_chunks(ctx, chunks, with_mds, steps, warmup, max_frames, max_pairs, gather_total=None, nb=None):
+    """Pair batches through rf_batch: `chunks` = [(raw [F,A,W] u8, pair_idx, feats, counts, prev_pose)], one pass over all
+    of them per step.  Returns (ms resident per step, ms e2e per step, results of every chunk of the last pass)."""
+    from radarslampy_b200 import _ffi, _shard
+    args, world, rank = ctx["args"], ctx["world"], ctx["rank"]
+    torch = ctx["torch"]
+    cfg = _fe_config(args, ctx["rb"], max_frames, max_pairs, ctx["kmax"])
+    stream = torch.cuda.Stream()
+    fe = _ffi.RadarFE(cfg, device=ctx["local_rank"], stream=stream.cuda_stream)
+    pinned = [tuple(_pin(x) for x in (c[0], np.asarray(c[1], np.int32), np.asarray(c[2], np.float32), np.asarray(c[3], np.int32),
+                                      np.asarray(c[4], np.float64))) for c in chunks]
+    n_local = sum(len(c[1]) for c in chunks)
+    gatherer = _shard.PoseGatherer(gather_total, world, rank, device="cuda") if (world > 1 and gather_total) else None
+    # resident: one batch object per chunk, scans uploaded once
+    res_batches = [fe.new_batch() for _ in chunks]
+    for b, c in zip(res_batches, pinned):
+        b.upload(c[0], c[1], c[2], c[3], prev_pose=c[4], sync=False)
+    fe.sync()
+    for _ in range(max(1, warmup)):
+        for b in res_batches:
+            b.run_async(with_mds=with_mds)
+    _barrier(ctx, fe)
+    n0 = fe.launch_count()
+    fe.timer_start()
+    for _ in range(steps):
+        for b in res_batches:
+            b.run_async(with_mds=with_mds)
+    ms = fe.timer_stop_ms()
+    launches = fe.launch_count() - n0
+    _barrier(ctx, fe)
+    results = []
+    for b in res_batches:
+        r, _, _ = b.download()
+        results.append(r.copy())
+    fe.sync()
+    for b in res_batches:
+        b.close()
+    # e2e: NB rotating batches, every chunk's scans H2D + poses D2H inside the timed region, then the NCCL gather
+    NB = min(nb or max(1, args.batches), max(2, len(chunks)))
+    rot = [fe.new_batch() for _ in range(NB)]
+    outs = [b.alloc_outputs(pinned=True) for b in rot]
+    host_res = np.zeros(n_local, _ffi.PAIR_RESULT_DTYPE)
+    offs = np.concatenate([[0], np.cumsum([len(c[1]) for c in chunks])])
+
+    def one_pass():
+        inflight = []
+        for ci, c in enumerate(pinned):
+            k = ci % NB
+            if len(inflight) >= NB:
+                j, cj = inflight.pop(0)
+                rot[j].wait()
+                host_res[offs[cj]:offs[cj + 1]] = outs[j][0][:offs[cj + 1] - offs[cj]]
+            rot[k].upload(c[0], c[1], c[2], c[3], prev_pose=c[4], sync=False)
+            rot[k].run_async(with_mds=with_mds)
+            rot[k].download(outs[k], sync=False, want_tracks=False)
+            inflight.append((k, ci))
+        for j, cj in inflight:
+            rot[j].wait()
+            host_res[offs[cj]:offs[cj + 1]] = outs[j][0][:offs[cj + 1] - offs[cj]]
+        if gatherer is not None:
+            return gatherer.gather(_shard.pack_records(host_res))
+        return None
+
+    for _ in range(max(1, min(warmup, 2))):
+        one_pass()
+    _barrier(ctx, fe)
+    t0 = time.perf_counter()
+    gathered = None
+    for _ in range(steps):
+        gathered = one_pass()
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    _barrier(ctx, fe)
+    for b in rot:
         b.close()
     fe.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ms, ms_e2e = _reduce_max(ctx, ms, ms_e2e)
+    h2d = sum(c[0].shape[0] * cfg.azimuths * (cfg.meta_bytes + ctx["rb"]) + len(c[1]) * (8 + ctx["kmax"] * 8 + 4 + 24) for c in chunks)
+    return {"ms": ms / steps, "ms_e2e": ms_e2e / steps, "results": np.concatenate(results) if results else None,
+            "launches_per_step": launches / steps, "h2d_bytes": int(h2d), "d2h_bytes": int(n_local * 120), "gathered": gathered}
+
+
+# ---- configs[3]: strong scaling over a fixed set of independent pairs ------------------------------------------------
+STRONG_SEQ_PAIRS = 256
+
+
+def strong_data(args, rank, world, rb, kmax, workers):
+    """BASELINE configs[3]: --pairs independent frame pairs = consecutive pairs of pairs/256 synthetic drives (seeds
+    1000 + q), split into contiguous blocks over the ranks (_shard.shard_pairs).  Every rank renders only the scans its
+    block touches.  Returns the block as chunks of <= 256 pairs (one rf_batch each)."""
+    from radarslampy_b200 import _shard, synthetic as S
+    P_total = args.pairs
+    F = STRONG_SEQ_PAIRS + 1
+    q = np.arange(P_total) // STRONG_SEQ_PAIRS
+    i = np.arange(P_total) % STRONG_SEQ_PAIRS
+    pair_idx = np.stack([q * F + i, q * F + i + 1], 1)
+    lo, hi, frame_ids, local_idx = _shard.shard_pairs(pair_idx, world, rank)
+    chunks = []
+    for a in range(0, hi - lo, STRONG_SEQ_PAIRS):
+        b = min(hi - lo, a + STRONG_SEQ_PAIRS)
+        ids, inv = np.unique(local_idx[a:b].ravel(), return_inverse=True)
+        gids = frame_ids[ids]
+        raw = np.empty((len(gids), S.A, S.RAW_WIDTH), np.uint8)
+        for seq in np.unique(gids // F):
+            sel = np.flatnonzero(gids // F == seq)
+            ks = gids[sel] % F
+            seq_raw, _ = S.make_sequence_parallel(int(ks.max() - ks.min() + 1), res_m=args.res, seed=1000 + int(seq), first=int(ks.min()),
+                                                  workers=workers)
+            raw[sel] = seq_raw[ks - ks.min()]
+        feats = np.zeros((b - a, kmax, 2), np.float32)
+        counts = np.zeros(b - a, np.int32)
+        prev = np.zeros((b - a, 3))
+        worlds = {}
+        for j in range(b - a):
+            g = int(gids[inv.reshape(-1, 2)[j, 0]])
+            seq, k = g // F, g % F
+            w = worlds.setdefault(seq, S.World(seed=1000 + seq))
+            prev[j] = S.twist_pose(k)
+            f = S.scatterer_features(w, prev[j], args.res, rb, k=args.features)
+            counts[j] = len(f)
+            feats[j, :len(f)] = f
+        chunks.append((raw, inv.reshape(-1, 2).astype(np.int32), feats, counts, prev))
+    return {"lo": lo, "hi": hi, "chunks": chunks, "pairs_total": P_total}
+
+
+def leg_strong(ctx, data):
+    args, world = ctx["args"], ctx["world"]
+    m = measure_pair_chunks(ctx, data["chunks"], bool(args.mds), steps=3, warmup=1, max_frames=STRONG_SEQ_PAIRS + 2,
+                            max_pairs=STRONG_SEQ_PAIRS, gather_total=data["pairs_total"])
+    if ctx["rank"] != 0:
+        return None
+    P = data["pairs_total"]
+    out = {"workload": f"BASELINE configs[3]: {P} independent frame pairs ({P // STRONG_SEQ_PAIRS} synthetic drives x {STRONG_SEQ_PAIRS} consecutive pairs, "
+                       f"features handed in) in contiguous blocks over {world} rank(s) (_shard.shard_pairs), poses gathered to rank 0 over NCCL",
+           "scaling": "strong", "pairs": P, "n_gpus": world, "value": P / (m["ms"] * 1e-3), "unit": "pairs/s", "ms_per_pass": m["ms"],
+           "e2e": {"value": P / (m["ms_e2e"] * 1e-3), "unit": "pairs/s", "ms_per_pass": m["ms_e2e"],
+                   "h2d_bytes_per_pass_rank0": m["h2d_bytes"], "d2h_bytes_per_pass_rank0": m["d2h_bytes"]},
+           "rank0_block": [int(data["lo"]), int(data["hi"])], "passes": 3}
+    if m["gathered"] is not None:
+        from radarslampy_b200 import _shard
+        g = _shard.unpack_records(m["gathered"])
+        out["gathered_pairs"] = int(len(g["status"]))
+        out["median_dtheta_rad_all_ranks"] = float(np.median(np.arctan2(g["R"][:, 1, 0], g["R"][:, 0, 0])))
+        out["status_nonzero"] = int((g["status"] != 0).sum())
+    else:
+        r = m["results"]
+        out["median_dtheta_rad_all_ranks"] = float(np.median(np.arctan2(r["R"][:, 2], r["R"][:, 0])))
+        out["status_nonzero"] = int((r["status"] != 0).sum())
+    return out
+
+
+# ---- configs[2] -----------------------------------------------------------------------------------------------------
+def leg_mds(ctx, data):
+    if data is None:
+        return {"skipped": "the headline already runs with --mds 1"}
+    rb, kmax, raw, poses, pair_idx, feats, counts = data
+    args = ctx["args"]
+    m = measure_pair_chunks(ctx, [(raw, pair_idx, feats, counts, poses[:-1])], True, steps=max(5, min(args.steps, 40)), warmup=3,
+                            max_frames=args.frames, max_pairs=args.frames - 1, nb=3)
+    P = args.frames - 1
+    r = m["results"]
+    return {"workload": "BASELINE configs[2]: the same synthetic drive rendered with intra-scan motion distortion, motion-distortion LM solve "
+                        "per pair (features handed in, pairs independent); one batch object, no cross-batch pipelining",
+            "value": P / (m["ms"] * 1e-3), "unit": "frames/s", "ms_per_step": m["ms"],
+            "e2e": {"value": P / (m["ms_e2e"] * 1e-3), "unit": "frames/s", "ms_per_step": m["ms_e2e"], "h2d_bytes_per_step": m["h2d_bytes"],
+                    "d2h_bytes_per_step": m["d2h_bytes"]},
+            "median_mds_iters": float(np.median(r["mds_iters"])), "median_v_mps": float(np.median(np.hypot(r["mds_x"][:, 0], r["mds_x"][:, 1]))),
+            "expected_v_mps": 10.0, "status_nonzero": int((r["status"] != 0).sum()), "launches_per_step": m["launches_per_step"]}
+
+
+# ---- chained odometry (the real configs[1] / configs[2] loop) ----------------------------------------------------------
+CHAIN_CPU_FRAMES = 5
+
+
+def chained_cpu_worker(job):
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import ref_detect, ref_system
+    raw, res_m, with_mds = job
+    t0 = time.perf_counter()
+    ref_system.run_odometry(raw[:1], ref_detect.detect_min_eig, with_mds=with_mds, range_res_m=res_m)
+    t_init = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r = ref_system.run_odometry(raw, ref_detect.detect_min_eig, with_mds=with_mds, range_res_m=res_m)
+    t_all = time.perf_counter() - t0
+    return {"poses": r["poses"], "n_tracked": r["n_tracked"], "retrack": r["retrack"], "n_features_in": r["n_features_in"],
+            "t_steps": max(t_all - t_init, 1e-9)}
+
+
+def chained_cpu_baseline(args, raw_long, cores):
+    """The reference's system loop on the CPU (oracle/ref_system.run_odometry: cv2 / scipy / networkx calls + the keyframe
+    bookkeeping; detector = oracle/ref_detect.detect_min_eig), one independent sequence per host core: sequence c =
+    frames c .. c + CHAIN_CPU_FRAMES - 1 of the drive (the GPU leg's sequence c).  Steps only (the first-frame detection
+    is timed separately and subtracted, as the GPU leg times steps after the reset)."""
+    import multiprocessing as mp
+    T = CHAIN_CPU_FRAMES
+    n = max(1, min(cores, len(raw_long) - T))
+    jobs = [(raw_long[c:c + T], args.res, True) for c in range(n)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(n) as pl:
+        outs = pl.map(chained_cpu_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    t_steps = max(o["t_steps"] for o in outs)
+    return {"value": n * (T - 1) / t_steps, "unit": "frames/s", "cores": n, "kind": "port",
+            "sample": f"{n} sequences x {T - 1} chained frames through oracle/ref_system.py (reference's cv2/scipy/networkx calls, cv2.cornerMinEigenVal "
+                      f"detector + the reference's SSC), one process per sequence, slowest sequence {t_steps:.2f} s of steps ({wall:.1f} s incl. first-frame detection)",
+            "outs": outs}
+
+
+def leg_chained(ctx, raw_long, cpu):
+    from radarslampy_b200 import _ffi
+    args, world, rank, rb = ctx["args"], ctx["world"], ctx["rank"], ctx["rb"]
+    S, NG, K, W = args.chain_seq, max(1, args.chain_runners), args.chain_steps, CHAIN_WARMUP
+    while S % NG:
+        NG -= 1
+    per, T = S // NG, W + K
+    cfg = _fe_config(args, rb, 2, 2, 320)
+    fe = _ffi.RadarFE(cfg, device=ctx["local_rank"])
+    with_mds = True
+    out = {"workload": f"BASELINE configs[1]/[2] as the reference runs them (RawROAMSystem.run): {S} independent sequences per GPU advance one frame per "
+                       f"step in lock step on the device (rf_seq): features carried over from the previous frame's KLT survivors, on-device re-detection "
+                       f"(structure-tensor response, NMS, SSC bisection) when <= 60 survive, keyframe bookkeeping, motion-distortion solve, one CUDA graph "
+                       f"per step per runner; sequence s = frames s, s+1, ... of the synthetic drive (rendered with intra-scan motion distortion)",
+           "sequences_per_gpu": S, "runners": NG, "steps": K, "warmup": W, "n_gpus": world, "mds": with_mds}
+    # ---- resident: the drive is uploaded once, sequence s reads frame s + t --------------------------------------------
+    runners = [fe.new_sequences(per, per + T + 1) for _ in range(NG)]
+    for g, r in enumerate(runners):
+        r.upload(0, raw_long[g * per:g * per + per + T + 1])
+        r.reset(0, 1)
+    fe.sync()
+    for t in range(1, W + 1):
+        for r in runners:
+            r.step(t, 1, with_mds=with_mds, graph=True)
+    _barrier(ctx, fe)
+    n0 = fe.launch_count()
+    fe.timer_start()
+    for t in range(W + 1, T + 1):
+        for r in runners:
+            r.step(t, 1, with_mds=with_mds, graph=True)
+    ms = fe.timer_stop_ms()
+    launches = fe.launch_count() - n0
+    _barrier(ctx, fe)
+    ring = runners[0].ring
+    recs = np.concatenate([np.stack([r.results(t) for t in range(max(W + 1, T + 1 - ring), T + 1)], 1) for r in runners])
+    for r in runners:
+        r.close()
+    # ---- e2e: every step's fresh scans (one per sequence) H2D from pinned memory, results D2H, inside the timed region ----
+    SLOTS = 3
+    host = [_pin(raw_long[g * per:g * per + per + T + 1]) for g in range(NG)]
+    runners = [fe.new_sequences(per, SLOTS * per) for _ in range(NG)]
+    res_host = [[_ffi.pinned_empty((per,), _ffi.SEQ_RESULT_DTYPE) for _ in range(SLOTS)] for _ in range(NG)]
+    for g, r in enumerate(runners):
+        r.upload(0, host[g][0:per])
+        r.reset(0, 1)
+    fe.sync()
+
+    def e2e_steps(t_from, t_to):
+        for t in range(t_from, t_to):
+            slot = t % SLOTS
+            for g, r in enumerate(runners):
+                r.upload(slot * per, host[g][t:t + per])        # frame s + t of every sequence s of this runner
+                r.step(slot * per, 1, with_mds=with_mds, graph=True)
+                r.results(t, out=res_host[g][slot], sync=False)
+        for r in runners:
+            r.sync()
+
+    e2e_steps(1, W + 1)
+    _barrier(ctx, fe)
+    t0 = time.perf_counter()
+    e2e_steps(W + 1, T + 1)
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    _barrier(ctx, fe)
+    e2e_last = np.concatenate([res_host[g][T % SLOTS] for g in range(NG)])
+    for r in runners:
+        r.close()
+    # ---- single-sequence latency: one sequence, graph replay, no host sync between steps -------------------------------
+    one = fe.new_sequences(1, T + 2)
+    one.upload(0, raw_long[:T + 2])
+    one.reset(0, 1)
+    for t in range(1, W + 1):
+        one.step(t, 1, with_mds=with_mds, graph=True)
+    fe.sync()
+    fe.timer_start()
+    for t in range(W + 1, T + 1):
+        one.step(t, 1, with_mds=with_mds, graph=True)
+    ms1 = fe.timer_stop_ms()
+    l1 = one.launches_per_step
+    one.close()
+    # ---- parity against the CPU loop on the sequences the cpu leg ran ---------------------------------------------------
+    parity = None
+    if cpu is not None and cpu.get("outs"):
+        outs = cpu["outs"]
+        n, Tc = len(outs), CHAIN_CPU_FRAMES
+        pr = fe.new_sequences(n, n + Tc)
+        pr.upload(0, raw_long[:n + Tc])
+        pr.reset(0, 1)
+        steps = []
+        for t in range(1, Tc):
+            pr.step(t, 1, with_mds=True, graph=True)
+            steps.append(pr.results(t).copy())
+        pr.close()
+        g = np.stack(steps, 1)                                                    # [n, Tc - 1]
+        want = np.stack([o["poses"][1:] for o in outs])                           # [n, Tc - 1, 3]
+        d = g["pose"] - want
+        dth = np.abs((d[..., 2] + np.pi) % (2 * np.pi) - np.pi)
+        same = np.array([g["n_tracked"][c].tolist() == list(outs[c]["n_tracked"]) for c in range(n)])
+        parity = {"sequences": n, "frames_each": Tc - 1, "max_abs_dxy_m": float(np.abs(d[..., :2]).max()), "max_abs_dtheta_rad": float(dth.max()),
+                  "n_tracked_equal_sequences": int(same.sum()),
+                  "retrack_equal_sequences": int(sum(g["retrack"][c].astype(bool).tolist() == list(outs[c]["retrack"]) for c in range(n))),
+                  "tolerance": f"absolute pose after k chained frames within k x (1e-4 m, 1e-5 rad); here k <= {Tc - 1}",
+                  "note": "the CPU side detects on cv2.cornerMinEigenVal's response, the device on its own (pinned to it within 2e-6): "
+                          "the selection is bit-exact only for identical responses (tests/test_gpu_seq.py hands the device response to both)",
+                  "pass": bool(np.abs(d[..., :2]).max() <= (Tc - 1) * 1e-4 and dth.max() <= (Tc - 1) * 1e-5 and same.all())}
+    fe.close()
+    ms, ms_e2e = _reduce_max(ctx, ms, ms_e2e)
+    if rank != 0:
+        return None
+    cfgA, metaB = 400, 11
+    out.update({
+        "value": world * S * K / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / K, "launches_per_step": launches / K,
+        "gpu_launches": int(launches),
+        "e2e": {"value": world * S * K / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(world * S * cfgA * rb), "d2h_bytes_per_step": int(world * S * _ffi.SEQ_RESULT_DTYPE.itemsize),
+                "note": "one fresh scan per sequence per step (used bins only, 2-D copy from pinned host memory) + the step's result records"},
+        "single_sequence": {"ms_per_frame": ms1 / K, "launches_per_step": l1, "note": "one sequence, one CUDA graph launch per frame, device-timed"},
+        "retrack_fraction": float(recs["retrack"].mean()), "median_tracked": float(np.median(recs["n_tracked"])),
+        "median_features_in": float(np.median(recs["n_features_in"])), "status_nonzero": int((recs["status"] != 0).sum()),
+        "median_step_m": float(np.median(np.hypot(recs["h"][..., 0], recs["h"][..., 1]))), "expected_step_m": 2.5,
+        "median_dtheta_rad": float(np.median(np.arctan2(recs["R"][..., 2], recs["R"][..., 0]))), "expected_dtheta_rad": 0.025,
+        "e2e_status_nonzero": int((e2e_last["status"] != 0).sum()),
+    })
+    if cpu is not None:
+        out["cpu_baseline"] = {k: v for k, v in cpu.items() if k != "outs"}
+    if parity is not None:
+        out["parity_sample"] = parity
+    return out
+
+
+# ---- configs[4] and the single-stage legs ------------------------------------------------------------------------------
+def leg_stress(ctx):
+    """BASELINE configs[4]: 2000^2 Cartesian grid, 10 k SSC-selected features, 4-level KLT -> tracks/s (tools/klt_stress.py)."""
+    import cv2
+    from radarslampy_b200 import _ffi, synthetic as S
+    N = 2000
+    cfg = _ffi.default_config()
+    cfg.range_bins, cfg.downsample = N + 1, 2
+    cfg.raw_width = cfg.meta_bytes + cfg.range_bins
+    cfg.max_frames, cfg.max_pairs, cfg.max_features = 2, 1, 2048
+    fe = _ffi.RadarFE(cfg, device=ctx["local_rank"])
+    a, b = S.dense_scene(5, n=N), S.dense_scene(5, shift=(1.7, -0.9), n=N)
+    fa, fb = fe.frame_from_cart(a), fe.frame_from_cart(b)
+    cand, n = fe.detect(fa, -0.01, cap=200000)
+    fe.ssc(cand, 10000, 0.1, N, N)
+    t0 = time.perf_counter()
+    sel = fe.ssc(cand, 10000, 0.1, N, N)
+    t_ssc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fe.detect(fa, -0.01, cap=200000)
+    t_det = time.perf_counter() - t0
+    pts = np.ascontiguousarray(cand[sel][:, [1, 0]], np.float32)
+    fe.klt(fa, fb, pts, apply_err_gate=True)
+    reps = 20
+    t0 = time.perf_counter()
+    fe.timer_start()
+    for _ in range(reps):
+        nxt, st, err = fe.klt(fa, fb, pts, apply_err_gate=True)
+    ms_dev = fe.timer_stop_ms() / reps
+    dt = (time.perf_counter() - t0) / reps
+    u8a, u8b = fa.download(1), fb.download(1)
+    cv2.setNumThreads(0)
+    t0 = time.perf_counter()
+    cv_nxt, cv_st, _ = cv2.calcOpticalFlowPyrLK(u8a, u8b, pts, None, winSize=(15, 15), maxLevel=3, criteria=(3, 10, 0.03))
+    dt_cv = time.perf_counter() - t0
+    g = (st.ravel() > 0) & (cv_st.ravel() > 0)
+    K = len(pts)
+    fe.close()
+    return {"workload": "BASELINE configs[4]: dense 2000^2 Cartesian grid (60 k Gaussian scatterers + speckle), SSC -> 10 k features, KLT 15x15 x 4 levels",
+            "features": K, "candidates": int(n), "value": K / (ms_dev * 1e-3), "unit": "tracks/s", "klt_ms_device": ms_dev,
+            "e2e": {"value": K / dt, "unit": "tracks/s", "note": "rf_klt with host points in / host results out (H2D + kernel + D2H per call)",
+                    "h2d_bytes_per_step": K * 8, "d2h_bytes_per_step": K * 13},
+            "ssc_ms": 1e3 * t_ssc, "detect_ms": 1e3 * t_det, "tracked_fraction": float(st.mean()),
+            "cpu_baseline": {"value": K / dt_cv, "unit": "tracks/s", "cores": cv2.getNumThreads(), "kind": "port",
+                             "sample": "the same 10 k points through cv2.calcOpticalFlowPyrLK once, OpenCV's own thread pool"},
+            "parity_sample": {"status_equal": int((st.ravel() == cv_st.ravel()).sum()), "of": K,
+                              "max_abs_dpx": float(np.abs(nxt[g] - cv_nxt.reshape(-1, 2)[g]).max()) if g.any() else None, "tolerance_px": 0.02}}
+
+
+def leg_detect_ssc(ctx, raw_long):
+    """a9 / a10 on the device: first-frame detection of 64 sequences in one reset (scan -> pyramid -> response -> NMS ->
+    candidate sort -> SSC bisection -> append), no host synchronisation; and the single-frame host-API path."""
+    from radarslampy_b200 import _ffi
+    args, rb = ctx["args"], ctx["rb"]
+    cfg = _fe_config(args, rb, 2, 2, 320)
+    fe = _ffi.RadarFE(cfg, device=ctx["local_rank"])
+    S = min(64, len(raw_long))
+    r = fe.new_sequences(S, S)
+    r.upload(0, raw_long[:S])
+    r.reset(0, 1)
+    fe.sync()
+    reps = 5
+    fe.timer_start()
+    for _ in range(reps):
+        r.reset(0, 1)
+    ms = fe.timer_stop_ms() / reps
+    rec = r.results(0)
+    r.close()
+    frame, cart = fe.polar_to_cart(raw=raw_long[0])
+    fe.detect(frame, -0.01)
+    t0 = time.perf_counter()
+    cand, n = fe.detect(frame, -0.01)
+    t_det = time.perf_counter() - t0
+    fe.ssc(cand, 200, 0.1, fe.n, fe.n)
+    t0 = time.perf_counter()
+    sel = fe.ssc(cand, 200, 0.1, fe.n, fe.n)
+    t_ssc = time.perf_counter() - t0
+    fe.close()
+    return {"workload": f"first-frame detection of {S} sequences in one rf_seq reset (scan -> u8 pyramid + f32 image, min-eigenvalue response, 3x3 NMS, "
+                        f"candidate sort, SSC bisection to 200 +- 10 %, append), device-timed; single frame through rf_detect / rf_ssc (host arrays)",
+            "value": S / (ms * 1e-3), "unit": "frames/s", "ms_per_frame_batched": ms / S, "frames": S,
+            "median_features": float(np.median(rec["n_features_out"])), "median_candidates": float(np.median(rec["n_candidates"])),
+            "single_frame": {"detect_ms": 1e3 * t_det, "ssc_ms": 1e3 * t_ssc, "candidates": int(n), "selected": int(len(sel))}}
+
+
+def leg_fmt(ctx, raw_np):
+    """N1: FMT rotation prior of every consecutive pair of the resident scans (rf_batch_fmt)."""
+    from radarslampy_b200 import _ffi
+    args, rb = ctx["args"], ctx["rb"]
+    F = min(len(raw_np), 256)
+    cfg = _fe_config(args, rb, F, F - 1, 64)
+    fe = _ffi.RadarFE(cfg, device=ctx["local_rank"])
+    b = fe.new_batch()
+    pairs = np.stack([np.arange(F - 1), np.arange(1, F)], 1).astype(np.int32)
+    b.upload(raw_np[:F], pairs, np.zeros((F - 1, 64, 2), np.float32), np.zeros(F - 1, np.int32))
+    clip = int(87.5 / (2 * args.res))
+    b.fmt_rotation(10, clip)
+    reps = 5
+    n0 = fe.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ang, sc, resp, sh = b.fmt_rotation(10, clip)
+    dt = (time.perf_counter() - t0) / reps
+    launches = (fe.launch_count() - n0) // reps
+    b.close()
+    fe.close()
+    return {"workload": f"FMT rotation prior (Tracker.py:62-63, FMT.py:13-90) of {F - 1} consecutive pairs from the resident u8 scans, synchronous call incl. D2H",
+            "value": (F - 1) / dt, "unit": "pairs/s", "ms_per_batch": 1e3 * dt, "launches_per_batch": int(launches),
+            "median_angle_rad": float(np.median(ang)), "note": "the reference's prior is taken between log-polar images of the raw polar scans"}
+
+
+def leg_peaks(ctx, raw_np):
+    """a12: getPointCloudPolarInd on one scan (host f32 polar in, int64 index pairs out)."""
+    from radarslampy_b200 import _ffi
+    args, rb = ctx["args"], ctx["rb"]
+    cfg = _fe_config(args, rb, 2, 1, 64)
+    fe = _ffi.RadarFE(cfg, device=ctx["local_rank"])
+    polar = fe.extract_polar(raw_np[0])[0]
+    fe.polar_peaks(polar)
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pk = fe.polar_peaks(polar)
+    dt = (time.perf_counter() - t0) / reps
+    fe.close()
+    return {"workload": f"getPointCloudPolarInd (getPointCloud.py:10-60) on one {polar.shape[0]} x {polar.shape[1]} f32 polar scan, host in / host out",
+            "value": 1.0 / dt, "unit": "scans/s", "ms_per_scan": 1e3 * dt, "peaks": int(len(pk))}
 
 
 if __name__ == "__main__":

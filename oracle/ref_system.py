@@ -7,7 +7,6 @@ import numpy as np
 
 from . import ref_pipeline as P
 
-RES = 0.0432 * 2
 N_FEATURES_BEFORE_RETRACK = 60
 ROT_THRESHOLD, TRANS_THRESHOLD_SQ = 0.2, 4.0
 
@@ -42,13 +41,15 @@ class _KF:
         return (T[:2, :2] @ self.pruned_und.T + T[:2, 2:]).T
 
 
-def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0), with_mds=True):
+def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0), with_mds=True, range_res_m=0.0432):
     """with_mds=False: the pose chain without motion compensation, T_wj = prev_pose @ [R, h] (RawROAMSystem.py:201,
     BASELINE configs[1]); the keyframe points are then undistorted with zero velocity."""
     scans = list(raw_scans)
+    RES = 2 * range_res_m                                            # RANGE_RESOLUTION_CART_M (parseData.py:13-15)
+    thr_px = 0.5 / RES                                               # outlierRejection.py:29-31
     init_pose = np.asarray(init_pose, np.float64)
     prev_pose = _pose_T(init_pose)
-    prev_cart = P.polar_to_cart(P.extract_polar(scans[0]))
+    prev_cart = P.polar_to_cart(P.extract_polar(scans[0], range_res_m))
     blob = detect(prev_cart, np.empty((0, 2), np.float32))
     center = np.array(prev_cart.shape) / 2
     metric = (blob - center) * RES
@@ -57,10 +58,10 @@ def run_odometry(raw_scans, detect, init_pose=(0.0, 0.0, 0.0), with_mds=True):
     possible = _KF(init_pose, metric, np.zeros(3))
     out = {"R": [], "h": [], "mds_x": [], "n_tracked": [], "n_features_in": [], "poses": [init_pose], "retrack": []}
     for k in range(1, len(scans)):
-        curr_cart = P.polar_to_cart(P.extract_polar(scans[k]))
+        curr_cart = P.polar_to_cart(P.extract_polar(scans[k], range_res_m))
         out["n_features_in"].append(len(blob))
         g_new, g_old, b_new, b_old, status = P.tracked_points_klt(prev_cart, curr_cart, blob)
-        good_old, good_new, mask = P.reject_outliers(g_old, g_new)
+        good_old, good_new, mask = P.reject_outliers(g_old, g_new, thr_px)
         corr = status.copy()
         corr[np.arange(len(corr))[corr.flatten().astype(bool)]] &= mask[:, np.newaxis].astype(corr.dtype)
         old_kf.prune(corr)

@@ -30,6 +30,14 @@ struct DetectWs {
     void* base; size_t bytes;
 };
 
+// CTAs per problem for the tile-walking kernels of a batch of S problems (some of which may be switched off by a device
+// flag): enough to fill the machine 16 deep when every problem is live, never fewer than 64 nor more than the tiles
+static inline int rf_tile_workers(const rf_handle* h, int ntiles, int S) {
+    int w = (h->sm_count * 16 + S - 1) / (S > 0 ? S : 1);
+    w = w < 64 ? 64 : w;
+    return w > ntiles ? ntiles : w;
+}
+
 size_t rf_detect_ws_bytes(int S, int rows, int cols, unsigned key_cap, unsigned ssc_cap, unsigned cells_cap, bool with_resp);
 // carve a workspace out of device memory `base` (rf_detect_ws_bytes); grid cells are initialised by rf_detect_ws_init
 DetectWs rf_detect_ws_carve(void* base, int S, int rows, int cols, unsigned key_cap, unsigned ssc_cap, unsigned cells_cap, bool with_resp);

@@ -45,13 +45,17 @@
 __global__ void __launch_bounds__(256)
 k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0, float k1, float* __restrict__ resp_base,
           size_t resp_stride, const int32_t* __restrict__ flags) {
-    if (flags && !flags[blockIdx.z]) return;
-    const float* __restrict__ img = img_base + (size_t)blockIdx.z * img_stride;
-    float* __restrict__ resp = resp_base + (size_t)blockIdx.z * resp_stride;
+    // grid = (tile workers, problems): a CTA walks the tiles of its problem, so the un-flagged problems of a lock-step
+    // batch cost gridDim.x empty CTAs each instead of one per tile
+    if (flags && !flags[blockIdx.y]) return;
+    const float* __restrict__ img = img_base + (size_t)blockIdx.y * img_stride;
+    float* __restrict__ resp = resp_base + (size_t)blockIdx.y * resp_stride;
     __shared__ float tile[ME_TH + 4][ME_TW + 4 + 1];
     __shared__ float gxx[ME_TH + 2][ME_TW + 2 + 1], gxy[ME_TH + 2][ME_TW + 2 + 1], gyy[ME_TH + 2][ME_TW + 2 + 1];
-    const int ox = blockIdx.x * ME_TW, oy = blockIdx.y * ME_TH;
+    const int tiles_x = (n + ME_TW - 1) / ME_TW, ntiles = tiles_x * ((n + ME_TH - 1) / ME_TH);
     const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int ox = (t % tiles_x) * ME_TW, oy = (t / tiles_x) * ME_TH;
     // tile position (r, c) holds img at clamp-reflected (oy - 2 + r, ox - 2 + c); positions are looked up
     // through T() so gradients at reflected locations read the taps a full-image Sobel would read
     for (int i = tid; i < (ME_TH + 4) * (ME_TW + 4); i += 256) {
@@ -100,6 +104,8 @@ k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0
         const float d = __fsub_rn(a, cc);
         resp[(size_t)y * n + x] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
     }
+    __syncthreads();           // the next tile overwrites the staging arrays
+    }
 }
 
 // maximum of a non-negative response map (bit pattern order == value order for floats >= 0); blockIdx.y = problem
@@ -130,24 +136,27 @@ __global__ void __launch_bounds__(256)
 k_nms_select(const float* __restrict__ resp_base, size_t resp_stride, int rows, int cols, float thr_abs, double thr_rel,
              const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ keys_base, unsigned cap,
              unsigned* __restrict__ count, const int32_t* __restrict__ flags) {
-    const int p = blockIdx.z;
+    const int p = blockIdx.y;      // grid = (tile workers, problems), see k_min_eig
     if (flags && !flags[p]) return;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) return;
     const float* __restrict__ resp = resp_base + (size_t)p * resp_stride;
     const float thr = thr_rel != 0.0 ? (float)((double)__uint_as_float(maxbits[p]) * thr_rel) : thr_abs;
-    const float v = __ldg(resp + (size_t)y * cols + x);
-    if (!(v > thr)) return;
-    float mx = v;
+    const int tiles_x = (cols + 31) / 32, ntiles = tiles_x * ((rows + 7) / 8);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int x = (t % tiles_x) * 32 + threadIdx.x, y = (t / tiles_x) * 8 + threadIdx.y;
+        if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) continue;
+        const float v = __ldg(resp + (size_t)y * cols + x);
+        if (!(v > thr)) continue;
+        float mx = v;
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy)
+        for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) mx = fmaxf(mx, __ldg(resp + (size_t)(y + dy) * cols + (x + dx)));
-    if (v != mx) return;
-    const unsigned slot = atomicAdd(count + p, 1u);
-    if (slot < cap) {
-        const unsigned idx = (unsigned)y * (unsigned)cols + (unsigned)x;
-        keys_base[(size_t)p * cap + slot] = ((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned long long)(~idx);
+            for (int dx = -1; dx <= 1; ++dx) mx = fmaxf(mx, __ldg(resp + (size_t)(y + dy) * cols + (x + dx)));
+        if (v != mx) continue;
+        const unsigned slot = atomicAdd(count + p, 1u);
+        if (slot < cap) {
+            const unsigned idx = (unsigned)y * (unsigned)cols + (unsigned)x;
+            keys_base[(size_t)p * cap + slot] = ((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned long long)(~idx);
+        }
     }
 }
 
@@ -513,7 +522,8 @@ int rf_detect_prepare(rf_handle* h) {
 int rf_launch_min_eig(rf_handle* h, const float* d_img, size_t img_stride, int n, float* d_resp, size_t resp_stride, int S,
                       const int32_t* d_flags) {
     const double scale = 1.0 / ((double)(1 << 2) * 3.0);  // ksize 3, blockSize 3, f32 input
-    dim3 blk(32, 8), grd((n + ME_TW - 1) / ME_TW, (n + ME_TH - 1) / ME_TH, S);
+    const int ntiles = ((n + ME_TW - 1) / ME_TW) * ((n + ME_TH - 1) / ME_TH);
+    dim3 blk(32, 8), grd(rf_tile_workers(h, ntiles, S), S);
     k_min_eig<<<grd, blk, 0, h->stream>>>(d_img, img_stride, n, (float)(2.0 * scale), (float)(1.0 * scale), d_resp, resp_stride, d_flags);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
@@ -531,7 +541,7 @@ int rf_launch_select_sorted(rf_handle* h, const DetectWs& ws, const float* d_res
         RF_CHECK_LAUNCH(h);
         rel = (double)(-threshold);
     }
-    dim3 blk(32, 8), grd((ws.cols + 31) / 32, (ws.rows + 7) / 8, S);
+    dim3 blk(32, 8), grd(rf_tile_workers(h, ((ws.cols + 31) / 32) * ((ws.rows + 7) / 8), S), S);
     k_nms_select<<<grd, blk, 0, h->stream>>>(d_resp, resp_stride, ws.rows, ws.cols, threshold, rel, ws.maxbits, ws.keys, ws.key_cap,
                                              ws.count, d_flags);
     RF_CHECK_LAUNCH(h);

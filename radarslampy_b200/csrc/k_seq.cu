@@ -68,17 +68,19 @@ __global__ void __launch_bounds__(256)
 k_seq_cart_f32(const uint8_t* __restrict__ arena, size_t frame_stride, const SeqDesc* __restrict__ desc, int row_pitch, int A,
                int W, const uint32_t* __restrict__ map, int n, float* __restrict__ cart, size_t cart_stride,
                const int32_t* __restrict__ flags) {
-    const int s_ = blockIdx.z;
+    const int s_ = blockIdx.y;     // grid = (tile workers, sequences): un-flagged sequences cost gridDim.x empty CTAs, not one per tile
     if (!flags[s_]) return;
     __shared__ float lut[256];
     const int tid = threadIdx.y * 16 + threadIdx.x;
     lut[tid] = __fdiv_rn((float)tid, 255.0f);  // parseData.py:43  u8 -> f32 / 255. (IEEE division)
     __syncthreads();
-    const int x4 = blockIdx.x * 16 + threadIdx.x;
-    const int y = blockIdx.y * 16 + threadIdx.y;
     const int n4 = n >> 2;
-    if (x4 >= n4 || y >= n) return;
+    const int tiles_x = (n4 + 15) / 16, ntiles = tiles_x * ((n + 15) / 16);
     const uint8_t* s = arena + (size_t)(desc->base + s_ * desc->stride) * frame_stride;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int x4 = (t % tiles_x) * 16 + threadIdx.x;
+    const int y = (t / tiles_x) * 16 + threadIdx.y;
+    if (x4 >= n4 || y >= n) continue;
     const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(map) + (size_t)y * n4 + x4);
     const uint32_t mm[4] = {m4.x, m4.y, m4.z, m4.w};
     float o[4];
@@ -107,6 +109,7 @@ k_seq_cart_f32(const uint8_t* __restrict__ arena, size_t frame_stride, const Seq
         o[k] = acc;
     }
     reinterpret_cast<float4*>(cart + (size_t)s_ * cart_stride + (size_t)y * n)[x4] = make_float4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -496,7 +499,7 @@ static int seq_enqueue_detect(rf_handle* h, rf_seq* q) {
     const rf_config& c = h->cfg;
     int rc;
     const size_t n2 = (size_t)h->n * h->n;
-    dim3 blk(16, 16), grd(((h->n >> 2) + 15) / 16, (h->n + 15) / 16, q->S);
+    dim3 blk(16, 16), grd(rf_tile_workers(h, (((h->n >> 2) + 15) / 16) * ((h->n + 15) / 16), q->S), q->S);
     k_seq_cart_f32<<<grd, blk, 0, h->stream>>>(q->d_arena, q->frame_stride, q->d_desc, q->raw_pitch, c.azimuths, c.range_bins, h->map,
                                                h->n, q->d_cart, n2, q->d_flags);
     RF_CHECK_LAUNCH(h);

@@ -120,50 +120,67 @@ __device__ __forceinline__ double wrap_pi(double th) {
 
 struct MdsEval { double cost; double g[6]; double H[21]; };
 
-// residual, gradient J^T r and Gauss-Newton matrix J^T J at x (warp-reduced; all lanes get the result)
+#define MDS_THREADS 128
+#define MDS_WARPS (MDS_THREADS / 32)
+#define MDS_SMEM_PTS 256     // problems with at most this many points keep them in shared memory
+
+// residual, gradient J^T r and Gauss-Newton matrix J^T J at x, reduced over the block (every thread gets the same
+// result: per-thread partial sums -> warp shuffles -> the MDS_WARPS partials added in warp order by every thread)
 __device__ void mds_eval(const double* __restrict__ pts, int N, const double x[6], const double T0inv[6], double th0,
-                         const MdsArgs& a, bool want_deriv, MdsEval& o, int lane) {
+                         const MdsArgs& a, MdsEval& o, double* red, int tid) {
     const double c = cos(x[5]), s = sin(x[5]);
     const double wp0 = 1.0 / a.sig_p0, wp1 = 1.0 / a.sig_p1;
-    double cost = 0, g[6] = {0, 0, 0, 0, 0, 0}, H[21];
+    double v[28];              // cost | g[6] | H[21]
 #pragma unroll
-    for (int i = 0; i < 21; ++i) H[i] = 0;
-    for (int i = lane; i < N; i += 32) {
+    for (int i = 0; i < 28; ++i) v[i] = 0;
+    for (int i = tid; i < N; i += MDS_THREADS) {
         const double pwx = pts[5 * i], pwy = pts[5 * i + 1], px = pts[5 * i + 2], py = pts[5 * i + 3], dT = pts[5 * i + 4];
         const double th = x[2] * dT;
-        const double ct = cos(th), st = sin(th);
+        double st, ct;
+        sincos(th, &st, &ct);
         const double qx = ct * px - st * py + x[0] * dT, qy = st * px + ct * py + x[1] * dT;
         const double dx = pwx - x[3], dy = pwy - x[4];
         const double mx = c * dx + s * dy, my = -s * dx + c * dy;
         const double ex = mx - qx, ey = my - qy;
         const double ux = ex * ex * 0.5 + 1.0, uy = ey * ey * 0.5 + 1.0;
         const double rx = wp0 * log(ux), ry = wp1 * log(uy);
-        cost += rx * rx + ry * ry;
-        if (want_deriv) {
-            const double kx = wp0 * ex / ux, ky = wp1 * ey / uy;   // d rho / d e
-            // d e / d x
-            const double dqx_dvt = dT * (-st * px - ct * py), dqy_dvt = dT * (ct * px - st * py);
-            double Jx[6] = {-dT, 0.0, -dqx_dvt, -c, -s, my};
-            double Jy[6] = {0.0, -dT, -dqy_dvt, s, -c, -mx};
+        v[0] += rx * rx + ry * ry;
+        const double kx = wp0 * ex / ux, ky = wp1 * ey / uy;   // d rho / d e
+        // d e / d x
+        const double dqx_dvt = dT * (-st * px - ct * py), dqy_dvt = dT * (ct * px - st * py);
+        double Jx[6] = {-dT, 0.0, -dqx_dvt, -c, -s, my};
+        double Jy[6] = {0.0, -dT, -dqy_dvt, s, -c, -mx};
 #pragma unroll
-            for (int k = 0; k < 6; ++k) { Jx[k] *= kx; Jy[k] *= ky; }
-            int idx = 0;
+        for (int k = 0; k < 6; ++k) { Jx[k] *= kx; Jy[k] *= ky; }
+        int idx = 7;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) {
-                g[r] += Jx[r] * rx + Jy[r] * ry;
+        for (int r = 0; r < 6; ++r) {
+            v[1 + r] += Jx[r] * rx + Jy[r] * ry;
 #pragma unroll
-                for (int cc = r; cc < 6; ++cc) H[idx++] += Jx[r] * Jx[cc] + Jy[r] * Jy[cc];
-            }
+            for (int cc = r; cc < 6; ++cc) v[idx++] += Jx[r] * Jx[cc] + Jy[r] * Jy[cc];
         }
     }
-    cost = warp_sum_d(cost);
-    if (want_deriv) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) g[k] = warp_sum_d(g[k]);
+    for (int k = 0; k < 28; ++k) v[k] = warp_sum_d(v[k]);
+    if ((tid & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 21; ++k) H[k] = warp_sum_d(H[k]);
+        for (int k = 0; k < 28; ++k) red[(tid >> 5) * 28 + k] = v[k];
     }
-    // velocity-consistency residuals (3 rows), identical on every lane
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 28; ++k) {
+        double t = red[k];
+#pragma unroll
+        for (int w = 1; w < MDS_WARPS; ++w) t += red[w * 28 + k];
+        v[k] = t;
+    }
+    __syncthreads();            // `red` is free for the next evaluation
+    double cost = v[0], g[6], H[21];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = v[1 + k];
+#pragma unroll
+    for (int k = 0; k < 21; ++k) H[k] = v[7 + k];
+    // velocity-consistency residuals (3 rows), identical on every thread
     const double tx = x[3] - T0inv[4], ty = x[4] - T0inv[5];                // t - t0
     const double relx = T0inv[0] * tx + T0inv[1] * ty, rely = T0inv[2] * tx + T0inv[3] * ty;  // R0^T (t - t0)
     const double relth = atan2(sin(x[5] - th0), cos(x[5] - th0));           // arctan2 of the relative rotation
@@ -171,7 +188,7 @@ __device__ void mds_eval(const double* __restrict__ pts, int N, const double x[6
     const double ip = 1.0 / a.period;
     const double r0 = wv0 * (x[0] - relx * ip), r1 = wv1 * (x[1] - rely * ip), r2 = wv2 * wrap_pi(x[2] - relth * ip);
     cost += r0 * r0 + r1 * r1 + r2 * r2;
-    if (want_deriv) {
+    {
         double J0[6] = {wv0, 0, 0, -wv0 * T0inv[0] * ip, -wv0 * T0inv[1] * ip, 0};
         double J1[6] = {0, wv1, 0, -wv1 * T0inv[2] * ip, -wv1 * T0inv[3] * ip, 0};
         double J2[6] = {0, 0, wv2, 0, 0, -wv2 * ip};
@@ -211,11 +228,17 @@ __device__ bool solve6(const double Hu[21], const double D[6], double lam, const
     return true;
 }
 
-__global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
-    const int lane = threadIdx.x;
+// One CTA of MDS_THREADS threads per problem: the points are spread over the threads (one or two each at the usual 60-200
+// inliers), the 6x6 solve and the step control run redundantly on every thread from block-reduced sums.
+__global__ void __launch_bounds__(MDS_THREADS) k_mds(const MdsArgs a) {
+    __shared__ double s_pts[MDS_SMEM_PTS * 5];
+    __shared__ double s_red[MDS_WARPS * 28];
+    __shared__ int s_N;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int p = blockIdx.x;
     if (p >= a.P) return;
-    double* pts = a.scratch + (size_t)p * a.Nstride * 5;
+    double* gpts = a.scratch + (size_t)p * a.Nstride * 5;
+    double* pts = gpts;
     double T0[9], Tw[9];
     int N = 0;
     if (a.p_w) {
@@ -225,7 +248,8 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
         for (int k = 0; k < 9; ++k) { T0[k] = a.T_wj0[(size_t)p * 9 + k]; Tw[k] = a.T_wj[(size_t)p * 9 + k]; }
         const double* pw = a.p_w + (size_t)p * a.Nstride * 2;
         const double* pj = a.p_jt + (size_t)p * a.Nstride * 2;
-        for (int i = lane; i < N; i += 32) {
+        if (N <= MDS_SMEM_PTS) pts = s_pts;
+        for (int i = tid; i < N; i += MDS_THREADS) {
             const double x = pj[2 * i], y = pj[2 * i + 1];
             pts[5 * i] = pw[2 * i]; pts[5 * i + 1] = pw[2 * i + 1]; pts[5 * i + 2] = x; pts[5 * i + 3] = y;
             pts[5 * i + 4] = a.period * atan2(-y, -x) / (2.0 * M_PI);   // compute_time_deltas :107-124
@@ -253,7 +277,9 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
             und = a.kf_und + (size_t)p * a.Kstride * 2; gsrc = a.good_src + (size_t)p * a.Kstride;
             kx = a.kf_pose[3 * p]; ky = a.kf_pose[3 * p + 1]; kc = cos(a.kf_pose[3 * p + 2]); ks = sin(a.kf_pose[3 * p + 2]);
         }
-        // order-preserving compaction of the inliers
+        // order-preserving compaction of the inliers (warp 0; straight into shared memory when they fit)
+        if (K <= MDS_SMEM_PTS) pts = s_pts;
+        if (tid < 32)
         for (int i0 = 0; i0 < K; i0 += 32) {
             const int i = i0 + lane;
             const bool ok = i < K && m[i];
@@ -273,8 +299,15 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
             }
             N += __popc(bm);
         }
+        if (tid == 0) s_N = N;
+        __syncthreads();
+        N = s_N;
+        if (pts != s_pts && N <= MDS_SMEM_PTS) {          // K > MDS_SMEM_PTS candidates but few inliers
+            for (int i = tid; i < 5 * N; i += MDS_THREADS) s_pts[i] = gpts[i];
+            pts = s_pts;
+        }
     }
-    __syncwarp();
+    __syncthreads();
     // T_wj0^{-1} = [R0^T, -R0^T t0]; keep R0^T (4) and t0 (2); theta0
     const double T0inv[6] = {T0[0], T0[3], T0[1], T0[4], T0[2], T0[5]};   // R0^T row-major, then t0
     const double th0 = atan2(T0[3], T0[0]);
@@ -289,7 +322,7 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
         x[3] = Tw[2]; x[4] = Tw[5]; x[5] = atan2(Tw[3], Tw[0]);
     }
     MdsEval ev;
-    mds_eval(pts, N, x, T0inv, th0, a, true, ev, lane);
+    mds_eval(pts, N, x, T0inv, th0, a, ev, s_red, tid);
     double lam = 1e-3;
     int it = 0;
     for (; it < a.max_iters; ++it) {
@@ -306,12 +339,12 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
             double xn[6];
             stepmax = 0;
             for (int k = 0; k < 6; ++k) { xn[k] = x[k] + dx[k]; stepmax = fmax(stepmax, fabs(dx[k]) / (fabs(x[k]) + 1e-6)); }
-            MdsEval en;
-            mds_eval(pts, N, xn, T0inv, th0, a, false, en, lane);
+            MdsEval en;                      // with derivatives: an accepted trial point is the next iterate
+            mds_eval(pts, N, xn, T0inv, th0, a, en, s_red, tid);
             if (en.cost <= ev.cost) {
                 const double dec = ev.cost - en.cost;
                 for (int k = 0; k < 6; ++k) x[k] = xn[k];
-                mds_eval(pts, N, x, T0inv, th0, a, true, ev, lane);
+                ev = en;
                 lam = fmax(lam * 0.2, 1e-15);
                 accepted = true;
                 if (dec <= 1e-17 * fmax(ev.cost, 1e-300) && stepmax < 1e-10) stepmax = 0;  // converged
@@ -322,7 +355,7 @@ __global__ void __launch_bounds__(32) k_mds(const MdsArgs a) {
         }
         if (!accepted || stepmax < 1e-13) { ++it; break; }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         for (int k = 0; k < 6; ++k) a.x_out[(size_t)p * 6 + k] = x[k];
         if (a.iters) a.iters[p] = it;
         if (a.cost) a.cost[p] = 0.5 * ev.cost;
@@ -365,7 +398,7 @@ int rf_launch_mds_fused(rf_handle* h, const float* d_old, const float* d_new, co
     a.P = P; a.counts = d_counts; a.Nstride = Kstride; a.px_old = d_old; a.px_new = d_new; a.mask = d_mask;
     a.mask_stride = mask_stride; a.Kstride = Kstride; a.kab_R = d_R; a.kab_h = d_h; a.prev_pose = d_prev_pose;
     a.x_out = d_x; a.iters = d_iters; a.cost = nullptr; a.scratch = d_scratch;
-    k_mds<<<P, 32, 0, h->stream>>>(a);
+    k_mds<<<P, MDS_THREADS, 0, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
@@ -380,7 +413,7 @@ int rf_launch_mds_chain(rf_handle* h, const float* d_old, const float* d_new, co
     a.mask_stride = mask_stride; a.Kstride = Kstride; a.kab_R = d_R; a.kab_h = d_h; a.prev_pose = d_prev_pose;
     a.kf_und = d_kf_und; a.kf_pose = d_kf_pose; a.good_src = d_good_src;
     a.x_out = d_x; a.iters = d_iters; a.cost = nullptr; a.scratch = d_scratch;
-    k_mds<<<P, 32, 0, h->stream>>>(a);
+    k_mds<<<P, MDS_THREADS, 0, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
@@ -437,7 +470,7 @@ int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const d
     if (period > 0) a.period = period;
     a.P = 1; a.p_w = dpw; a.p_jt = dpj; a.counts = dc; a.Nstride = Ns; a.T_wj0 = dT0; a.T_wj = dTw;
     a.x_out = dx; a.iters = dit; a.cost = dcost; a.scratch = dsc;
-    k_mds<<<1, 32, 0, h->stream>>>(a);
+    k_mds<<<1, MDS_THREADS, 0, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
     double xo[7]; int32_t ito;
     RF_CUDA(h, cudaMemcpyAsync(xo, dx, 56, cudaMemcpyDeviceToHost, h->stream));

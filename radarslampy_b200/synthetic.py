@@ -131,3 +131,49 @@ def sequence_pairs(n_frames, world, poses, res_m, range_bins, k=200, max_feature
         counts[p] = len(f)
         feats[p, :len(f)] = f
     return pair_idx, feats, counts
+
+
+def _render_job(job):
+    seed, n_scat, extent, k, first, res_m, v, w, distort = job
+    world = World(n_scat, extent, seed)
+    pose = twist_pose(first + k, v, w)
+    return render_scan(world, pose, first + k, res_m=res_m, distort=(v, w) if distort else None)
+
+
+def make_sequence_parallel(n_frames, res_m=0.0438, seed=1234, v=10.0, w=0.10, first=0, out=None, distort=False, workers=None,
+                           n_scatterers=4000, extent_m=250.0):
+    """make_sequence over a process pool (identical output: every frame is rendered from its own seeds).  Call it
+    BEFORE the CUDA context exists (fork)."""
+    import multiprocessing as mp
+    import os
+    workers = max(1, min(workers or (os.cpu_count() or 1), n_frames))
+    raw = out if out is not None else np.empty((n_frames, A, RAW_WIDTH), np.uint8)
+    poses = np.stack([twist_pose(first + k, v, w) for k in range(n_frames)]) if n_frames else np.zeros((0, 3))
+    jobs = [(seed, n_scatterers, extent_m, k, first, res_m, v, w, distort) for k in range(n_frames)]
+    if workers == 1:
+        for k, j in enumerate(jobs):
+            raw[k] = _render_job(j)
+        return raw, poses
+    with mp.get_context("fork").Pool(workers) as pool:
+        for k, scan in enumerate(pool.imap(_render_job, jobs, chunksize=max(1, n_frames // (4 * workers)))):
+            raw[k] = scan
+    return raw, poses
+
+
+def dense_scene(seed, shift=(0.0, 0.0), n=2000, n_points=60000):
+    """BASELINE configs[4] input: dense point-scatterer scene on an n x n Cartesian grid (Gaussian blobs, sigma 1.5 px)
+    plus weak speckle; `shift` moves every scatterer (the second frame of a tracking pair).  f32 in [0, 1]."""
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(8, n - 8, (n_points, 2))
+    amp = rng.uniform(0.3, 1.0, len(pts))
+    img = np.zeros((n, n), np.float32)
+    x, y = pts[:, 0] + shift[0], pts[:, 1] + shift[1]
+    ix, iy = np.floor(x).astype(int), np.floor(y).astype(int)
+    for dy in range(-4, 6):
+        for dx in range(-4, 6):
+            xx, yy = ix + dx, iy + dy
+            ok = (xx >= 0) & (xx < n) & (yy >= 0) & (yy < n)
+            w = amp * np.exp(-((xx - x) ** 2 + (yy - y) ** 2) / (2 * 1.5 ** 2))
+            np.add.at(img, (yy[ok], xx[ok]), w[ok].astype(np.float32))
+    img += np.random.default_rng(99).exponential(0.01, img.shape).astype(np.float32)
+    return np.clip(img, 0, 1).astype(np.float32)

@@ -10,21 +10,8 @@ N = 2000
 
 
 def _scene(seed, shift=(0.0, 0.0)):
-    """Dense point-scatterer scene rendered on the 2000^2 grid (Gaussian blobs, sigma 1.5 px) + weak speckle."""
-    rng = np.random.default_rng(seed)
-    pts = rng.uniform(8, N - 8, (60000, 2))
-    amp = rng.uniform(0.3, 1.0, len(pts))
-    img = np.zeros((N, N), np.float32)
-    x, y = pts[:, 0] + shift[0], pts[:, 1] + shift[1]
-    ix, iy = np.floor(x).astype(int), np.floor(y).astype(int)
-    for dy in range(-4, 6):
-        for dx in range(-4, 6):
-            xx, yy = ix + dx, iy + dy
-            ok = (xx >= 0) & (xx < N) & (yy >= 0) & (yy < N)
-            w = amp * np.exp(-((xx - x) ** 2 + (yy - y) ** 2) / (2 * 1.5 ** 2))
-            np.add.at(img, (yy[ok], xx[ok]), w[ok].astype(np.float32))
-    img += np.random.default_rng(99).exponential(0.01, img.shape).astype(np.float32)
-    return np.clip(img, 0, 1).astype(np.float32)
+    from radarslampy_b200.synthetic import dense_scene
+    return dense_scene(seed, shift, n=N)
 
 
 @pytest.fixture(scope="module")
