@@ -631,7 +631,7 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
 def parity_sample(res, cpu_out, with_mds):
     """GPU batch results of the first pairs against what the cpu_baseline leg computed for the same pairs
     (oracle/ref_pipeline.track_pair: the reference's own cv2 / scipy / networkx / numpy calls)."""
-    n = min(len(cpu_out), len(res))
+    n = min(len(cpu_out), len(res["h"]))
     dm, drad, same = 0.0, 0.0, 0
     for p in range(n):
         h, R, n_in = cpu_out[p]

@@ -131,6 +131,12 @@ RF_API void rf_frame_destroy(rf_handle* h, rf_frame* f);
  * if cart_out != NULL, copies the f32 image [2R, 2R] to the host. */
 RF_API int rf_polar_to_cart(rf_handle* h, const uint8_t* raw, const float* polar, rf_frame* frame,
                      float* cart_out);
+/* convertPolarImageToCartesian(imgPolar, logPolarMode=True): cv2.warpPolar with WARP_POLAR_LOG | WARP_INVERSE_MAP
+ *                                                              parseData.py:100-135 (:131-133)
+ * polar f32 [A, range_bins] (host) -> cart_out f32 [2R, 2R] (host).  Never taken on the reference's live path; matches
+ * cv2 to the tolerance of its vendor logf (1 ulp on the radius -> a different 1/32-pixel sample position for a few pixels
+ * in a thousand). */
+RF_API int rf_polar_to_cart_log(rf_handle* h, const float* polar, float* cart_out);
 /* Build a frame from a caller-supplied f32 Cartesian image [n, n], n == 2R (the path
  * getTrackedPointsKLT takes when handed plain NumPy images). */
 RF_API int rf_frame_from_cart(rf_handle* h, const float* cart, int n, rf_frame* frame);
@@ -174,6 +180,9 @@ RF_API int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, 
 /* static MotionDistortionSolver.undistort                  motionDistortion.py:127-153 */
 RF_API int rf_mds_undistort(rf_handle* h, const double v[3], const double* pts_xy, int N, double period,
                      double* out_xy);
+/* the same with explicit per-point time offsets: undistort(v_j, points, times=...)   motionDistortion.py:135-138 */
+RF_API int rf_mds_undistort_times(rf_handle* h, const double v[3], const double* pts_xy, const double* times, int N,
+                           double* out_xy);
 
 /* ---- a9  ANMS.ssc                                        ANMS.py:5-102 ------------- */
 /* kp [n,3] f64 (row, col, sigma) in caller order -> sel_idx [<= n] in selection order. */
@@ -186,7 +195,24 @@ RF_API int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double tol
  * out [cap,3] f64 (row, col, response).  *n receives the total candidate count.
  * threshold >= 0 is absolute; threshold < 0 means the fraction -threshold of the maximum response
  * (cv2.goodFeaturesToTrack's qualityLevel). */
+/* mode 1: the reference's own detector, determinant-of-Hessian blobs = skimage.feature.blob_doh with the handle's
+ * doh_* parameters (getFeatures.DEFAULT_FEATURE_PARAMS); threshold < 0 selects cfg.doh_threshold.
+ * out [cap,3] f64 (row, col, sigma) — blob_doh's return value.  See rf_detect_doh. */
 RF_API int rf_detect(rf_handle* h, const rf_frame* f, int mode, float threshold, double* out, int cap, int* n);
+/* getFeatures.getBlobsFromCart(cartImage, min_sigma, max_sigma, num_sigma, threshold, method="doh")
+ *                                                           getFeatures.py:22-53
+ * = skimage.feature.blob_doh(img.astype(double), ...) on the frame's f32 Cartesian image: float64 integral image,
+ * box-filter Hessian determinant per sigma of np.linspace(min_sigma, max_sigma, num_sigma) (num_sigma <= 16),
+ * 3x3x3 peak_local_max above `threshold`, blobs ordered by descending response, _prune_blobs(overlap).
+ * out [cap,3] f64 (row, col, sigma), *n = number of blobs.  scikit-image 0.19.2 is not part of the reference tree:
+ * parity with it is UNPINNED; the algorithm and its three implementation-defined points (all-NaN plane of a
+ * zero-size box, order of equal responses, pruning order) are written down in oracle/doh_restate.py. */
+RF_API int rf_detect_doh(rf_handle* h, const rf_frame* f, double min_sigma, double max_sigma, int num_sigma,
+                  double threshold, double overlap, double* out, int cap, int* n);
+/* parity-test hook: the float64 integral image (sigma_index < 0) or the Hessian-determinant plane of one scale
+ * (f64 [2R,2R]) */
+RF_API int rf_doh_response(rf_handle* h, const rf_frame* f, double min_sigma, double max_sigma, int num_sigma,
+                    int sigma_index, double* out);
 /* response map only (f32 [2R,2R]) — used by the parity tests */
 RF_API int rf_corner_response(rf_handle* h, const rf_frame* f, int mode, float* resp);
 /* selection half of rf_detect on a caller-supplied response map (f32 [rows, cols]): interior
@@ -216,6 +242,12 @@ RF_API int rf_fmt_rotation_frames(rf_handle* h, const float* const* frames, int 
 /* The log-polar image itself (stage-level parity): out [h_lp, w_lp] f32; out == NULL only queries the size. */
 RF_API int rf_fmt_log_polar(rf_handle* h, const float* polar, int A, int W, int downsample, int clip_px, float* out,
                      int64_t out_cap, int* h_lp, int* w_lp);
+/* parseData.convertCartesianImageToPolar(imgCart, logPolarMode, shapeHW)                parseData.py:69-97
+ * cv2.warpPolar forward map of a square f32 image [n, n] (host), linear or semi-log radius, INTER_LINEAR with
+ * outliers filled with 0.  rows_out / cols_out <= 0 select cv2's default size (round(n / 2 * pi), round(n / 2));
+ * out [rows, cols] f32 (host); out == NULL only queries the size. */
+RF_API int rf_cart_to_polar(rf_handle* h, const float* cart, int n, int log_mode, int rows_out, int cols_out, float* out,
+                     int64_t out_cap, int* rows, int* cols);
 /* cv2.phaseCorrelate(a, b, cv2.createHanningWindow((cols, rows), CV_32F))   FMT.py:13-33
  * a, b [rows, cols] f32 (host) -> (dx, dy), response. */
 RF_API int rf_phase_correlate(rf_handle* h, const float* a, const float* b, int rows, int cols, double* dx, double* dy,

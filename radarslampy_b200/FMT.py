@@ -1,6 +1,7 @@
 """Drop-in for the reference's FMT.py: Fourier-Mellin rotation prior on libradarfe.so.
 Same names, arguments and return values as FMT.py:13-90; the arithmetic runs in
-rf_fmt_rotation / rf_phase_correlate (csrc/k_fmt.cu).  Plotting helpers are out of scope."""
+rf_fmt_rotation / rf_phase_correlate (csrc/k_fmt.cu).  The plotting helpers (FMT.py:103-165) import matplotlib lazily;
+rotateImg (cv2.warpAffine, only used by those plots) is not provided."""
 from typing import Tuple
 
 import numpy as np
@@ -26,3 +27,26 @@ def getRotationUsingFMT(srcPolarImg: np.ndarray, targetPolarImg: np.ndarray, dow
     fe = _engine.engine()
     ang, sc, resp, _ = fe.fmt_rotation([srcPolarImg, targetPolarImg], ((0, 1),), downsample=int(downsampleFactor), clip_px=clip_px)
     return float(ang[0]), float(sc[0]), float(resp[0])
+
+
+def plotCartPolar(prevImgPolar, currImgPolar, prevImgCart, currImgCart):
+    """FMT.py:103-133: 2 x 2 panel of the polar / Cartesian images."""
+    from matplotlib import pyplot as plt
+    panels = ((prevImgPolar, "Prev Image Polar"), (currImgPolar, "Curr Image Polar"),
+              (prevImgCart, "Prev Image Cartesian"), (currImgCart, "Curr Image Cartesian"))
+    for i, (img, title) in enumerate(panels, start=1):
+        plt.subplot(2, 2, i)
+        if img is not None:
+            plt.imshow(img)
+            plt.title(title)
+
+
+def plotCartPolarWithRotation(prevImgCart, currImgCart, rotRad):
+    """FMT.py:136-165 without the rotation-corrected panels (they need rotateImg)."""
+    from matplotlib import pyplot as plt
+    for i, (img, title) in enumerate(((prevImgCart, "Prev Image"), (currImgCart, "Curr Image")), start=1):
+        plt.subplot(1, 2, i)
+        if img is not None:
+            plt.imshow(img)
+            plt.axis("off")
+            plt.title(title)

@@ -5,7 +5,7 @@ from typing import Tuple
 import numpy as np
 
 from .FMT import getRotationUsingFMT
-from .getTransformKLT import calculateTransformSVD, getTrackedPointsKLT
+from .getTransformKLT import calculateTransformSVD, getTrackedPointsKLT, visualize_transform
 from .outlierRejection import rejectOutliers
 from .parseData import RANGE_RESOLUTION_CART_M
 
@@ -48,3 +48,15 @@ class Tracker():
         if not pixel:
             h *= RANGE_RESOLUTION_CART_M
         return R, h
+
+    def plot(self, prevImg, currImg, good_old, good_new, seqInd, save=True, show=False):
+        """Tracker.py:129-150: tracking overlay of one frame (RawROAMSystem.plot calls it every third frame,
+        RawROAMSystem.py:371-377); saved to filePaths["imgSave"] as the reference does."""
+        import os
+        from matplotlib import pyplot as plt
+        visualize_transform(prevImg, currImg, good_old, good_new, show=False)
+        plt.title(f"Tracking on Image {seqInd:04d}")
+        if save:
+            plt.savefig(os.path.join(self.filePaths["imgSave"], f"{seqInd:04d}.jpg"))
+        if show:
+            plt.pause(0.01)

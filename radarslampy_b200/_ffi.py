@@ -57,12 +57,12 @@ RF_SEQ_MDS, RF_SEQ_GRAPH = 1, 2
 SYMBOLS = [
     "rf_default_config", "rf_create", "rf_destroy", "rf_last_error", "rf_version", "rf_cart_size", "rf_stream",
     "rf_timer_start", "rf_timer_stop_ms", "rf_launch_count", "rf_extract_polar", "rf_frame_create",
-    "rf_frame_destroy", "rf_polar_to_cart", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
-    "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_ssc",
-    "rf_detect", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
+    "rf_frame_destroy", "rf_polar_to_cart", "rf_polar_to_cart_log", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
+    "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_mds_undistort_times", "rf_ssc",
+    "rf_detect", "rf_detect_doh", "rf_doh_response", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_track_pair", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
-    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_rotation_frames", "rf_fmt_log_polar",
+    "rf_batch_stage_times", "rf_host_alloc", "rf_host_free", "rf_batch_wait", "rf_fmt_rotation", "rf_fmt_rotation_frames", "rf_fmt_log_polar", "rf_cart_to_polar",
     "rf_phase_correlate", "rf_batch_fmt", "rf_chain_poses", "rf_png_info", "rf_ingest_png",
     "rf_seq_create", "rf_seq_destroy", "rf_seq_upload_async", "rf_seq_reset_async", "rf_seq_step_async", "rf_seq_results",
     "rf_seq_results_async", "rf_seq_ring", "rf_seq_steps_done", "rf_seq_features", "rf_seq_sync", "rf_seq_launches_per_step",
@@ -550,6 +550,15 @@ class RadarFE:
             self._check(self.lib.rf_polar_to_cart(self.h, None, _ptr(polar), frame.p, _ptr(out)))
         return frame, out
 
+    def polar_to_cart_log(self, polar):
+        """convertPolarImageToCartesian(polar, logPolarMode=True) -> f32 [n, n]."""
+        polar = _c(polar, np.float32)
+        if polar.shape != (self.cfg.azimuths, self.cfg.range_bins):
+            raise ValueError(f"polar image must be {(self.cfg.azimuths, self.cfg.range_bins)}, got {polar.shape}")
+        out = np.empty((self.n, self.n), np.float32)
+        self._check(self.lib.rf_polar_to_cart_log(self.h, _ptr(polar), _ptr(out)))
+        return out
+
     def frame_from_cart(self, cart, frame: Frame = None):
         cart = _c(cart, np.float32)
         if cart.ndim != 2 or cart.shape[0] != cart.shape[1]:
@@ -580,7 +589,15 @@ class RadarFE:
         mask = np.zeros(K, np.uint8)
         n_in, nodes = C.c_int(0), C.c_int(0)
         if K:
-            self._check(self.lib.rf_reject_outliers(self.h, _ptr(a), _ptr(b), K, _ptr(mask), C.byref(n_in), C.byref(nodes)))
+            rc = self.lib.rf_reject_outliers(self.h, _ptr(a), _ptr(b), K, _ptr(mask), C.byref(n_in), C.byref(nodes))
+            if rc == RF_E_WORKLIMIT:
+                # the reference always completes (in seconds to minutes on such graphs); keep the odometry loop alive with
+                # the largest clique found within cfg.clique_node_limit search nodes
+                import warnings
+                warnings.warn(f"rejectOutliers: clique search stopped after {nodes.value} nodes; using the best clique so far "
+                              f"({n_in.value} of {K} points)", RuntimeWarning, stacklevel=3)
+            else:
+                self._check(rc)
         return mask.astype(bool), n_in.value, nodes.value
 
     def consistency_adjacency(self, prev_xy, new_xy):
@@ -629,11 +646,14 @@ class RadarFE:
                                           C.c_double(period), _ptr(x), C.byref(it), C.byref(cost)))
         return x, it.value, cost.value
 
-    def mds_undistort(self, v, pts_xy, period):
+    def mds_undistort(self, v, pts_xy, period, times=None):
         v = _c(v, np.float64).reshape(3)
         p = _c(np.asarray(pts_xy)[:, :2], np.float64)
         out = np.zeros_like(p)
-        if p.shape[0]:
+        if p.shape[0] and times is not None:
+            t = _c(np.broadcast_to(np.asarray(times, np.float64), (p.shape[0],)), np.float64)
+            self._check(self.lib.rf_mds_undistort_times(self.h, _ptr(v), _ptr(p), _ptr(t), p.shape[0], _ptr(out)))
+        elif p.shape[0]:
             self._check(self.lib.rf_mds_undistort(self.h, _ptr(v), _ptr(p), p.shape[0], C.c_double(period), _ptr(out)))
         return out
 
@@ -653,6 +673,21 @@ class RadarFE:
         n = C.c_int(0)
         self._check(self.lib.rf_detect(self.h, frame.p, mode, C.c_float(threshold), _ptr(out), cap, C.byref(n)))
         return out[:min(n.value, cap)].copy(), n.value
+
+    def detect_doh(self, frame: Frame, min_sigma=1, max_sigma=30, num_sigma=10, threshold=0.01, overlap=0.5, cap=8192):
+        """skimage.feature.blob_doh on the frame's f32 Cartesian image -> f64 [K, 3] (row, col, sigma)."""
+        out = np.zeros((cap, 3), np.float64)
+        n = C.c_int(0)
+        self._check(self.lib.rf_detect_doh(self.h, frame.p, C.c_double(min_sigma), C.c_double(max_sigma), int(num_sigma),
+                                           C.c_double(threshold), C.c_double(overlap), _ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def doh_response(self, frame: Frame, min_sigma, max_sigma, num_sigma, sigma_index):
+        """Test hook: float64 integral image (sigma_index < 0) or one Hessian-determinant plane."""
+        out = np.zeros((self.n, self.n), np.float64)
+        self._check(self.lib.rf_doh_response(self.h, frame.p, C.c_double(min_sigma), C.c_double(max_sigma), int(num_sigma),
+                                             int(sigma_index), _ptr(out)))
+        return out
 
     def nms_select(self, resp, threshold, cap=None):
         resp = _c(resp, np.float32)
@@ -728,6 +763,20 @@ class RadarFE:
         out = np.empty((h_lp.value, w_lp.value), np.float32)
         self._check(self.lib.rf_fmt_log_polar(self.h, _ptr(polar), A, W, int(downsample), int(clip_px), _ptr(out),
                                               C.c_int64(out.size), C.byref(h_lp), C.byref(w_lp)))
+        return out
+
+    def cart_to_polar(self, cart, log_mode=False, shape_hw=None):
+        """cv2.warpPolar forward map of a square f32 image (parseData.convertCartesianImageToPolar) -> f32 [rows, cols]."""
+        cart = _c(cart, np.float32)
+        if cart.ndim != 2 or cart.shape[0] != cart.shape[1]:
+            raise AssertionError("Should be a square Cartesian image")
+        ro, co = (0, 0) if shape_hw is None else (int(shape_hw[0]), int(shape_hw[1]))
+        r, c = C.c_int(0), C.c_int(0)
+        self._check(self.lib.rf_cart_to_polar(self.h, _ptr(cart), cart.shape[0], int(bool(log_mode)), ro, co, None, C.c_int64(0),
+                                              C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.float32)
+        self._check(self.lib.rf_cart_to_polar(self.h, _ptr(cart), cart.shape[0], int(bool(log_mode)), ro, co, _ptr(out),
+                                              C.c_int64(out.size), C.byref(r), C.byref(c)))
         return out
 
     def phase_correlate(self, a, b):

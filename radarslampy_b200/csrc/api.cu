@@ -130,6 +130,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
 }
 
 void rf_destroy(rf_handle* h) {
+    RfDeviceGuard rf_guard_(h);
     if (!h) return;
     cudaSetDevice(h->device);
     rf_sync_all(h);
@@ -154,6 +155,7 @@ void* rf_stream(const rf_handle* h) { return h ? (void*)h->stream : nullptr; }
 int64_t rf_launch_count(const rf_handle* h) { return h ? h->launches : 0; }
 
 int rf_timer_start(rf_handle* h) {
+    RfDeviceGuard rf_guard_(h);
     if (!h) return RF_E_BADARG;
     int rc = rf_join_streams(h);
     if (rc) return rc;
@@ -161,6 +163,7 @@ int rf_timer_start(rf_handle* h) {
     return RF_OK;
 }
 int rf_timer_stop_ms(rf_handle* h, float* ms) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !ms) return RF_E_BADARG;
     int rc = rf_join_streams(h);   // the interval ends when the copy and tail streams have drained too
     if (rc) return rc;
@@ -170,6 +173,7 @@ int rf_timer_stop_ms(rf_handle* h, float* ms) {
     return RF_OK;
 }
 int rf_sync(rf_handle* h) {
+    RfDeviceGuard rf_guard_(h);
     if (!h) return RF_E_BADARG;
     return rf_sync_all(h);
 }
@@ -177,6 +181,7 @@ int rf_sync(rf_handle* h) {
 // ---- a1 -------------------------------------------------------------------------------
 int rf_extract_polar(rf_handle* h, const uint8_t* raw, float* polar, int64_t* timestamps, float* azimuths,
                      uint8_t* valid) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !raw) return rf_fail(h, RF_E_BADARG, "rf_extract_polar: null argument");
     const rf_config& c = h->cfg;
     if (polar) {
@@ -205,6 +210,7 @@ int rf_extract_polar(rf_handle* h, const uint8_t* raw, float* polar, int64_t* ti
 
 // ---- frames ---------------------------------------------------------------------------
 int rf_frame_create(rf_handle* h, rf_frame** out) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !out) return rf_fail(h, RF_E_BADARG, "rf_frame_create: null argument");
     rf_frame* f = new rf_frame();
     int rc = rf_frameset_alloc(h, &f->fs, 1, true);
@@ -214,6 +220,7 @@ int rf_frame_create(rf_handle* h, rf_frame** out) {
 }
 
 void rf_frame_destroy(rf_handle* h, rf_frame* f) {
+    RfDeviceGuard rf_guard_(h);
     if (!f) return;
     if (h) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
     rf_frameset_free(&f->fs);
@@ -221,6 +228,7 @@ void rf_frame_destroy(rf_handle* h, rf_frame* f) {
 }
 
 int rf_polar_to_cart(rf_handle* h, const uint8_t* raw, const float* polar, rf_frame* frame, float* cart_out) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !frame || (!raw == !polar)) return rf_fail(h, RF_E_BADARG, "rf_polar_to_cart: need exactly one of raw/polar");
     const rf_config& c = h->cfg;
     int rc;
@@ -242,6 +250,7 @@ int rf_polar_to_cart(rf_handle* h, const uint8_t* raw, const float* polar, rf_fr
 }
 
 int rf_frame_from_cart(rf_handle* h, const float* cart, int n, rf_frame* frame) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !cart || !frame) return rf_fail(h, RF_E_BADARG, "rf_frame_from_cart: null argument");
     if (n != h->n) return rf_fail(h, RF_E_BADARG, "rf_frame_from_cart: image is %d x %d, handle expects %d", n, n, h->n);
     RF_CUDA(h, cudaMemcpyAsync(frame->fs.cart, cart, (size_t)n * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -253,6 +262,7 @@ int rf_frame_from_cart(rf_handle* h, const float* cart, int n, rf_frame* frame) 
 }
 
 int rf_frame_download(rf_handle* h, const rf_frame* f, int what, void* out, int* rows, int* cols) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !f) return rf_fail(h, RF_E_BADARG, "rf_frame_download: null argument");
     if (what == 0) {
         if (rows) *rows = h->n;

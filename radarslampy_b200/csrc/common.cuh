@@ -56,6 +56,20 @@ struct rf_handle {
     std::string err;
 };
 
+// Every extern "C" entry point that takes a handle runs on the handle's device whatever the calling thread's current
+// device is (a second handle on another GPU, a Python thread, a host application that called cudaSetDevice), and
+// leaves the caller's current device as it found it.
+struct RfDeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit RfDeviceGuard(const rf_handle* h) {
+        if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+    }
+    ~RfDeviceGuard() { if (switched) cudaSetDevice(prev); }
+    RfDeviceGuard(const RfDeviceGuard&) = delete;
+    RfDeviceGuard& operator=(const RfDeviceGuard&) = delete;
+};
+
 extern thread_local std::string g_rf_err;  // for failures without a handle
 
 int rf_fail(rf_handle* h, int code, const char* fmt, ...);

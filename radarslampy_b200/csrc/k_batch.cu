@@ -196,6 +196,7 @@ extern "C" {
 static int batch_create_sized(rf_handle* h, int max_frames, int max_pairs, rf_batch** out);
 
 int rf_batch_create(rf_handle* h, rf_batch** out) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !out) return rf_fail(h, RF_E_BADARG, "rf_batch_create: null argument");
     return batch_create_sized(h, h->cfg.max_frames, h->cfg.max_pairs, out);
 }
@@ -255,6 +256,7 @@ static int batch_create_sized(rf_handle* h, int max_frames, int max_pairs, rf_ba
 }
 
 void rf_batch_destroy(rf_handle* h, rf_batch* b) {
+    RfDeviceGuard rf_guard_(h);
     if (!b) return;
     if (h) {
         cudaSetDevice(h->device);
@@ -266,6 +268,7 @@ void rf_batch_destroy(rf_handle* h, rf_batch* b) {
 
 int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx,
                           int n_pairs, const float* feats, const int32_t* feat_counts, const double* prev_pose) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b || n_frames < 0 || n_pairs < 0 || (n_frames > 0 && !raw) ||
         (n_pairs > 0 && (!pair_idx || !feats || !feat_counts)))
         return rf_fail(h, RF_E_BADARG, "rf_batch_upload: null argument");
@@ -301,6 +304,7 @@ int rf_batch_upload_async(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_f
 
 int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx, int n_pairs,
                     const float* feats, const int32_t* feat_counts, const double* prev_pose) {
+    RfDeviceGuard rf_guard_(h);
     int rc = rf_batch_upload_async(h, b, raw, n_frames, pair_idx, n_pairs, feats, feat_counts, prev_pose);
     if (rc) return rc;
     RF_CUDA(h, cudaStreamSynchronize(h->stream_copy));
@@ -308,6 +312,7 @@ int rf_batch_upload(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames,
 }
 
 int rf_batch_set_profiling(rf_handle* h, rf_batch* b, int on) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_set_profiling: null argument");
     if (on && !b->ev[0][0]) {
         for (int i = 0; i < RF_PROFILE_RING; ++i)
@@ -318,6 +323,7 @@ int rf_batch_set_profiling(rf_handle* h, rf_batch* b, int on) {
 }
 
 int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_run_async: null argument");
     const rf_config& c = h->cfg;
     const int P = b->n_pairs, F = b->n_frames, K = b->Kmax;
@@ -402,6 +408,7 @@ int rf_batch_run_async(rf_handle* h, rf_batch* b, int with_mds) {
 }
 
 int rf_batch_stage_times(rf_handle* h, rf_batch* b, float* ms_sum, int cap, int* n_runs) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b || !ms_sum || cap < RF_N_STAGES) return rf_fail(h, RF_E_BADARG, "rf_batch_stage_times: bad argument");
     for (int s = 0; s < cap; ++s) ms_sum[s] = 0.f;
     if (n_runs) *n_runs = b->prof_count;
@@ -421,6 +428,7 @@ int rf_batch_stage_times(rf_handle* h, rf_batch* b, float* ms_sum, int cap, int*
 }
 
 int rf_batch_download_async(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b || (b->n_pairs > 0 && !results)) return rf_fail(h, RF_E_BADARG, "rf_batch_download: null argument");
     const size_t P = b->n_pairs, K = b->Kmax;
     if (!P) return RF_OK;
@@ -432,6 +440,7 @@ int rf_batch_download_async(rf_handle* h, rf_batch* b, rf_pair_result* results, 
 }
 
 int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float* next_xy, uint8_t* status) {
+    RfDeviceGuard rf_guard_(h);
     int rc = rf_batch_download_async(h, b, results, next_xy, status);
     if (rc) return rc;
     RF_CUDA(h, cudaStreamSynchronize(b->tail));
@@ -439,12 +448,14 @@ int rf_batch_download(rf_handle* h, rf_batch* b, rf_pair_result* results, float*
 }
 
 int rf_batch_wait(rf_handle* h, rf_batch* b) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_wait: null argument");
     RF_CUDA(h, cudaStreamSynchronize(b->tail));
     return RF_OK;
 }
 
 int rf_batch_klt_status(rf_handle* h, rf_batch* b, uint8_t* klt_status, float* err) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b) return rf_fail(h, RF_E_BADARG, "rf_batch_klt_status: null argument");
     const size_t P = b->n_pairs, K = b->Kmax;
     if (!P) return RF_OK;
@@ -459,6 +470,7 @@ int rf_batch_klt_status(rf_handle* h, rf_batch* b, uint8_t* klt_status, float* e
 // Runs on the handle's main stream after the batch's upload; synchronous on return.
 int rf_batch_fmt(rf_handle* h, rf_batch* b, int downsample, int clip_px, double* angle_rad, double* scale, double* response,
                  double* shift_xy) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b || !angle_rad) return rf_fail(h, RF_E_BADARG, "rf_batch_fmt: null argument");
     const int P = b->n_pairs, F = b->n_frames;
     if (!P) return RF_OK;
@@ -479,6 +491,7 @@ int rf_batch_fmt(rf_handle* h, rf_batch* b, int downsample, int clip_px, double*
 int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, const int32_t* pair_idx, int n_pairs,
                    const float* feats, const int32_t* feat_counts, const double* prev_pose, int with_mds,
                    rf_pair_result* results, float* next_xy, uint8_t* status) {
+    RfDeviceGuard rf_guard_(h);
     int rc = rf_batch_upload_async(h, b, raw, n_frames, pair_idx, n_pairs, feats, feat_counts, prev_pose);
     if (rc) return rc;
     if ((rc = rf_batch_run_async(h, b, with_mds))) return rc;
@@ -490,6 +503,7 @@ int rf_track_batch(rf_handle* h, rf_batch* b, const uint8_t* raw, int n_frames, 
 // next_xy [K, 2] / corr_status [K] may be NULL.  Synchronous on return.
 int rf_track_pair(rf_handle* h, const uint8_t* raw_prev, const uint8_t* raw_next, const float* feats_xy, int K,
                   const double* prev_pose, int with_mds, rf_pair_result* result, float* next_xy, uint8_t* corr_status) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !raw_prev || !raw_next || !result || K < 0 || (K > 0 && !feats_xy))
         return rf_fail(h, RF_E_BADARG, "rf_track_pair: bad argument");
     const rf_config& c = h->cfg;
@@ -519,6 +533,7 @@ int rf_track_pair(rf_handle* h, const uint8_t* raw_prev, const uint8_t* raw_next
 }
 
 int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, int what, void* out, int* rows, int* cols) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !b || frame < 0 || frame >= b->n_frames) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: bad frame");
     { int rcs = rf_sync_all(h); if (rcs) return rcs; }
     if (what == 0) {

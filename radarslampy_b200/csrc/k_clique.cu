@@ -1179,6 +1179,7 @@ int rf_launch_reject(rf_handle* h, void* ws_base, const float* d_prev, const flo
 extern "C" {
 
 int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* adj) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !prev_xy || !new_xy || !adj || K < 0) return rf_fail(h, RF_E_BADARG, "rf_consistency_adjacency: bad argument");
     if (K == 0) return RF_OK;
     CliqueGeom g = make_geom(K);
@@ -1203,6 +1204,7 @@ int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* ne
 
 int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* mask, int* n_inliers,
                        int* nodes) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !prev_xy || !new_xy || !mask || K < 0) return rf_fail(h, RF_E_BADARG, "rf_reject_outliers: bad argument");
     if (n_inliers) *n_inliers = 0;
     if (nodes) *nodes = 0;
@@ -1237,6 +1239,7 @@ int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, 
 // Test hook: clique search on a caller-supplied adjacency matrix (K x K bytes).
 int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, int32_t* clique_mask_out, int* size,
                      int64_t* n_yields, uint64_t* order_hash, int64_t* nodes) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !adj || K < 0) return rf_fail(h, RF_E_BADARG, "rf_clique_search: bad argument");
     if (K == 0) { if (size) *size = 0; return RF_OK; }
     size_t ab = ((size_t)K * K + 255) & ~(size_t)255;

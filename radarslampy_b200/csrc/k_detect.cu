@@ -577,6 +577,7 @@ static unsigned pow2_at_least(size_t v) { unsigned p = 2; while (p < v) p <<= 1;
 extern "C" {
 
 int rf_ssc(rf_handle* h, const double* kp, int n, int num_ret, double tol, int cols, int rows, int32_t* sel_idx, int* m) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !m || n < 0 || (n > 0 && (!kp || !sel_idx)) || cols <= 0 || rows <= 0)
         return rf_fail(h, RF_E_BADARG, "rf_ssc: bad argument");
     if (num_ret == 1) return rf_fail(h, RF_E_BADARG, "rf_ssc: num_ret_points == 1 divides by zero (ANMS.py:19-22)");
@@ -646,11 +647,12 @@ static int detect_scratch(rf_handle* h, size_t resp_bytes, int rows, int cols, u
 }
 
 // k_doh.cu: determinant-of-Hessian response planes (mode 1)
-int rf_doh_detect_host(rf_handle* h, const float* d_cart, int n, float threshold, double* out, int cap, int* n_out);
+int rf_doh_detect_host(rf_handle* h, const rf_frame* f, float threshold, double* out, int cap, int* n_out);
 
 extern "C" {
 
 int rf_corner_response(rf_handle* h, const rf_frame* f, int mode, float* resp) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !f || !resp) return rf_fail(h, RF_E_BADARG, "rf_corner_response: null argument");
     if (mode != 0) return rf_fail(h, RF_E_BADARG, "rf_corner_response: mode %d has no single response plane (0 = structure-tensor min eigenvalue; DoH planes: rf_doh_response)", mode);
     if (!f->fs.cart) return rf_fail(h, RF_E_BADARG, "rf_corner_response: frame has no f32 plane");
@@ -664,10 +666,11 @@ int rf_corner_response(rf_handle* h, const rf_frame* f, int mode, float* resp) {
 }
 
 int rf_detect(rf_handle* h, const rf_frame* f, int mode, float threshold, double* out, int cap, int* n) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !f || !n || cap < 0 || (cap > 0 && !out)) return rf_fail(h, RF_E_BADARG, "rf_detect: bad argument");
     if (mode != 0 && mode != 1) return rf_fail(h, RF_E_BADARG, "rf_detect: mode %d is not available (0 = structure-tensor min eigenvalue, 1 = determinant of Hessian)", mode);
     if (!f->fs.cart) return rf_fail(h, RF_E_BADARG, "rf_detect: frame has no f32 plane");
-    if (mode == 1) return rf_doh_detect_host(h, f->fs.cart, h->n, threshold, out, cap, n);
+    if (mode == 1) return rf_doh_detect_host(h, f, threshold, out, cap, n);
     const size_t bytes = (size_t)h->n * h->n * sizeof(float);
     const unsigned key_cap = pow2_at_least((size_t)h->n * h->n / 4 + 1024);   // 3x3 maxima cannot be denser than 1 in 4
     size_t off;
@@ -679,6 +682,7 @@ int rf_detect(rf_handle* h, const rf_frame* f, int mode, float threshold, double
 }
 
 int rf_nms_select(rf_handle* h, const float* resp, int rows, int cols, float threshold, double* out, int cap, int* n) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !resp || !n || rows < 3 || cols < 3 || cap < 0 || (cap > 0 && !out))
         return rf_fail(h, RF_E_BADARG, "rf_nms_select: bad argument");
     const size_t bytes = (size_t)rows * cols * sizeof(float);

@@ -117,6 +117,38 @@ k_fmt_cart(const float* __restrict__ src, int A, int Wd, float* __restrict__ car
 }
 
 // ------------------------------------------------------------------------------------
+// forward warpPolar of an n x n image, linear or semi-log radius (no window): same map arithmetic as k_fmt_logpolar
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_cart_to_polar(const float* __restrict__ cart, int n, int w_out, int h_out, int semilog, float* __restrict__ out) {
+    const int rho = blockIdx.x * blockDim.x + threadIdx.x, phi = blockIdx.y;
+    if (rho >= w_out || phi >= h_out) return;
+    const double max_radius = (double)n / 2.0;
+    const float ctr = (float)(n / 2.0);
+    const double Kangle = (2.0 * M_PI) / h_out;
+    const double Kmag = semilog ? log(max_radius) / w_out : max_radius / w_out;
+    const float r = semilog ? (float)(exp(rho * Kmag) - 1.0) : (float)(rho * Kmag);
+    const double ang = Kangle * phi;
+    const float mx = (float)__dadd_rn(__dmul_rn((double)r, cos(ang)), (double)ctr);
+    const float my = (float)__dadd_rn(__dmul_rn((double)r, sin(ang)), (double)ctr);
+    const int sx = __float2int_rn(__fmul_rn(mx, 32.0f)), sy = __float2int_rn(__fmul_rn(my, 32.0f));
+    const int ix = sx >> 5, iy = sy >> 5;
+    const float fx = (float)(sx & 31) * 0.03125f, fy = (float)(sy & 31) * 0.03125f;
+    const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy);
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int yy = iy + (t >> 1), xx = ix + (t & 1);
+        v[t] = (xx >= 0 && xx < n && yy >= 0 && yy < n) ? __ldg(cart + (size_t)yy * n + xx) : 0.0f;
+    }
+    float acc = __fmul_rn(v[0], __fmul_rn(gy, gx));
+    acc = __fadd_rn(acc, __fmul_rn(v[1], __fmul_rn(gy, fx)));
+    acc = __fadd_rn(acc, __fmul_rn(v[2], __fmul_rn(fy, gx)));
+    acc = __fadd_rn(acc, __fmul_rn(v[3], __fmul_rn(fy, fx)));
+    out[(size_t)phi * w_out + rho] = acc;
+}
+
+// ------------------------------------------------------------------------------------
 // forward semi-log warpPolar (+ Hann window, zero padding to M x N)
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -507,6 +539,7 @@ static int fmt_rotation_impl(rf_handle* h, const float* polar, const float* cons
 
 int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W, const int32_t* pair_idx, int n_pairs,
                     int downsample, int clip_px, double* angle_rad, double* scale, double* response, double* shift_xy) {
+    RfDeviceGuard rf_guard_(h);
     return fmt_rotation_impl(h, polar, nullptr, n_frames, A, W, pair_idx, n_pairs, downsample, clip_px, angle_rad, scale, response,
                              shift_xy);
 }
@@ -515,6 +548,7 @@ int rf_fmt_rotation(rf_handle* h, const float* polar, int n_frames, int A, int W
 int rf_fmt_rotation_frames(rf_handle* h, const float* const* frames, int n_frames, int A, int W, const int32_t* pair_idx,
                            int n_pairs, int downsample, int clip_px, double* angle_rad, double* scale, double* response,
                            double* shift_xy) {
+    RfDeviceGuard rf_guard_(h);
     return fmt_rotation_impl(h, nullptr, frames, n_frames, A, W, pair_idx, n_pairs, downsample, clip_px, angle_rad, scale, response,
                              shift_xy);
 }
@@ -522,6 +556,7 @@ int rf_fmt_rotation_frames(rf_handle* h, const float* const* frames, int n_frame
 // parseData.convertPolarImgToLogPolar(cv2.resize(polar[:, :clip_px], (clip_px // downsample, A)))
 int rf_fmt_log_polar(rf_handle* h, const float* polar, int A, int W, int downsample, int clip_px, float* out, int64_t out_cap,
                      int* h_lp, int* w_lp) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !polar || !h_lp || !w_lp) return rf_fail(h, RF_E_BADARG, "rf_fmt_log_polar: bad argument");
     FmtDims d;
     int rc = fmt_dims(h, A, W, downsample, clip_px, &d);
@@ -551,8 +586,35 @@ int rf_fmt_log_polar(rf_handle* h, const float* polar, int A, int W, int downsam
     return RF_OK;
 }
 
+// parseData.convertCartesianImageToPolar(imgCart, logPolarMode, shapeHW)          parseData.py:69-97
+// cv::warpPolar forward map (linear or semi-log), INTER_LINEAR | WARP_FILL_OUTLIERS, centre (n / 2, n / 2), maxRadius n / 2;
+// dsize (0, 0) selects cv's default (round(maxRadius), round(maxRadius * pi)).
+int rf_cart_to_polar(rf_handle* h, const float* cart, int n, int log_mode, int rows_out, int cols_out, float* out, int64_t out_cap,
+                     int* rows, int* cols) {
+    RfDeviceGuard rf_guard_(h);
+    if (!h || !cart || n < 2 || !rows || !cols) return rf_fail(h, RF_E_BADARG, "rf_cart_to_polar: bad argument");
+    const double max_radius = (double)n / 2.0;
+    const int w = cols_out > 0 ? cols_out : (int)nearbyint(max_radius);
+    const int hgt = rows_out > 0 ? rows_out : (int)nearbyint(max_radius * M_PI);
+    *rows = hgt; *cols = w;
+    if (!out) return RF_OK;
+    if (out_cap < (int64_t)hgt * w) return rf_fail(h, RF_E_CAPACITY, "rf_cart_to_polar: output buffer too small");
+    const size_t b_cart = al256((size_t)n * n * 4), b_out = al256((size_t)hgt * w * 4);
+    int rc = rf_ensure_scratch(h, b_cart + b_out);
+    if (rc) return rc;
+    float* d_cart = (float*)h->d_scratch;
+    float* d_out = (float*)((char*)h->d_scratch + b_cart);
+    RF_CUDA(h, cudaMemcpyAsync(d_cart, cart, (size_t)n * n * 4, cudaMemcpyHostToDevice, h->stream));
+    k_cart_to_polar<<<dim3((w + 127) / 128, hgt, 1), 128, 0, h->stream>>>(d_cart, n, w, hgt, log_mode ? 1 : 0, d_out);
+    RF_CHECK_LAUNCH(h);
+    RF_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)hgt * w * 4, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
 // cv2.phaseCorrelate(a, b, cv2.createHanningWindow((cols, rows), CV_32F)) -> (dx, dy), response   (FMT.py:13-33)
 int rf_phase_correlate(rf_handle* h, const float* a, const float* b, int rows, int cols, double* dx, double* dy, double* response) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !a || !b || rows < 2 || cols < 2 || !dx || !dy) return rf_fail(h, RF_E_BADARG, "rf_phase_correlate: bad argument");
     const int M = optimal_dft_size(rows);
     int N = optimal_dft_size(cols);

@@ -21,7 +21,7 @@
 // geometry table
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_build_map(uint32_t* __restrict__ map, int n, float cx, float cy,
-                                                   double Kmag, double Kangle) {
+                                                   double Kmag, double Kangle, int semilog) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= n || y >= n) return;
@@ -30,6 +30,9 @@ __global__ void __launch_bounds__(256) k_build_map(uint32_t* __restrict__ map, i
     const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
     float dx = __fsub_rn((float)x, cx), dy = __fsub_rn((float)y, cy);
     float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    // WARP_POLAR_LOG: bufp += 1.f; cv::log(bufp, bufp).  cv::log's f32 kernel is a vendor routine that differs from a
+    // correctly rounded logf by at most one ulp on ~2 % of its arguments, so this mode is a tolerance match (parseData.py:131-133)
+    if (semilog) mag = logf(__fadd_rn(mag, 1.0f));
     float ax = fabsf(dx), ay = fabsf(dy);
     float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
     float c = __fdiv_rn(mn, __fadd_rn(mx, (float)DBL_EPSILON));
@@ -228,7 +231,7 @@ int rf_launch_build_map(rf_handle* h) {
     const double Kangle = (2.0 * M_PI) / h->cfg.azimuths;          // CV_2PI / ssize.height
     const double Kmag = (double)h->R / (double)h->cfg.range_bins;  // maxRadius / ssize.width
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
-    k_build_map<<<grd, blk, 0, h->stream>>>(h->map, n, (float)h->R, (float)h->R, Kmag, Kangle);
+    k_build_map<<<grd, blk, 0, h->stream>>>(h->map, n, (float)h->R, (float)h->R, Kmag, Kangle, 0);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
@@ -283,5 +286,37 @@ int rf_launch_extract(rf_handle* h, const uint8_t* d_raw, float* d_polar) {
     dim3 grd((W + 255) / 256, h->cfg.azimuths);
     k_extract<<<grd, 256, 0, h->stream>>>(d_raw, h->cfg.azimuths, h->cfg.raw_width, h->cfg.meta_bytes, W, d_polar);
     RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+
+// convertPolarImageToCartesian(imgPolar, logPolarMode=True)      parseData.py:100-135 (flags += cv2.WARP_POLAR_LOG)
+// cv::warpPolar's inverse SEMI-LOG map: rho = log(|p - centre| + 1) * W / log(maxRadius).  The map is built into
+// scratch for the call (the reference never takes this branch on its live path) and sampled by the same remap kernel.
+extern "C" int rf_polar_to_cart_log(rf_handle* h, const float* polar, float* cart_out) {
+    RfDeviceGuard rf_guard_(h);
+    if (!h || !polar || !cart_out) return rf_fail(h, RF_E_BADARG, "rf_polar_to_cart_log: null argument");
+    const rf_config& c = h->cfg;
+    const int n = h->n;
+    if (n % 4) return rf_fail(h, RF_E_BADARG, "cartesian size %d is not a multiple of 4", n);
+    const size_t n2 = (size_t)n * n;
+    const size_t map_b = (n2 * 4 + 255) & ~(size_t)255, cart_b = (n2 * 4 + 255) & ~(size_t)255, u8_b = (n2 + 255) & ~(size_t)255;
+    int rc = rf_ensure_scratch(h, map_b + cart_b + u8_b);
+    if (rc) return rc;
+    uint32_t* d_map = (uint32_t*)h->d_scratch;
+    float* d_cart = (float*)((char*)h->d_scratch + map_b);
+    uint8_t* d_u8 = (uint8_t*)((char*)h->d_scratch + map_b + cart_b);
+    const double Kangle = (2.0 * M_PI) / c.azimuths;
+    const double Kmag = log((double)h->R) / (double)c.range_bins;     // std::log(maxRadius) / ssize.width
+    dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
+    k_build_map<<<grd, blk, 0, h->stream>>>(d_map, n, (float)h->R, (float)h->R, Kmag, Kangle, 1);
+    RF_CHECK_LAUNCH(h);
+    RF_CUDA(h, cudaMemcpyAsync(h->d_polar, polar, (size_t)c.azimuths * c.range_bins * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    dim3 blk2(16, 16), grd2((n / 4 + 15) / 16, (n + 15) / 16, 1);
+    k_polar2cart<float, true><<<grd2, blk2, 0, h->stream>>>(h->d_polar, 0, c.range_bins, 0, c.azimuths, c.range_bins, d_map, n, d_cart, 0,
+                                                            d_u8, 0, 0);
+    RF_CHECK_LAUNCH(h);
+    RF_CUDA(h, cudaMemcpyAsync(cart_out, d_cart, n2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RF_OK;
 }

@@ -338,15 +338,17 @@ static void seq_free(rf_seq* q) {
     } while (0)
 
 // k_doh.cu: determinant-of-Hessian candidates (keys) for every flagged problem
-int rf_launch_doh_candidates(rf_handle* h, const DetectWs& ws, const float* d_cart, size_t cart_stride, int n, void* d_doh_ws,
+int rf_launch_doh_keypoints(rf_handle* h, const DetectWs& ws, const float* d_cart, size_t cart_stride, int n, void* d_doh_ws,
                              const int32_t* d_flags);
 size_t rf_doh_ws_bytes(const rf_handle* h, int S);
+int rf_doh_prepare(rf_handle* h);
 
 static std::map<rf_seq*, void*> g_doh_ws;   // DoH scratch (integral images) of runners created with detector_mode 1
 
 extern "C" {
 
 int rf_seq_create(rf_handle* h, int n_seq, int arena_frames, int detector_mode, rf_seq** out) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !out || n_seq < 1 || arena_frames < n_seq) return rf_fail(h, RF_E_BADARG, "rf_seq_create: bad argument (arena_frames must be >= n_seq)");
     if (detector_mode != 0 && detector_mode != 1) return rf_fail(h, RF_E_BADARG, "rf_seq_create: detector_mode %d (0 = structure tensor, 1 = determinant of Hessian)", detector_mode);
     *out = nullptr;
@@ -415,7 +417,7 @@ int rf_seq_create(rf_handle* h, int n_seq, int arena_frames, int detector_mode, 
     }
     {
         SeqScope sc(h, q->stream);
-        if ((rc = rf_detect_ws_init(h, q->det)) || (rc = rf_detect_prepare(h))) { seq_free(q); return rc; }
+        if ((rc = rf_detect_ws_init(h, q->det)) || (rc = rf_detect_prepare(h)) || (detector_mode == 1 && (rc = rf_doh_prepare(h)))) { seq_free(q); return rc; }
         cudaMemsetAsync(q->d_next, 0, S * K * 2 * sizeof(float), q->stream);
         cudaMemsetAsync(q->d_status, 0, S * K, q->stream);
         cudaMemsetAsync(q->d_err, 0, S * K * sizeof(float), q->stream);
@@ -431,6 +433,7 @@ int rf_seq_create(rf_handle* h, int n_seq, int arena_frames, int detector_mode, 
 }
 
 void rf_seq_destroy(rf_handle* h, rf_seq* q) {
+    RfDeviceGuard rf_guard_(h);
     if (!q) return;
     if (h) {
         cudaSetDevice(h->device);
@@ -444,6 +447,7 @@ void rf_seq_destroy(rf_handle* h, rf_seq* q) {
 }
 
 int rf_seq_upload_async(rf_handle* h, rf_seq* q, int first_frame, int n_frames, const uint8_t* raw) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !q || !raw || first_frame < 0 || n_frames < 0 || first_frame + n_frames > q->arena_frames)
         return rf_fail(h, RF_E_BADARG, "rf_seq_upload: frames [%d, %d) outside the arena of %d", first_frame, first_frame + n_frames, q ? q->arena_frames : 0);
     if (!n_frames) return RF_OK;
@@ -506,10 +510,12 @@ static int seq_enqueue_detect(rf_handle* h, rf_seq* q) {
     if (q->detector_mode == 0) {
         if ((rc = rf_launch_min_eig(h, q->d_cart, n2, h->n, q->det.resp, q->det.resp_stride, q->S, q->d_flags))) return rc;
         if ((rc = rf_launch_select_sorted(h, q->det, q->det.resp, q->det.resp_stride, (float)-c.detect_quality, q->d_flags))) return rc;
+        if ((rc = rf_launch_ssc_from_keys(h, q->det, c.ssc_num_ret, c.ssc_tolerance, q->d_flags))) return rc;
     } else {
-        if ((rc = rf_launch_doh_candidates(h, q->det, q->d_cart, n2, h->n, g_doh_ws[q], q->d_flags))) return rc;
+        // the reference's detector: blob_doh -> adaptiveNMS' argsort by sigma -> ssc (getFeatures.py:47-51,66-72)
+        if ((rc = rf_launch_doh_keypoints(h, q->det, q->d_cart, n2, h->n, g_doh_ws[q], q->d_flags))) return rc;
+        if ((rc = rf_launch_ssc(h, q->det, c.ssc_num_ret, c.ssc_tolerance, h->n, h->n, q->d_flags))) return rc;
     }
-    if ((rc = rf_launch_ssc_from_keys(h, q->det, c.ssc_num_ret, c.ssc_tolerance, q->d_flags))) return rc;
     SeqAppendArgs a;
     a.S = q->S; a.Kmax = q->Kmax; a.center = (double)h->R; a.res = c.cart_res_m; a.period = c.mds_period;
     a.desc = q->d_desc; a.flags = q->d_flags; a.sel_idx = q->det.sel_idx; a.rc = q->det.rc; a.ssc_cap = q->det.ssc_cap;
@@ -548,6 +554,7 @@ static int seq_enqueue_step(rf_handle* h, rf_seq* q, int parity, int with_mds) {
 }
 
 int rf_seq_reset_async(rf_handle* h, rf_seq* q, int base, int stride, const double* init_pose) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !q) return rf_fail(h, RF_E_BADARG, "rf_seq_reset: null argument");
     cudaSetDevice(h->device);
     int rc = seq_check_range(h, q, base, stride);
@@ -571,6 +578,7 @@ int rf_seq_reset_async(rf_handle* h, rf_seq* q, int base, int stride, const doub
 }
 
 int rf_seq_step_async(rf_handle* h, rf_seq* q, int base, int stride, int flags) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !q) return rf_fail(h, RF_E_BADARG, "rf_seq_step: null argument");
     cudaSetDevice(h->device);
     int rc = seq_check_range(h, q, base, stride);
@@ -613,6 +621,7 @@ int rf_seq_step_async(rf_handle* h, rf_seq* q, int base, int stride, int flags) 
 }
 
 int rf_seq_results_async(rf_handle* h, rf_seq* q, int step, rf_seq_result* out) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !q || !out) return rf_fail(h, RF_E_BADARG, "rf_seq_results: null argument");
     if (step < 0 || step > q->steps || step <= q->steps - q->ring)
         return rf_fail(h, RF_E_BADARG, "rf_seq_results: step %d is not among the last %d of %d", step, q->ring, q->steps);
@@ -623,6 +632,7 @@ int rf_seq_results_async(rf_handle* h, rf_seq* q, int step, rf_seq_result* out) 
 }
 
 int rf_seq_results(rf_handle* h, rf_seq* q, int step, rf_seq_result* out) {
+    RfDeviceGuard rf_guard_(h);
     int rc = rf_seq_results_async(h, q, step, out);
     if (rc) return rc;
     RF_CUDA(h, cudaStreamSynchronize(q->stream));
@@ -634,6 +644,7 @@ int rf_seq_steps_done(const rf_seq* q) { return q ? q->steps : 0; }
 int rf_seq_launches_per_step(const rf_seq* q) { return q ? q->launches_per_step : 0; }
 
 int rf_seq_features(rf_handle* h, rf_seq* q, float* feats, int32_t* counts) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !q) return rf_fail(h, RF_E_BADARG, "rf_seq_features: null argument");
     cudaSetDevice(h->device);
     if (feats) RF_CUDA(h, cudaMemcpyAsync(feats, q->d_feats, (size_t)q->S * q->Kmax * 2 * sizeof(float), cudaMemcpyDeviceToHost, q->stream));
@@ -643,6 +654,7 @@ int rf_seq_features(rf_handle* h, rf_seq* q, float* feats, int32_t* counts) {
 }
 
 int rf_seq_sync(rf_handle* h, rf_seq* q) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !q) return rf_fail(h, RF_E_BADARG, "rf_seq_sync: null argument");
     cudaSetDevice(h->device);
     RF_CUDA(h, cudaStreamSynchronize(h->stream_copy));

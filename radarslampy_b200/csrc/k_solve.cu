@@ -373,6 +373,18 @@ k_undistort(const double* __restrict__ pts, int N, double vx, double vy, double 
     out[2 * i + 1] = s * x + c * y + vy * t;
 }
 
+// explicit per-point time offsets (MotionDistortionSolver.undistort(..., times=...), motionDistortion.py:127-153)
+__global__ void __launch_bounds__(256)
+k_undistort_times(const double* __restrict__ pts, const double* __restrict__ times, int N, double vx, double vy, double vth,
+                  double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double x = pts[2 * i], y = pts[2 * i + 1], t = times[i];
+    const double th = vth * t, c = cos(th), s = sin(th);
+    out[2 * i] = c * x - s * y + vx * t;
+    out[2 * i + 1] = s * x + c * y + vy * t;
+}
+
 // ---- launchers ------------------------------------------------------------------------
 int rf_launch_kabsch(rf_handle* h, const float* d_src, const float* d_tgt, const uint8_t* d_mask, int mask_stride,
                      const int32_t* d_counts, int Kstride, int P, double* d_R, double* d_h, int32_t* d_nused) {
@@ -421,6 +433,7 @@ int rf_launch_mds_chain(rf_handle* h, const float* d_old, const float* d_new, co
 extern "C" {
 
 int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, double R[4], double hvec[2]) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !src_xy || !tgt_xy || !R || !hvec || N < 0) return rf_fail(h, RF_E_BADARG, "rf_kabsch: bad argument");
     size_t bp = ((size_t)N * 8 + 255) & ~(size_t)255;
     int rc = rf_ensure_scratch(h, 2 * bp + 1024);
@@ -445,6 +458,7 @@ int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, dou
 
 int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const double* p_jt, int N, const double T_wj[9],
                  const double* sigma_p, const double* sigma_v, double period, double x_out[6], int* iters, double* cost) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !T_wj0 || !T_wj || !x_out || N < 0 || (N > 0 && (!p_w || !p_jt)))
         return rf_fail(h, RF_E_BADARG, "rf_mds_solve: bad argument");
     const int Ns = N > 0 ? N : 1;
@@ -483,6 +497,7 @@ int rf_mds_solve(rf_handle* h, const double T_wj0[9], const double* p_w, const d
 }
 
 int rf_mds_undistort(rf_handle* h, const double v[3], const double* pts_xy, int N, double period, double* out_xy) {
+    RfDeviceGuard rf_guard_(h);
     if (!h || !v || N < 0 || (N > 0 && (!pts_xy || !out_xy))) return rf_fail(h, RF_E_BADARG, "rf_mds_undistort: bad argument");
     if (N == 0) return RF_OK;
     size_t bp = ((size_t)N * 16 + 255) & ~(size_t)255;
@@ -491,6 +506,23 @@ int rf_mds_undistort(rf_handle* h, const double v[3], const double* pts_xy, int 
     double* din = (double*)h->d_scratch; double* dout = (double*)((char*)h->d_scratch + bp);
     RF_CUDA(h, cudaMemcpyAsync(din, pts_xy, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
     k_undistort<<<(N + 255) / 256, 256, 0, h->stream>>>(din, N, v[0], v[1], v[2], period, dout);
+    RF_CHECK_LAUNCH(h);
+    RF_CUDA(h, cudaMemcpyAsync(out_xy, dout, (size_t)N * 16, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RF_OK;
+}
+
+int rf_mds_undistort_times(rf_handle* h, const double v[3], const double* pts_xy, const double* times, int N, double* out_xy) {
+    RfDeviceGuard rf_guard_(h);
+    if (!h || !v || N < 0 || (N > 0 && (!pts_xy || !times || !out_xy))) return rf_fail(h, RF_E_BADARG, "rf_mds_undistort_times: bad argument");
+    if (N == 0) return RF_OK;
+    const size_t bp = ((size_t)N * 16 + 255) & ~(size_t)255;
+    int rc = rf_ensure_scratch(h, 3 * bp);
+    if (rc) return rc;
+    double* din = (double*)h->d_scratch; double* dout = (double*)((char*)h->d_scratch + bp); double* dt = (double*)((char*)h->d_scratch + 2 * bp);
+    RF_CUDA(h, cudaMemcpyAsync(din, pts_xy, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dt, times, (size_t)N * 8, cudaMemcpyHostToDevice, h->stream));
+    k_undistort_times<<<(N + 255) / 256, 256, 0, h->stream>>>(din, dt, N, v[0], v[1], v[2], dout);
     RF_CHECK_LAUNCH(h);
     RF_CUDA(h, cudaMemcpyAsync(out_xy, dout, (size_t)N * 16, cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -29,7 +29,21 @@ def getTrackedPointsKLT(srcImg: np.ndarray, targetImg: np.ndarray, blobCoordSrc:
     return nextPts[good, :], featurePtSrc[good, :], nextPts[~good, :], featurePtSrc[~good, :], status
 
 
-def visualize_transform(*args, **kwargs):
-    """getTransformKLT.py:165-230 is a matplotlib debugging plot (imported, never called on the hot path by
-    Tracker.py:9); it is outside this front end."""
-    raise NotImplementedError("visualize_transform is a plotting helper of the reference and is not part of the drop-in")
+def visualize_transform(prevImg: np.ndarray, currImg: np.ndarray, prevFeatureCoord: np.ndarray, newFeatureCoord: np.ndarray,
+                        alpha: float = 1, extraLabel: str = "", show: bool = False) -> None:
+    """getTransformKLT.py:20-73: the tracking overlay Tracker.plot draws (matplotlib is imported only here; plotting is
+    not part of the hot path and touches no device state)."""
+    from matplotlib import pyplot as plt
+    if currImg is not None:
+        plt.imshow(currImg)
+    if newFeatureCoord is not None or alpha == 0:
+        plt.scatter(newFeatureCoord[:, 0], newFeatureCoord[:, 1], marker='+', color='red', alpha=alpha,
+                    label=f'Tracked Features{extraLabel}')
+    if prevFeatureCoord is not None or alpha == 0:
+        plt.scatter(prevFeatureCoord[:, 0], prevFeatureCoord[:, 1], marker='.', color='yellow', alpha=alpha,
+                    label=f'Previous Features{extraLabel}')
+    plt.legend()
+    plt.axis("off")
+    plt.tight_layout()
+    if show:
+        plt.show()

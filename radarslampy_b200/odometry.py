@@ -14,10 +14,12 @@ from .Tracker import Tracker
 from .trajectoryPlotting import Trajectory, convertPoseToTransform
 
 
-def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_flags=None, use_fmt_prior=True):
+def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_flags=None, use_fmt_prior=True, append_features=None):
     """raw_scans: iterable of u8 [A, 11 + bins] scans.  Returns a dict with the estimated Trajectory (`traj`), the
     per-frame relative transforms (`R` [P,2,2], `h` [P,2,1] metres), MDS solutions (`mds_x` [P,6]), per-frame feature
-    counts and the Map of keyframes."""
+    counts and the Map of keyframes.  append_features(cart, old_xy) -> (f32 [K, 2], threshold) replaces
+    getFeatures.appendNewFeatures (the reference's determinant-of-Hessian detector) when given."""
+    append = append_features or appendNewFeatures
     flags = {"rejectOutliers": True, "useFMT": False}
     flags.update(param_flags or {})
     scans = list(raw_scans)
@@ -34,7 +36,7 @@ def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_fl
     prev_pose = convertPoseToTransform(init_pose)
     prev_polar = extractDataFromRadarImage(scans[0])[0]              # RawROAMSystem.py:145-146
     prev_cart = convertRawScanToCartesian(scans[0])                  # = convertPolarImageToCartesian(prev_polar), bit for bit, without re-uploading the f32 polar image
-    blob, _ = appendNewFeatures(prev_cart, np.empty((0, 2)))         # RawROAMSystem.py:149-150
+    blob, _ = append(prev_cart, np.empty((0, 2)))         # RawROAMSystem.py:149-150
     center = Mapping.cartCenter(prev_polar)
     metric = (blob - center) * RANGE_RESOLUTION_CART_M               # RawROAMSystem.py:153
     zero_v = np.zeros((3,))
@@ -76,7 +78,7 @@ def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_fl
             mp.addKeyframe(possible_kf)
             old_kf = possible_kf
             if retrack:
-                good_new, _ = appendNewFeatures(curr_cart, good_new)
+                good_new, _ = append(curr_cart, good_new)
                 centered_new = (good_new - center) * RANGE_RESOLUTION_CART_M
                 old_kf.updateInfo(latest, centered_new, curr_polar, velocity)
             possible_kf = Keyframe(latest, centered_new, curr_polar, velocity)
@@ -90,11 +92,13 @@ def run_odometry(raw_scans, timestamps=None, init_pose=(0.0, 0.0, 0.0), param_fl
     return res
 
 
-def run_odometry_device(sequences, init_pose=None, with_mds=True, graph=True, detector_mode=0, device=None, fe=None):
+def run_odometry_device(sequences, init_pose=None, with_mds=True, graph=True, detector_mode=1, device=None, fe=None):
     """The same loop for several independent sequences at once, entirely on the device (rf_seq, csrc/k_seq.cu):
     features, keyframe state and poses never leave HBM between frames, re-detection (response, NMS, SSC bisection,
     append) runs on the device for exactly the sequences that need it, and a step is one CUDA-graph launch.
 
+    detector_mode 1 (default) is the reference's detector, determinant-of-Hessian blobs (getFeatures.py:13-18; csrc/k_doh.cu);
+    0 is the structure-tensor minimum-eigenvalue response (BASELINE.json north_star; csrc/k_detect.cu).
     sequences: [S][T] raw scans (u8 [A, 11 + bins] each; every sequence has T frames).  with_mds=False gives the pose
     chain without motion compensation (T_wj = prev_pose @ [R, h], RawROAMSystem.py:201; BASELINE configs[1]).
     Returns per-sequence arrays: poses [S, T, 3], R [S, T-1, 2, 2], h [S, T-1, 2, 1], mds_x [S, T-1, 6], n_tracked,

@@ -35,17 +35,36 @@ def convertPolarImageToCartesian(imgPolar: np.ndarray, logPolarMode: bool = Fals
                                  changeGlobalRangeResolution: bool = False) -> np.ndarray:
     """parseData.py:100-135 (cv2.warpPolar, inverse linear map) -> f32 [2R, 2R].  The returned array
     also keeps its device frame (u8 image + LK pyramid) for getTrackedPointsKLT."""
-    if logPolarMode:
-        raise NotImplementedError("inverse log-polar conversion is not used on the hot path (the FMT rotation prior "
-                                  "goes polar -> Cartesian -> log-polar: see convertPolarImgToLogPolar)")
     imgPolar = np.ascontiguousarray(imgPolar, dtype=np.float32)
     A, W = imgPolar.shape
     if changeGlobalRangeResolution:
         global RANGE_RESOLUTION_CART_M
         RANGE_RESOLUTION_CART_M = RANGE_RESOLUTION_M * downsampleFactor
     fe = _engine.engine(range_bins=W, azimuths=A, downsample=max(int(downsampleFactor), 1))
+    if logPolarMode:
+        # parseData.py:131-133 (flags += cv2.WARP_POLAR_LOG): never taken on the reference's live path; a plain array
+        # (no device frame), equal to cv2's within the tolerance of its f32 log (INTEGRATION.md §3)
+        return fe.polar_to_cart_log(imgPolar)
     frame, cart = fe.polar_to_cart(polar=imgPolar)
     return _engine.wrap(cart, fe, frame)
+
+
+def convertCartesianImageToPolar(imgCart: np.ndarray, logPolarMode: bool = False, shapeHW: Tuple[int, int] = None) -> np.ndarray:
+    """parseData.py:69-97 (cv2.warpPolar forward map, linear or semi-log) -> f32 [round(pi n / 2), round(n / 2)] or shapeHW."""
+    imgCart = np.ascontiguousarray(imgCart, dtype=np.float32)
+    h, w = imgCart.shape
+    assert w == h, "Should be a square Cartesian image"
+    return _engine.engine().cart_to_polar(imgCart, log_mode=logPolarMode, shape_hw=shapeHW)
+
+
+def drawCVPoint(img: np.ndarray, point, point_color: Tuple[int, int, int] = (0, 0, 255)):
+    """parseData.py:56-66: cv2.circle(img, point, radius=0, thickness=-1) paints exactly the pixel (x, y), in place."""
+    if hasattr(point, "asTuple"):
+        point = point.asTuple()
+    x, y = int(point[0]), int(point[1])
+    if 0 <= y < img.shape[0] and 0 <= x < img.shape[1]:
+        img[y, x] = point_color if img.ndim == 3 else point_color[0]
+    return img
 
 
 def convertPolarImgToLogPolar(imgPolar: np.ndarray) -> np.ndarray:
@@ -98,3 +117,16 @@ def getRadarImgPaths(dataPath: str, timestampPath: str) -> List[str]:
             if valid:                                  # parseData.py:221 (a non-empty string, so "0" passes too)
                 imgPathArr.append(os.path.join(dataPath, stamp + ".png"))
     return imgPathArr
+
+
+def getRadarStreamPolar(dataPath: str, timestampPath: str) -> np.ndarray:
+    """parseData.py:229-259 -> f32 [A, W, N] stack of the polar images of a sequence (scans decoded in parallel)."""
+    imgPathArr = getRadarImgPaths(dataPath, timestampPath)
+    raws = readRadarScans(imgPathArr)
+    streamArr = None
+    for i in range(len(imgPathArr)):
+        imgPolar = extractDataFromRadarImage(raws[i])[0]
+        if streamArr is None:
+            streamArr = np.empty(imgPolar.shape + (len(imgPathArr),), dtype=imgPolar.dtype)
+        streamArr[:, :, i] = imgPolar
+    return streamArr

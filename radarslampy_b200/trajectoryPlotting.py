@@ -1,6 +1,6 @@
 """Drop-in for the numeric half of the reference's trajectoryPlotting.py: trajectory
 bookkeeping, ground-truth integration, cubic pose interpolation and RMSE.  Same names, arguments and
-return values as trajectoryPlotting.py:11-123,183-213; plotting is out of scope.
+return values as trajectoryPlotting.py:11-123,183-236; the plot functions import matplotlib lazily.
 
 `Trajectory.from_relative_transforms` chains a whole batch of per-pair (R, h) results on the device
 (rf_chain_poses, csrc/k_traj.cu) — the concatenation step of the multi-GPU gather."""
@@ -113,6 +113,20 @@ class Trajectory():
         self.timestamps = np.append(self.timestamps, time)
         self.poses = np.vstack((self.poses, pose))
 
+    def plot(self, title='My Trajectory', savePath=False):
+        """trajectoryPlotting.py:103-113."""
+        from matplotlib import pyplot as plt
+        plt.clf()
+        plt.plot(self.poses[:, 0], self.poses[:, 1], 'b-')
+        plt.xlabel('x [m]')
+        plt.ylabel('y [m]')
+        plt.grid(True)
+        plt.axis('square')
+        plt.title(title)
+        if savePath:
+            plt.tight_layout()
+            plt.savefig(savePath)
+
     def getPoseAtTimes(self, times):
         """Cubic interpolation of x, y, theta at `times`; nearest recorded pose if there are too few points."""
         scalar = np.ndim(times) == 0
@@ -127,6 +141,33 @@ class Trajectory():
         if poses.shape[0] == 1 and scalar and isinstance(times, int):
             poses = poses[0, :]
         return poses
+
+
+def plotGtAndEstTrajectory(gtTraj, estTraj, title='GT and EST Trajectories', info=None, savePath=None, arrow=False):
+    """trajectoryPlotting.py:125-180 (RawROAMSystem.plotTraj draws this; matplotlib is imported only here)."""
+    from matplotlib import pyplot as plt
+    if savePath is not None:
+        plt.clf()
+    t0, t1 = estTraj.timestamps[0], estTraj.timestamps[-1]
+    timestamps = [t for t in gtTraj.timestamps if t0 <= t <= t1]
+    gtPoses, estPoses = gtTraj.getPoseAtTimes(timestamps), estTraj.getPoseAtTimes(timestamps)
+    if arrow:
+        for poses, c, label in ((gtPoses, 'b', "Ground Truth"), (estPoses, 'r', "Estimated")):   # utils.quiver
+            plt.quiver(poses[:, 0], poses[:, 1], np.cos(poses[:, 2]), np.sin(poses[:, 2]), color=c, width=0.02, scale=10, alpha=.5, label=label)
+    else:
+        plt.plot(gtPoses[:, 0], gtPoses[:, 1], 'b-', label='Ground Truth')
+        plt.plot(estPoses[:, 0], estPoses[:, 1], 'r-', label='Estimated')
+    if info is not None:
+        plt.text(0.01, 0.99, info, horizontalalignment='left', verticalalignment='top', transform=plt.gca().transAxes, fontsize='small')
+    plt.xlabel('x [m]')
+    plt.ylabel('y [m]')
+    plt.grid(True)
+    plt.legend()
+    plt.axis('square')
+    plt.title(f'{title}: RMSE={computePosesRMSE(gtPoses, estPoses):.2f}')
+    if savePath:
+        plt.tight_layout()
+        plt.savefig(savePath)
 
 
 def computePosesRMSE(gtPoses, estPoses):
@@ -162,3 +203,14 @@ def getGroundTruthTrajectory(gtPath):
     gt_traj = Trajectory(np.array(gt_timestamps), np.array(gt_poses))
     gt_traj.gt_deltas = d_xyths
     return gt_traj
+
+
+def getGroundTruthTrajectoryGPS(gtPath):
+    """trajectoryPlotting.py:216-236: gps.csv -> Trajectory of (x, y, 0) at the source timestamps."""
+    stamps, poses = [], []
+    with open(gtPath) as f:
+        next(f)                                      # header
+        for row in csv.reader(f):
+            stamps.append(int(row[0]))
+            poses.append([float(row[2]), float(row[3]), 0])
+    return Trajectory(np.array(stamps), np.array(poses))

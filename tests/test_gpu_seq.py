@@ -50,7 +50,7 @@ def test_device_chain_matches_cpu_reference_loop(fe, sequences, with_mds):
     from oracle import ref_system
     T = len(sequences[0])
     init = np.array([[0.0, 0.0, 0.0], [1.5, -2.0, 0.3], [10.0, 5.0, -1.0]])
-    got = odometry.run_odometry_device(sequences, init_pose=init, with_mds=with_mds, graph=True, fe=fe)
+    got = odometry.run_odometry_device(sequences, init_pose=init, with_mds=with_mds, graph=True, detector_mode=0, fe=fe)
     assert np.all(got["status"] == 0)
     det = oracle_detector(fe)
     for s, raw in enumerate(sequences):
@@ -91,13 +91,14 @@ def test_device_chain_features_bit_exact(fe, sequences):
 
 def test_graph_and_eager_steps_are_identical(fe, sequences):
     from radarslampy_b200 import odometry
-    a = odometry.run_odometry_device(sequences[:2], with_mds=True, graph=True, fe=fe)
-    b = odometry.run_odometry_device(sequences[:2], with_mds=True, graph=False, fe=fe)
+    a = odometry.run_odometry_device(sequences[:2], with_mds=True, graph=True, detector_mode=0, fe=fe)
+    b = odometry.run_odometry_device(sequences[:2], with_mds=True, graph=False, detector_mode=0, fe=fe)
     assert a["steps"].tobytes() == b["steps"].tobytes()
 
 
 def test_device_chain_matches_dropin_loop(fe, sequences):
-    """rf_seq against the per-frame drop-in loop (odometry.run_odometry: NumPy in / NumPy out through the C ABI)"""
+    """rf_seq against the per-frame drop-in loop (odometry.run_odometry: NumPy in / NumPy out through the C ABI), both
+    with the reference's detector (determinant of Hessian, detector_mode 1 = the default of both)"""
     from radarslampy_b200 import odometry
     got = odometry.run_odometry_device(sequences[:1], with_mds=True, fe=fe)
     want = odometry.run_odometry(sequences[0], use_fmt_prior=False)
