@@ -924,6 +924,11 @@ __global__ void __launch_bounds__(32 * MC_WARPS) k_maxclique(const MaxCliqueArgs
         int ncol = 0;
         const int n = mc_colour(Pall, adj, RSa, NWe, 1, root, K, lane, &ncol);
         if (lane == 0) { s_best = size; s_nroot = n; s_next = n - 1; if (ncol <= size) s_next = -1; }   // colours == incumbent: optimal
+        // Inlier-dominated graphs (a greedy clique of at least half the vertices): the order-exact walk with its
+        // peeling bound is already short there (chains of universal candidates are taken in one step), while proving
+        // the exact maximum costs a colouring per level of a ~100-deep tree and the colour bound a colouring per pop.
+        // Report "unknown" and let k_clique run on its own bound.
+        if (lane == 0 && 2 * size >= K) { s_fail = 1; s_next = -1; }
     }
     __syncthreads();
     const int nroot = s_nroot;
