@@ -119,7 +119,7 @@ int rf_create(const rf_config* cfg, int device, void* stream, rf_handle** out) {
         cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess)
         return bail(rf_fail(nullptr, RF_E_CUDA, "cudaEventCreate failed"));
     if (cudaMalloc(&h->map, (size_t)h->n * h->n * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&h->map2, (size_t)h->n * h->n * sizeof(uint2)) != cudaSuccess ||
+        cudaMalloc(&h->map2, (size_t)h->n * h->n * sizeof(uint4)) != cudaSuccess ||
         cudaMalloc(&h->d_raw, (size_t)cfg->azimuths * cfg->raw_width) != cudaSuccess ||
         cudaMalloc(&h->d_polar, (size_t)cfg->azimuths * cfg->range_bins * sizeof(float)) != cudaSuccess)
         return bail(rf_fail(nullptr, RF_E_NOMEM, "rf_create: device allocation failed"));
@@ -273,7 +273,7 @@ int rf_frame_download(rf_handle* h, const rf_frame* f, int what, void* out, int*
         if (l < 0 || l >= f->fs.n_levels) return rf_fail(h, RF_E_BADARG, "rf_frame_download: no pyramid level %d", l);
         if (rows) *rows = f->fs.h[l];
         if (cols) *cols = f->fs.w[l];
-        if (out) RF_CUDA(h, cudaMemcpyAsync(out, f->fs.lvl[l], (size_t)f->fs.w[l] * f->fs.h[l], cudaMemcpyDeviceToHost, h->stream));
+        if (out) RF_CUDA(h, cudaMemcpy2DAsync(out, f->fs.w[l], f->fs.lvl[l], f->fs.pitch[l], f->fs.w[l], f->fs.h[l], cudaMemcpyDeviceToHost, h->stream));
     }
     RF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RF_OK;

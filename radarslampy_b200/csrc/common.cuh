@@ -16,9 +16,10 @@
 struct FrameSet {
     float* cart;                   // [count][n][n] f32 (null when the batch path elides it)
     size_t cart_stride;            // elements between frames
-    uint8_t* lvl[RF_MAX_LEVELS];   // u8 pyramid levels, tightly packed rows
-    size_t lvl_stride[RF_MAX_LEVELS];  // bytes between frames
+    uint8_t* lvl[RF_MAX_LEVELS];   // u8 pyramid levels, rows `pitch` bytes apart
+    size_t lvl_stride[RF_MAX_LEVELS];  // bytes between frames (multiple of 256)
     int w[RF_MAX_LEVELS], h[RF_MAX_LEVELS];
+    int pitch[RF_MAX_LEVELS];      // row pitch in bytes: w rounded up to 16 (TMA tensor maps need 16-byte strides)
     int n_levels;
     int count;
 };
@@ -43,7 +44,7 @@ struct rf_handle {
     int sm_count;
     // geometry table: packed fixed-point sample coordinates of cv2.warpPolar's inverse map
     uint32_t* map;  // [n][n]  (sx | sy << 17), sx = round(32*rho), sy = round(32*(phi+1))
-    uint2* map2;    // [n][n]  geometry records of the fused batch path (k_fused.cu)
+    uint4* map2;    // [n][n]  geometry records of the fused batch path (k_fused.cu)
     // staging
     uint8_t* d_raw;      // one raw scan
     float* d_polar;      // one f32 polar image

@@ -547,8 +547,8 @@ int rf_batch_frame_download(rf_handle* h, const rf_batch* b, int frame, int what
         if (l < 0 || l >= b->fs.n_levels) return rf_fail(h, RF_E_BADARG, "rf_batch_frame_download: no pyramid level %d", l);
         if (rows) *rows = b->fs.h[l];
         if (cols) *cols = b->fs.w[l];
-        if (out) RF_CUDA(h, cudaMemcpyAsync(out, b->fs.lvl[l] + (size_t)frame * b->fs.lvl_stride[l],
-                                            (size_t)b->fs.w[l] * b->fs.h[l], cudaMemcpyDeviceToHost, h->stream));
+        if (out) RF_CUDA(h, cudaMemcpy2DAsync(out, b->fs.w[l], b->fs.lvl[l] + (size_t)frame * b->fs.lvl_stride[l], b->fs.pitch[l],
+                                              b->fs.w[l], b->fs.h[l], cudaMemcpyDeviceToHost, h->stream));
     }
     RF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RF_OK;

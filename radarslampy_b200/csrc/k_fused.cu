@@ -44,11 +44,19 @@
 #endif
 #define FT_RW (2 * FT_TW1 + 4)   // 132 region columns: level-0 x in [2*ox1 - 2, 2*ox1 + 130)
 #define FT_RH (2 * FT_TH1 + 3)   // 19 region rows:     level-0 y in [2*oy1 - 2, 2*oy1 + 2*FT_TH1 + 1)
-#define FT_RWW (FT_RW / 4)       // 33 words per region row
+#define FT_RWW (FT_RW / 4)       // 33 words per region row (plain byte tiles of k_pyr_down_w)
+#define FT_ITEMS (FT_RH * FT_RW) // region pixels of one CTA
 #define FT_FR 16                 // frames per CTA (one interleave group)
-#define FT_TILE_WORDS (FT_RH * FT_RWW)
-#define FT_TILE_BYTES (FT_TILE_WORDS * 4)
-#define FT_SMEM_BYTES ((FT_FR * FT_TILE_WORDS + 8 * 64) * 4)   // tiles + 8 per-warp deferred lists
+#define FT_PAIRS (FT_FR / 2)
+// Shared tile of the scan kernel: [FT_PAIRS][FT_ITEMS] u16, byte f & 1 of element (f >> 1, item) = frame f of region pixel item.
+// The blend stores one u16 per frame pair and pixel (neighbouring lanes -> neighbouring elements: one wavefront); the
+// pyramid pass reads four pixels of a pair as one 64-bit word and splits the two frames with a PRMT each.
+#define FT_TILE_BYTES (FT_PAIRS * FT_ITEMS * 2)
+#define FT_LIST_CAP 64           // deferred (pixel, frame flags) entries per warp
+#define FT_LIST_WORDS 7          // item, geometry words x / y, four words of per-frame flag bytes
+#define FT_SMEM_BYTES (FT_TILE_BYTES + 8 * FT_LIST_WORDS * FT_LIST_CAP * 4 + 1024)   // + fl(b / 255) table
+#define FT_OFF_BITS 22           // sample offsets inside one interleave group (A * Wp < 4 M)
+#define FT_OFF_MASK ((1u << FT_OFF_BITS) - 1u)
 
 __device__ __forceinline__ int reflect101_safe(int p, int len) {
     p = min(max(p, -(len - 1)), 2 * len - 2);
@@ -92,10 +100,15 @@ k_interleave16(const uint8_t* __restrict__ raw, size_t frame_stride, int pitch, 
 }
 
 // ------------------------------------------------------------------------------------
-// geometry records
+// geometry records (16 B per Cartesian pixel, built once per handle from the fixed-point inverse map)
+//   x = off0 | fx << 22 | fy << 27     sample offset of tap (iy, ix) inside an interleave group, 5-bit fractions
+//   y = off1 | valid << 22 | ident << 26    offset of tap (iy + 1, ix); tap validity (bit 0: 00, 1: 01, 2: 10, 3: 11)
+//   z = 64 * (m00 | m01 << 16), w = 64 * (m10 | m11 << 16)    m = (32 - fy | fy)(32 - fx | fx), 0 for a tap outside the scan
+// ident marks fx = fy = 0 with tap 00 valid: its weight 64 * 1024 does not fit 16 bits (and every V is a multiple of 1024
+// there), so all sixteen frames of such a pixel go through the exact chain.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_build_map2(const uint32_t* __restrict__ map, size_t count, int A, int W, int Wp, uint2* __restrict__ map2) {
+k_build_map2(const uint32_t* __restrict__ map, size_t count, int A, int W, int Wp, uint4* __restrict__ geo) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const uint32_t m = map[i];
@@ -105,67 +118,71 @@ k_build_map2(const uint32_t* __restrict__ map, size_t count, int A, int W, int W
     int r1 = iy;     r1 = r1 >= A ? r1 - A : r1;
     const bool y0ok = iy < A + 2, y1ok = iy + 1 < A + 2;
     const bool x0ok = ix < W, x1ok = ix + 1 < W;
-    const unsigned flags = (unsigned)(y0ok && x0ok) | ((unsigned)(y0ok && x1ok) << 1) | ((unsigned)(y1ok && x0ok) << 2) |
+    const unsigned valid = (unsigned)(y0ok && x0ok) | ((unsigned)(y0ok && x1ok) << 1) | ((unsigned)(y1ok && x0ok) << 2) |
                            ((unsigned)(y1ok && x1ok) << 3);
     const int ixc = min(ix, Wp - 2);
-    uint2 o;
-    o.x = (unsigned)r0 * (unsigned)Wp + (unsigned)ixc;
-    o.y = (unsigned)(sx & 31) | ((unsigned)(sy & 31) << 5) | (flags << 10) | ((unsigned)(r1 != r0 + 1) << 14);
-    map2[i] = o;
+    const unsigned fx = sx & 31, fy = sy & 31;
+    const unsigned ident = (fx == 0u && fy == 0u && (valid & 1u)) ? 1u : 0u;
+    unsigned m00 = (32u - fy) * (32u - fx), m01 = (32u - fy) * fx, m10 = fy * (32u - fx), m11 = fy * fx;
+    if (!(valid & 1u) || ident) m00 = 0u;
+    if (!(valid & 2u)) m01 = 0u;
+    if (!(valid & 4u)) m10 = 0u;
+    if (!(valid & 8u)) m11 = 0u;
+    uint4 o;
+    // a pixel with no valid tap points at sample 0: its loads are one broadcast line and meet zero weights
+    o.x = (valid ? (unsigned)r0 * (unsigned)Wp + (unsigned)ixc : 0u) | (fx << FT_OFF_BITS) | (fy << (FT_OFF_BITS + 5));
+    o.y = (valid ? (unsigned)r1 * (unsigned)Wp + (unsigned)ixc : 0u) | (valid << FT_OFF_BITS) | (ident << (FT_OFF_BITS + 4));
+    o.z = 64u * (m00 | (m01 << 16));
+    o.w = 64u * (m10 | (m11 << 16));
+    geo[i] = o;
 }
 
 // ------------------------------------------------------------------------------------
-// warp-level pyrDown of one tile held in shared memory (optionally also the level-0 store of it).
-//   tile : [FT_RH][FT_RWW] words = 19 x 132 source bytes; byte (i, j) = source (2*oy1 - 2 + i, 2*ox1 - 2 + j)
-// Lane k owns destination columns ox1 + 2k, 2k + 1: their horizontal 1-4-6-4-1 sums (two u16 per word) of
-// the last five source rows roll through registers, every second row emits one destination row.
-// Writes the FT_TH1 x 64 destination tile at (oy1, ox1); with L0, also source rows 2..2*FT_TH1+1 / bytes 2..129 of the
-// tile to the level-0 image (n x n) as 32 aligned words per row.
+// One row of the warp-level pyrDown: lane k owns destination columns 2k, 2k + 1 of the tile; w0 / w1 are source bytes
+// 4k .. 4k+3 / 4k+4 .. 4k+7 of the row.  Returns the horizontal 1-4-6-4-1 sums of the two columns as two u16.
 // ------------------------------------------------------------------------------------
-// INTERIOR: the whole tile lies inside both images and the destination pitch is even — no per-row or per-lane
-// bounds checks; addresses advance by pointer increments either way.
-template <bool L0, bool INTERIOR, int TH1>
-__device__ __forceinline__ void warp_pyr_tile_impl(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
-                                                   int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
+__device__ __forceinline__ uint32_t pyr_hsum(uint32_t w0, uint32_t w1) {
+    const uint32_t he = __dp4a(w1, 0x00000001u, __dp4a(w0, 0x04060401u, 0u));   // columns 4k .. 4k+4
+    const uint32_t ho = __dp4a(w1, 0x00010406u, __dp4a(w0, 0x04010000u, 0u));   // columns 4k+2 .. 4k+6
+    return he | (ho << 16);
+}
+// vertical 1-4-6-4-1 of five packed row sums, + 128 >> 8, as two bytes (both halves stay below 2^16: 255 * 256 + 128)
+__device__ __forceinline__ uint32_t pyr_vsum(uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t h4) {
+    const uint32_t s = h0 + 4u * h1 + 6u * h2 + 4u * h3 + h4 + 0x00800080u;
+    return __byte_perm(s, 0u, 0x4431);   // (s >> 8) & 0xFF | (s >> 24) << 8
+}
+
+// ------------------------------------------------------------------------------------
+// warp-level pyrDown of one plain byte tile held in shared memory (k_pyr_down_w).
+//   tile : [rows][tile_ww] words; byte (i, j) = source (2*oy1 - 2 + i, 2*ox1 - 2 + j)
+// Writes the TH1 x 64 destination tile at (oy1, ox1); destination rows are `dp` bytes apart (a multiple of 16, so the
+// two-byte store of an odd last column lands in row padding).
+// ------------------------------------------------------------------------------------
+template <bool INTERIOR, int TH1>
+__device__ __forceinline__ void warp_pyr_tile_impl(const uint32_t* __restrict__ tile, int tile_ww, uint8_t* __restrict__ dst, int dp, int dw,
+                                                   int dh, int ox1, int oy1, int lane) {
     const int x = ox1 + 2 * lane;
-    const bool even_pitch = INTERIOR || (dw & 1) == 0;
-    const bool x_ok = INTERIOR || x < dw, x0_ok = INTERIOR || 2 * ox1 + 4 * lane < n;
-    const int rows0 = INTERIOR ? 2 * TH1 : min(2 * TH1, n - 2 * oy1);   // level-0 rows of this tile inside the image
+    const bool x_ok = INTERIOR || x < dw;
     const int rows1 = INTERIOR ? TH1 : min(TH1, dh - oy1);
-    uint8_t* q0 = L0 ? l0 + (size_t)(2 * oy1) * n + 2 * ox1 + 4 * lane : nullptr;
-    uint8_t* q1 = dst + (size_t)oy1 * dw + x;
+    uint8_t* q1 = dst + (size_t)oy1 * dp + x;
     const uint32_t* tp = tile + lane;
     uint32_t h[5];
 #pragma unroll
     for (int r = 0; r < 2 * TH1 + 3; ++r) {
-        const uint32_t w0 = tp[r * FT_RWW], w1 = tp[r * FT_RWW + 1];
-        if (L0 && r >= 2 && r < 2 + 2 * TH1) {
-            if (INTERIOR || (r - 2 < rows0 && x0_ok)) *reinterpret_cast<uint32_t*>(q0) = __funnelshift_r(w0, w1, 16);
-            q0 += n;
-        }
-        const uint32_t he = __dp4a(w1, 0x00000001u, __dp4a(w0, 0x04060401u, 0u));   // columns 4k .. 4k+4
-        const uint32_t ho = __dp4a(w1, 0x00010406u, __dp4a(w0, 0x04010000u, 0u));   // columns 4k+2 .. 4k+6
-        h[r % 5] = he | (ho << 16);
+        h[r % 5] = pyr_hsum(tp[r * tile_ww], tp[r * tile_ww + 1]);
         if (r >= 4 && (r & 1) == 0) {
-            // both halves stay below 2^16 (255 * 256 + 128), so the packed sum never carries across
-            const uint32_t s = h[(r - 4) % 5] + 4u * h[(r - 3) % 5] + 6u * h[(r - 2) % 5] + 4u * h[(r - 1) % 5] + h[r % 5] + 0x00800080u;
-            if (INTERIOR || ((r - 4) / 2 < rows1 && x_ok)) {
-                const uint32_t px2 = __byte_perm(s, 0u, 0x4431);   // (s >> 8) & 0xFF | (s >> 24) << 8
-                if (even_pitch) *reinterpret_cast<uint16_t*>(q1) = (uint16_t)px2;
-                else { q1[0] = (uint8_t)px2; if (x + 1 < dw) q1[1] = (uint8_t)(px2 >> 8); }
-            }
-            q1 += dw;
+            const uint32_t px2 = pyr_vsum(h[(r - 4) % 5], h[(r - 3) % 5], h[(r - 2) % 5], h[(r - 1) % 5], h[r % 5]);
+            if (INTERIOR || ((r - 4) / 2 < rows1 && x_ok)) *reinterpret_cast<uint16_t*>(q1) = (uint16_t)px2;
+            q1 += dp;
         }
     }
 }
 
-template <bool L0, int TH1>
-__device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dw, int dh,
-                                              int ox1, int oy1, int lane, uint8_t* __restrict__ l0, int n) {
-    const bool interior = (dw & 1) == 0 && ox1 + FT_TW1 <= dw && oy1 + TH1 <= dh &&
-                          (!L0 || (2 * ox1 + 2 * FT_TW1 <= n && 2 * oy1 + 2 * TH1 <= n));
-    if (interior) warp_pyr_tile_impl<L0, true, TH1>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
-    else warp_pyr_tile_impl<L0, false, TH1>(tile, dst, dw, dh, ox1, oy1, lane, l0, n);
+template <int TH1>
+__device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile, int tile_ww, uint8_t* __restrict__ dst, int dp, int dw, int dh,
+                                              int ox1, int oy1, int lane) {
+    if (ox1 + FT_TW1 <= dw && oy1 + TH1 <= dh) warp_pyr_tile_impl<true, TH1>(tile, tile_ww, dst, dp, dw, dh, ox1, oy1, lane);
+    else warp_pyr_tile_impl<false, TH1>(tile, tile_ww, dst, dp, dw, dh, ox1, oy1, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -174,207 +191,243 @@ __device__ __forceinline__ void warp_pyr_tile(const uint32_t* __restrict__ tile,
 struct FusedArgs {
     const uint4* rawi; size_t group_stride;   // samples per interleave group plane (A * Wp)
     int Wp, A;
-    const uint2* map2; int n;
-    uint8_t* l0; size_t l0_stride;
-    uint8_t* l1; size_t l1_stride; int w1, h1;
+    const uint4* geo; int n;
+    uint8_t* l0; size_t l0_stride; int p0;            // level 0: frame stride, row pitch
+    uint8_t* l1; size_t l1_stride; int p1, w1, h1;    // level 1
     int n_frames;
 };
 
 __device__ float g_lut255[256];   // fl(b / 255), parseData.py:43 (filled by k_build_lut at handle creation)
 
-__device__ uint8_t g_lut_id[256];  // trunc(fl(fl(b / 255) * 255)): parseData.py:43 followed by getTransformKLT.py:356-357
-
 __global__ void k_build_lut() {
-    const float s = __fdiv_rn((float)threadIdx.x, 255.0f);
-    g_lut255[threadIdx.x] = s;
-    g_lut_id[threadIdx.x] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(s, 255.0f), 8388608.0f));
+    g_lut255[threadIdx.x] = __fdiv_rn((float)threadIdx.x, 255.0f);
 }
 
-// V (the 10-bit fixed-point bilinear sum, <= 255 * 1024) for the four frames of one tap word.
+// the two frames of one pair of the scan tile, pyrDown'ed and stored together (level 0 rows 2 .. 2*FT_TH1+1 of the tile as
+// 32 aligned words per row and frame; level 1 as two bytes per lane, row and frame)
+template <bool INTERIOR>
+__device__ __forceinline__ void warp_pyr_pair_impl(const uint16_t* __restrict__ tp, const FusedArgs& a, int frame, int nb, int ox1, int oy1,
+                                                   int lane) {
+    const int x = ox1 + 2 * lane;
+    const bool x_ok = INTERIOR || x < a.w1, x0_ok = INTERIOR || 2 * ox1 + 4 * lane < a.n;
+    const int rows0 = INTERIOR ? 2 * FT_TH1 : min(2 * FT_TH1, a.n - 2 * oy1);   // level-0 rows of this tile inside the image
+    const int rows1 = INTERIOR ? FT_TH1 : min(FT_TH1, a.h1 - oy1);
+    uint8_t* q0 = a.l0 + (size_t)frame * a.l0_stride + (size_t)(2 * oy1) * a.p0 + 2 * ox1 + 4 * lane;
+    uint8_t* q1 = a.l1 + (size_t)frame * a.l1_stride + (size_t)oy1 * a.p1 + x;
+    const bool two = nb > 1;
+    const uint2* rp = reinterpret_cast<const uint2*>(tp) + lane;   // four pixels x two frames per 64-bit word
+    uint32_t hA[5], hB[5];
+#pragma unroll
+    for (int r = 0; r < FT_RH; ++r) {
+        const uint2 u = rp[r * FT_RWW], v = rp[r * FT_RWW + 1];
+        const uint32_t a0 = __byte_perm(u.x, u.y, 0x6420), b0 = __byte_perm(u.x, u.y, 0x7531);
+        const uint32_t a1 = __byte_perm(v.x, v.y, 0x6420), b1 = __byte_perm(v.x, v.y, 0x7531);
+        if (r >= 2 && r < 2 + 2 * FT_TH1) {
+            if (INTERIOR || (r - 2 < rows0 && x0_ok)) {
+                *reinterpret_cast<uint32_t*>(q0) = __funnelshift_r(a0, a1, 16);
+                if (two) *reinterpret_cast<uint32_t*>(q0 + a.l0_stride) = __funnelshift_r(b0, b1, 16);
+            }
+            q0 += a.p0;
+        }
+        hA[r % 5] = pyr_hsum(a0, a1);
+        hB[r % 5] = pyr_hsum(b0, b1);
+        if (r >= 4 && (r & 1) == 0) {
+            const uint32_t pa = pyr_vsum(hA[(r - 4) % 5], hA[(r - 3) % 5], hA[(r - 2) % 5], hA[(r - 1) % 5], hA[r % 5]);
+            const uint32_t pb = pyr_vsum(hB[(r - 4) % 5], hB[(r - 3) % 5], hB[(r - 2) % 5], hB[(r - 1) % 5], hB[r % 5]);
+            if (INTERIOR || ((r - 4) / 2 < rows1 && x_ok)) {
+                *reinterpret_cast<uint16_t*>(q1) = (uint16_t)pa;
+                if (two) *reinterpret_cast<uint16_t*>(q1 + a.l1_stride) = (uint16_t)pb;
+            }
+            q1 += a.p1;
+        }
+    }
+}
+
+// the four taps (16 frames each) of one pixel
+struct Taps { uint4 t00, t01, t10, t11; };
+__device__ __forceinline__ Taps load_taps(const uint4* __restrict__ src, uint4 m) {
+    const uint4* p0 = src + (m.x & FT_OFF_MASK);
+    const uint4* p1 = src + (m.y & FT_OFF_MASK);
+    Taps t;
+    t.t00 = __ldg(p0); t.t01 = __ldg(p0 + 1); t.t10 = __ldg(p1); t.t11 = __ldg(p1 + 1);
+    return t;
+}
+
+// 4-bit "byte is non-zero" mask of a word whose bytes are 0 or a single bit
+__device__ __forceinline__ uint32_t nz_nibble(uint32_t a) {
+    const uint32_t m = (((a + 0x7F7F7F7Fu) | a) & 0x80808080u) >> 7;   // bit 8i = byte i != 0
+    return ((m * 0x00204081u) >> 21) & 15u;                             // bit 8i -> bit 21 + i (no two terms collide)
+}
+
+// byte f (0 .. 15) of a 16-frame tap
+__device__ __forceinline__ uint32_t tap_byte(const uint4& t, uint32_t sel, bool hi) {
+    return (hi ? __byte_perm(t.z, t.w, sel) : __byte_perm(t.x, t.y, sel)) & 0xFFu;
+}
+
+// cv2's f32 chain for the flagged frames of one pixel (deferred list entry `slot` of this warp).  The entry carries the
+// pixel's geometry words, so nothing but the four taps is fetched again (one round trip for all sixteen frames: the
+// shared-memory carve-out leaves too little L1 for the lines to have survived), and fl(b / 255) comes from shared memory.
+__device__ __forceinline__ void exact_item(const uint4* __restrict__ src, const uint32_t* __restrict__ list, int slot,
+                                           uint8_t* __restrict__ tile_bytes, const float* __restrict__ lut) {
+    const int item = (int)list[slot];
+    const uint32_t mx = list[FT_LIST_CAP + slot], my = list[2 * FT_LIST_CAP + slot];
+    const uint4* p0 = src + (mx & FT_OFF_MASK);
+    const uint4* p1 = src + (my & FT_OFF_MASK);
+    const uint4 t00 = __ldg(p0), t01 = __ldg(p0 + 1), t10 = __ldg(p1), t11 = __ldg(p1 + 1);
+    uint32_t mask = nz_nibble(list[3 * FT_LIST_CAP + slot]) | (nz_nibble(list[4 * FT_LIST_CAP + slot]) << 4) |
+                    (nz_nibble(list[5 * FT_LIST_CAP + slot]) << 8) | (nz_nibble(list[6 * FT_LIST_CAP + slot]) << 12);
+    const unsigned fx = (mx >> FT_OFF_BITS) & 31u, fy = mx >> (FT_OFF_BITS + 5), fl = (my >> FT_OFF_BITS) & 15u;
+    // (1 - fy)(1 - fx) etc. are exact multiples of 2^-10, as cv2 computes them; a tap outside the source has weight 0
+    const float w00 = (fl & 1u) ? (float)((32u - fy) * (32u - fx)) * 0.0009765625f : 0.0f;
+    const float w01 = (fl & 2u) ? (float)((32u - fy) * fx) * 0.0009765625f : 0.0f;
+    const float w10 = (fl & 4u) ? (float)(fy * (32u - fx)) * 0.0009765625f : 0.0f;
+    const float w11 = (fl & 8u) ? (float)(fy * fx) * 0.0009765625f : 0.0f;
+    uint8_t* out = tile_bytes + 2 * item;
+    while (mask) {
+        const int f = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const uint32_t sel = f & 7;
+        const bool hi = (f & 8) != 0;
+        float acc = __fmul_rn(lut[tap_byte(t00, sel, hi)], w00);
+        acc = __fadd_rn(acc, __fmul_rn(lut[tap_byte(t01, sel, hi)], w01));
+        acc = __fadd_rn(acc, __fmul_rn(lut[tap_byte(t10, sel, hi)], w10));
+        acc = __fadd_rn(acc, __fmul_rn(lut[tap_byte(t11, sel, hi)], w11));
+        // (img * 255).astype(uint8): f32 product, truncation; 2^23 + x rounded toward zero keeps floor(x) in the low byte
+        out[(f >> 1) * (2 * FT_ITEMS) + (f & 1)] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(acc, 255.0f), 8388608.0f));
+    }
+}
+
+// v = 64 V (V the 10-bit fixed-point bilinear sum, v < 2^24) for the four frames of one tap word:
 //   c0r0, c1r0 / c0r1, c1r1   left, right column taps of the upper / lower source row (byte f = frame 4q + f)
-//   wtop = w00 | w01 << 16, wbot = w10 | w11 << 16    the four integer weights m = (32 - fy | fy)(32 - fx | fx)
 // One PRMT pairs the two taps of a row for two frames, one dp2a (u16 weights x u8 samples) per frame and row
-// accumulates them.  The u8 result is V >> 10; V is a multiple of 1024 exactly when its low 10 bits are 0.
-// Such frames (V != 0) are flagged in `need` and redone with cv2's f32 chain.
+// accumulates them.  The u8 result floor(V / 1024) is byte 2 of v.  V is a non-zero multiple of 1024 exactly when the
+// lowest set bit of v is bit 16 or above: byte 2 of v & -v is then non-zero, and those bytes (one per frame) are what
+// the deferred list keeps.
 #define FT_QUAD(q, c0r0, c0r1, c1r0, c1r1)                                                                        \
     {                                                                                                             \
         const uint32_t ta = __byte_perm((c0r0), (c1r0), 0x5140), tb4 = __byte_perm((c0r0), (c1r0), 0x7362);       \
         const uint32_t ba = __byte_perm((c0r1), (c1r1), 0x5140), bb = __byte_perm((c0r1), (c1r1), 0x7362);        \
-        const uint32_t v4[4] = {__dp2a_lo(wbot, ba, __dp2a_lo(wtop, ta, 0u)), __dp2a_hi(wbot, ba, __dp2a_hi(wtop, ta, 0u)), \
-                                __dp2a_lo(wbot, bb, __dp2a_lo(wtop, tb4, 0u)), __dp2a_hi(wbot, bb, __dp2a_hi(wtop, tb4, 0u))}; \
-        _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                                           \
-            if ((v4[f] & 0x3FFu) == 0u && v4[f] != 0u) need |= 1u << (4 * (q) + f);                               \
-            tb[(4 * (q) + f) * FT_TILE_BYTES] = (uint8_t)(v4[f] >> 10);                                           \
+        const uint32_t v0 = __dp2a_lo(wbot, ba, __dp2a_lo(wtop, ta, 0u)), v1 = __dp2a_hi(wbot, ba, __dp2a_hi(wtop, ta, 0u));   \
+        const uint32_t v2 = __dp2a_lo(wbot, bb, __dp2a_lo(wtop, tb4, 0u)), v3 = __dp2a_hi(wbot, bb, __dp2a_hi(wtop, tb4, 0u)); \
+        if (st) {                                                                                                 \
+            tp[(2 * (q)) * FT_ITEMS] = (uint16_t)__byte_perm(v0, v1, 0x3362);                                     \
+            tp[(2 * (q) + 1) * FT_ITEMS] = (uint16_t)__byte_perm(v2, v3, 0x3362);                                 \
         }                                                                                                         \
+        const uint32_t l0 = v0 & (0u - v0), l1 = v1 & (0u - v1), l2 = v2 & (0u - v2), l3 = v3 & (0u - v3);        \
+        acc[q] = __byte_perm(__byte_perm(l0, l1, 0x3362), __byte_perm(l2, l3, 0x3362), 0x5410);                   \
     }
 
-struct PixelGeom {
-    const uint4 *p0, *p1;      // sample (iy, ix) and (iy + 1, ix) of the interleave group
-    unsigned fx, fy, fl;       // 5-bit fractions, tap validity (bit 0: 00, 1: 01, 2: 10, 3: 11)
-};
-
-// geometry record of region item `item` (REFLECT_101 at the image border: the pyrDown halo)
-__device__ __forceinline__ uint2 load_geom(const FusedArgs& a, int item, int ox1, int oy1) {
-    const int ry = item / FT_RW, rx = item - ry * FT_RW;
-    const int gy = reflect101_safe(2 * oy1 - 2 + ry, a.n), gx = reflect101_safe(2 * ox1 - 2 + rx, a.n);
-    return __ldg(a.map2 + (unsigned)(gy * a.n + gx));
-}
-
-__device__ __forceinline__ PixelGeom decode_geom(const FusedArgs& a, const uint4* __restrict__ src, uint2 m) {
-    PixelGeom g;
-    g.fx = m.y & 31u; g.fy = (m.y >> 5) & 31u; g.fl = (m.y >> 10) & 15u;
-    g.p0 = src + m.x;
-    g.p1 = g.p0 + a.Wp - ((m.y & 0x4000u) ? (unsigned)a.A * (unsigned)a.Wp : 0u);
-    return g;
-}
-
-__device__ __forceinline__ PixelGeom pixel_geom(const FusedArgs& a, const uint4* __restrict__ src, int item, int ox1, int oy1) {
-    return decode_geom(a, src, load_geom(a, item, ox1, oy1));
-}
-
-// the four taps (16 frames each) of one pixel; nothing is loaded for a pixel with no valid tap
-struct Taps { uint4 t00, t01, t10, t11; };
-__device__ __forceinline__ Taps load_taps(const FusedArgs& a, const uint4* __restrict__ src, uint2 m) {
-    Taps t;
-    t.t00 = t.t01 = t.t10 = t.t11 = make_uint4(0u, 0u, 0u, 0u);
-    if ((m.y >> 10) & 15u) {
-        const PixelGeom g = decode_geom(a, src, m);
-        t.t00 = __ldg(g.p0); t.t01 = __ldg(g.p0 + 1); t.t10 = __ldg(g.p1); t.t11 = __ldg(g.p1 + 1);
-    }
-    return t;
-}
-
-// cv2's f32 chain for the flagged frames of one pixel: entry = item | frame mask << 13
-__device__ __forceinline__ void exact_item(const FusedArgs& a, const uint4* __restrict__ src, uint32_t entry, int ox1, int oy1,
-                                           uint8_t* __restrict__ tile_bytes) {
-    const int item = entry & 0x1FFF;
-    uint32_t mask = entry >> 13;
-    const PixelGeom g = pixel_geom(a, src, item, ox1, oy1);
-    // (1 - fy)(1 - fx) etc. are exact multiples of 2^-10, as cv2 computes them; a tap outside the source has weight 0
-    const float w00 = (g.fl & 1u) ? (float)((32u - g.fy) * (32u - g.fx)) * 0.0009765625f : 0.0f;
-    const float w01 = (g.fl & 2u) ? (float)((32u - g.fy) * g.fx) * 0.0009765625f : 0.0f;
-    const float w10 = (g.fl & 4u) ? (float)(g.fy * (32u - g.fx)) * 0.0009765625f : 0.0f;
-    const float w11 = (g.fl & 8u) ? (float)(g.fy * g.fx) * 0.0009765625f : 0.0f;
-    const uint8_t* b0 = reinterpret_cast<const uint8_t*>(g.p0);
-    const uint8_t* b1 = reinterpret_cast<const uint8_t*>(g.p1);
-    uint8_t* out = tile_bytes + item;
-    while (mask) {
-        const int f = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        float acc = __fmul_rn(g_lut255[__ldg(b0 + f)], w00);
-        acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b0 + f + 16)], w01));
-        acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1 + f)], w10));
-        acc = __fadd_rn(acc, __fmul_rn(g_lut255[__ldg(b1 + f + 16)], w11));
-        // (img * 255).astype(uint8): f32 product, truncation; 2^23 + x rounded toward zero keeps floor(x) in the low byte
-        out[f * FT_TILE_BYTES] = (uint8_t)__float_as_uint(__fadd_rz(__fmul_rn(acc, 255.0f), 8388608.0f));
-    }
-}
-
-#define FT_LIST_CAP 64   // deferred (pixel, frame) entries per warp
-
-__global__ void __launch_bounds__(256, FT_SCAN_MIN_BLOCKS) k_scan16_to_l0l1(const FusedArgs a) {
-    extern __shared__ uint32_t smem[];
-    uint32_t* tiles = smem;                                  // [FT_FR][FT_RH][FT_RWW]
-    uint32_t* lists = tiles + FT_FR * FT_TILE_WORDS;         // [8 warps][FT_LIST_CAP]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // frame group fastest: the CTAs resident at any time share one neighbourhood of the geometry table
-    const int ox1 = blockIdx.y * FT_TW1, oy1 = blockIdx.z * FT_TH1;
-    const int f0 = blockIdx.x * FT_FR;
-    const uint4* __restrict__ src = a.rawi + (size_t)blockIdx.x * a.group_stride;
-    uint8_t* tile_bytes = reinterpret_cast<uint8_t*>(tiles);
-    uint32_t* list = lists + warp * FT_LIST_CAP;
+template <bool INTERIOR>
+__device__ __forceinline__ void scan_blend(const FusedArgs& a, const uint4* __restrict__ src, uint16_t* __restrict__ tile, uint32_t* __restrict__ list,
+                                           const float* __restrict__ lut, int ox1, int oy1, int tid, int lane) {
+    uint8_t* tile_bytes = reinterpret_cast<uint8_t*>(tile);
     int cnt = 0;                                             // warp-uniform fill of `list`
     const unsigned lt = (1u << lane) - 1u;
-
     // Two-deep software pipeline over the CTA's FT_RH x 132 region pixels (one per thread and step): while pixel `it`
     // is blended, the taps of pixel it + 1 and the geometry record of pixel it + 2 are in flight, so neither of
     // the two dependent gathers (L2-resident record -> scan samples) is waited for.
-    constexpr int NIT = (FT_RH * FT_RW + 255) / 256;
+    constexpr int NIT = (FT_ITEMS + 255) / 256;
     // region coordinates of the next geometry fetch; they advance by 256 items = one row + 124 columns.
-    // (A 4 x 8 pixel patch per warp instead of a 32 x 1 strip was measured: 4 % fewer L1 wavefronts, 9 % more
-    // instructions from the ragged 33 x 5 patch grid, 5 % slower.)
     int gry = tid / FT_RW, grx = tid - gry * FT_RW;
     int gitem = tid;
-    auto next_geom = [&](int& item) -> uint2 {
-        uint2 m = make_uint2(0u, 0u);                        // fl == 0: no taps
+    const uint4* gp = a.geo + ((long long)(2 * oy1 - 2 + gry) * a.n + (2 * ox1 - 2 + grx));   // INTERIOR: walks the table directly
+    auto next_geom = [&](int& item) -> uint4 {
+        uint4 m = make_uint4(0u, 0u, 0u, 0u);                // no valid tap, zero weights, sample 0
         item = -1;
-        if (gitem < FT_RH * FT_RW) {
+        if (gitem < FT_ITEMS) {
             item = gitem;
-            const int gy = reflect101_safe(2 * oy1 - 2 + gry, a.n), gx = reflect101_safe(2 * ox1 - 2 + grx, a.n);
-            m = __ldg(a.map2 + (unsigned)(gy * a.n + gx));
+            if (INTERIOR) m = __ldg(gp);
+            else {
+                const int gy = reflect101_safe(2 * oy1 - 2 + gry, a.n), gx = reflect101_safe(2 * ox1 - 2 + grx, a.n);
+                m = __ldg(a.geo + (unsigned)(gy * a.n + gx));
+            }
         }
-        gitem += 256; grx += 256 - FT_RW; gry += 1;
-        if (grx >= FT_RW) { grx -= FT_RW; gry += 1; }
+        gitem += 256; grx += 256 - FT_RW; gry += 1; gp += a.n + 256 - FT_RW;
+        if (grx >= FT_RW) { grx -= FT_RW; gry += 1; gp += a.n - FT_RW; }
         return m;
     };
     // blend one region pixel for the 16 frames of the group, then queue its flagged frames
-    auto step = [&](const int item, const uint2 m, const Taps& T) {
-        uint32_t need = 0u;
-        if (item >= 0) {
-            const unsigned fx = m.y & 31u, fy = (m.y >> 5) & 31u, fl = (m.y >> 10) & 15u;
-            uint8_t* tb = tile_bytes + item;
-            if (fl == 0u) {   // beyond the last range bin (image corners): WARP_FILL_OUTLIERS
+    auto step = [&](const int item, const uint4 m, const Taps& T) {
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+        const bool st = item >= 0;
+        uint16_t* tp = tile + (st ? item : 0);
+        // beyond the last range bin (image corners, WARP_FILL_OUTLIERS) whole warps have no valid tap: store zeros
+        if (__any_sync(0xffffffffu, (m.y >> FT_OFF_BITS) & 15u)) {
+            const uint32_t wtop = m.z, wbot = m.w;
+            FT_QUAD(0, T.t00.x, T.t10.x, T.t01.x, T.t11.x)
+            FT_QUAD(1, T.t00.y, T.t10.y, T.t01.y, T.t11.y)
+            FT_QUAD(2, T.t00.z, T.t10.z, T.t01.z, T.t11.z)
+            FT_QUAD(3, T.t00.w, T.t10.w, T.t01.w, T.t11.w)
+            if (m.y & (1u << (FT_OFF_BITS + 4))) acc[0] = acc[1] = acc[2] = acc[3] = 0x01010101u;   // ident: all frames exact
+        } else if (st) {
 #pragma unroll
-                for (int f = 0; f < FT_FR; ++f) tb[f * FT_TILE_BYTES] = 0;
-            } else if ((m.y & 0x7FFu) == 0x400u) {
-                // fx = fy = 0 and tap 00 valid: the weights are 1, 0, 0, 0 and cv2's chain collapses to
-                // trunc(fl(fl(b / 255) * 255)) of that one sample (every such V is a multiple of 1024)
-                const uint32_t q[4] = {T.t00.x, T.t00.y, T.t00.z, T.t00.w};
-#pragma unroll
-                for (int f = 0; f < FT_FR; ++f) tb[f * FT_TILE_BYTES] = g_lut_id[(q[f >> 2] >> (8 * (f & 3))) & 0xFFu];
-            } else {
-                uint4 T00 = T.t00, T01 = T.t01, T10 = T.t10, T11 = T.t11;
-                if (fl != 15u) {   // a tap outside the source contributes 0
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    if (!(fl & 1u)) T00 = z; if (!(fl & 2u)) T01 = z; if (!(fl & 4u)) T10 = z; if (!(fl & 8u)) T11 = z;
-                }
-                const uint32_t wy0 = 32u - fy, wx0 = 32u - fx;
-                const uint32_t wtop = wy0 * wx0 | (wy0 * fx) << 16, wbot = fy * wx0 | (fy * fx) << 16;
-                FT_QUAD(0, T00.x, T10.x, T01.x, T11.x)
-                FT_QUAD(1, T00.y, T10.y, T01.y, T11.y)
-                FT_QUAD(2, T00.z, T10.z, T01.z, T11.z)
-                FT_QUAD(3, T00.w, T10.w, T01.w, T11.w)
-            }
+            for (int p = 0; p < FT_PAIRS; ++p) tp[p * FT_ITEMS] = 0;
         }
-        // Defer the flagged frames: a lane appends ONE entry (pixel, frame mask) to the warp's list, and whenever 32
+        // Defer the flagged frames: a lane appends ONE entry (pixel, flag bytes) to the warp's list, and whenever 32
         // are waiting the whole warp redoes them with the f32 chain, one pixel per lane.
-        const unsigned pending = __ballot_sync(0xffffffffu, need != 0u);
+        const bool flagged = (acc[0] | acc[1] | acc[2] | acc[3]) != 0u;
+        const unsigned pending = __ballot_sync(0xffffffffu, flagged);
         if (pending) {
-            if (need) list[cnt + __popc(pending & lt)] = (uint32_t)item | (need << 13);
+            if (flagged) {
+                const int slot = cnt + __popc(pending & lt);
+                list[slot] = (uint32_t)item;
+                list[FT_LIST_CAP + slot] = m.x; list[2 * FT_LIST_CAP + slot] = m.y;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) list[(q + 3) * FT_LIST_CAP + slot] = acc[q];
+            }
             cnt += __popc(pending);
             __syncwarp();
             if (cnt >= 32) {
                 cnt -= 32;
-                exact_item(a, src, list[cnt + lane], ox1, oy1, tile_bytes);
+                exact_item(src, list, cnt + lane, tile_bytes, lut);
                 __syncwarp();
             }
         }
     };
     int iA, iB, iC, iD;
-    uint2 mA = next_geom(iA);
-    Taps TA = load_taps(a, src, mA);
-    uint2 mB = next_geom(iB);
+    uint4 mA = next_geom(iA);
+    Taps TA = load_taps(src, mA);
+    uint4 mB = next_geom(iB);
 #pragma unroll 1
     for (int it = 0; it + 1 < NIT; it += 2) {
-        const Taps TB = load_taps(a, src, mB);
-        const uint2 mC = next_geom(iC);
+        const Taps TB = load_taps(src, mB);
+        const uint4 mC = next_geom(iC);
         step(iA, mA, TA);
-        TA = load_taps(a, src, mC);
-        const uint2 mD = next_geom(iD);
+        TA = load_taps(src, mC);
+        const uint4 mD = next_geom(iD);
         step(iB, mB, TB);
         mA = mC; mB = mD; iA = iC; iB = iD;
     }
     if (NIT & 1) step(iA, mA, TA);
-    if (lane < cnt) exact_item(a, src, list[lane], ox1, oy1, tile_bytes);
+    if (lane < cnt) exact_item(src, list, lane, tile_bytes, lut);
+}
+
+__global__ void __launch_bounds__(256, FT_SCAN_MIN_BLOCKS) k_scan16_to_l0l1(const FusedArgs a) {
+    extern __shared__ uint4 smem4[];
+    uint16_t* tile = reinterpret_cast<uint16_t*>(smem4);                                           // [FT_PAIRS][FT_ITEMS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* list = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(smem4) + FT_TILE_BYTES) + warp * FT_LIST_WORDS * FT_LIST_CAP;
+    float* lut = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(smem4) + FT_TILE_BYTES + 8 * FT_LIST_WORDS * FT_LIST_CAP * 4);
+    lut[tid] = g_lut255[tid];   // fl(b / 255) for the exact chain
+    __syncthreads();
+    // frame group fastest: the CTAs resident at any time share one neighbourhood of the geometry table
+    const int ox1 = blockIdx.y * FT_TW1, oy1 = blockIdx.z * FT_TH1;
+    const int f0 = blockIdx.x * FT_FR;
+    const uint4* src = a.rawi + (size_t)blockIdx.x * a.group_stride;
+    asm volatile("" : "+l"(src));   // keep the group base in a register pair: tap addresses are then one IMAD.WIDE each
+    // the whole region (tile + pyrDown halo) inside the image: no REFLECT_101 on the record fetch, no bounds on the stores
+    const bool interior = 2 * ox1 - 2 >= 0 && 2 * oy1 - 2 >= 0 && 2 * ox1 - 2 + FT_RW <= a.n && 2 * oy1 - 2 + FT_RH <= a.n &&
+                          ox1 + FT_TW1 <= a.w1 && oy1 + FT_TH1 <= a.h1;
+    if (interior) scan_blend<true>(a, src, tile, list, lut, ox1, oy1, tid, lane);
+    else scan_blend<false>(a, src, tile, list, lut, ox1, oy1, tid, lane);
     __syncthreads();
 
-    // one warp per frame from here on (two frames per warp): level-0 store + level 1 from the shared-memory tile
-#pragma unroll 1
-    for (int fw = warp; fw < FT_FR; fw += 8) {
-        const int frame = f0 + fw;
-        if (frame >= a.n_frames) break;
-        warp_pyr_tile<true, FT_TH1>(tiles + fw * FT_TILE_WORDS, a.l1 + (size_t)frame * a.l1_stride, a.w1, a.h1, ox1, oy1, lane,
-                            a.l0 + (size_t)frame * a.l0_stride, a.n);
+    // one warp per frame pair from here on: level-0 store + level 1 from the shared-memory tile
+    const int frame = f0 + 2 * warp;
+    if (frame < a.n_frames) {
+        const int nb = min(2, a.n_frames - frame);
+        if (interior) warp_pyr_pair_impl<true>(tile + warp * FT_ITEMS, a, frame, nb, ox1, oy1, lane);
+        else warp_pyr_pair_impl<false>(tile + warp * FT_ITEMS, a, frame, nb, ox1, oy1, lane);
     }
 }
 
@@ -393,8 +446,8 @@ __global__ void __launch_bounds__(256, FT_SCAN_MIN_BLOCKS) k_scan16_to_l0l1(cons
 #define FT_PYR_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(128, FT_PYR_MIN_BLOCKS)
-k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh, uint8_t* __restrict__ dst,
-             size_t dst_stride, int dw, int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
+k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sp, int sw, int sh, uint8_t* __restrict__ dst,
+             size_t dst_stride, int dp, int dw, int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
     __shared__ uint32_t s_tile[4][FT_PYR_TILE_WORDS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = blockIdx.x * 4 + warp;
@@ -416,9 +469,9 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
         // byte-aligned (odd widths at the higher levels), so each region word is cut out of two aligned loads.
         const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3u);
         const uint32_t* __restrict__ s4 = reinterpret_cast<const uint32_t*>(s - mis) + lane;   // aligned frame base
-        unsigned off = mis + (unsigned)(2 * oy1 - 2) * (unsigned)sw + (unsigned)x0;             // byte offset of the row's region
+        unsigned off = mis + (unsigned)(2 * oy1 - 2) * (unsigned)sp + (unsigned)x0;             // byte offset of the row's region
 #pragma unroll 5
-        for (int r = 0; r < FT_PYR_RH; ++r, off += sw) {
+        for (int r = 0; r < FT_PYR_RH; ++r, off += sp) {
             const uint32_t* ap = s4 + (off >> 2);
             const unsigned sh8 = 8u * (off & 3u);
             tw[r * FT_RWW + lane] = __funnelshift_r(__ldg(ap), __ldg(ap + 1), sh8);
@@ -428,7 +481,7 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     const bool in_k = xk >= 0 && xk + 3 < sw, in_32 = xk32 + 3 < sw;
 #pragma unroll 5
     for (int r = 0; r < FT_PYR_RH; ++r) {
-        const uint8_t* row = s + (size_t)reflect101_safe(2 * oy1 - 2 + r, sh) * sw;
+        const uint8_t* row = s + (size_t)reflect101_safe(2 * oy1 - 2 + r, sh) * sp;
         const uint8_t* p = row + x0;
         const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
         const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
@@ -457,7 +510,7 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sw, int sh,
     }
     }
     __syncwarp();
-    warp_pyr_tile<false, FT_PYR_TH1>(s_tile[warp], dst + (size_t)frame * dst_stride, dw, dh, ox1, oy1, lane, nullptr, 0);
+    warp_pyr_tile<FT_PYR_TH1>(s_tile[warp], FT_RWW, dst + (size_t)frame * dst_stride, dp, dw, dh, ox1, oy1, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -467,6 +520,7 @@ int rf_fused_wp(const rf_handle* h) { return ((h->cfg.range_bins + 1) + 3) & ~3;
 
 int rf_launch_build_map2(rf_handle* h) {
     const size_t count = (size_t)h->n * h->n;
+    if ((size_t)h->cfg.azimuths * rf_fused_wp(h) > (size_t)FT_OFF_MASK) return RF_OK;   // no fused path for this geometry (rf_launch_scan_to_l0l1 refuses)
     k_build_map2<<<(unsigned)((count + 255) / 256), 256, 0, h->stream>>>(h->map, count, h->cfg.azimuths, h->cfg.range_bins,
                                                                           rf_fused_wp(h), h->map2);
     RF_CHECK_LAUNCH(h);
@@ -494,6 +548,9 @@ size_t rf_interleave_words(const rf_handle* h, int max_frames) {
 int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet& fs, int n_frames) {
     if (h->n % 4) return rf_fail(h, RF_E_BADARG, "cartesian size %d is not a multiple of 4", h->n);
     if (fs.n_levels < 2) return rf_fail(h, RF_E_BADARG, "fused image path needs at least two pyramid levels");
+    if ((size_t)h->cfg.azimuths * rf_fused_wp(h) > (size_t)FT_OFF_MASK)
+        return rf_fail(h, RF_E_BADARG, "fused image path: %d azimuths x %d bins exceed the %d-bit sample offsets of the geometry records",
+                       h->cfg.azimuths, rf_fused_wp(h), FT_OFF_BITS);
     static bool attr_set[64] = {};   // per device: the attribute belongs to the device's context
     if (!attr_set[h->device & 63]) {
         RF_CUDA(h, cudaFuncSetAttribute(k_scan16_to_l0l1, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
@@ -501,9 +558,9 @@ int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet&
     }
     FusedArgs a;
     a.rawi = reinterpret_cast<const uint4*>(d_rawi); a.Wp = rf_fused_wp(h); a.A = h->cfg.azimuths; a.group_stride = (size_t)a.A * a.Wp;
-    a.map2 = h->map2; a.n = h->n;
-    a.l0 = fs.lvl[0]; a.l0_stride = fs.lvl_stride[0];
-    a.l1 = fs.lvl[1]; a.l1_stride = fs.lvl_stride[1]; a.w1 = fs.w[1]; a.h1 = fs.h[1];
+    a.geo = h->map2; a.n = h->n;
+    a.l0 = fs.lvl[0]; a.l0_stride = fs.lvl_stride[0]; a.p0 = fs.pitch[0];
+    a.l1 = fs.lvl[1]; a.l1_stride = fs.lvl_stride[1]; a.p1 = fs.pitch[1]; a.w1 = fs.w[1]; a.h1 = fs.h[1];
     a.n_frames = n_frames;
     dim3 grd((n_frames + FT_FR - 1) / FT_FR, (fs.w[1] + FT_TW1 - 1) / FT_TW1, (fs.h[1] + FT_TH1 - 1) / FT_TH1);
     k_scan16_to_l0l1<<<grd, 256, FT_SMEM_BYTES, h->stream>>>(a);
@@ -516,8 +573,8 @@ int rf_launch_pyr_levels(rf_handle* h, const FrameSet& fs, int first_level, int 
     for (int l = first_level; l < fs.n_levels; ++l) {
         const int tiles_x = (fs.w[l] + FT_TW1 - 1) / FT_TW1, tiles_y = (fs.h[l] + FT_PYR_TH1 - 1) / FT_PYR_TH1;
         const int n_tiles = tiles_x * tiles_y * n_frames;
-        k_pyr_down_w<<<(n_tiles + 3) / 4, 128, 0, h->stream>>>(fs.lvl[l - 1], fs.lvl_stride[l - 1], fs.w[l - 1], fs.h[l - 1],
-                                                               fs.lvl[l], fs.lvl_stride[l], fs.w[l], fs.h[l], tiles_x,
+        k_pyr_down_w<<<(n_tiles + 3) / 4, 128, 0, h->stream>>>(fs.lvl[l - 1], fs.lvl_stride[l - 1], fs.pitch[l - 1], fs.w[l - 1], fs.h[l - 1],
+                                                               fs.lvl[l], fs.lvl_stride[l], fs.pitch[l], fs.w[l], fs.h[l], tiles_x,
                                                                tiles_x * tiles_y, n_tiles);
         RF_CHECK_LAUNCH(h);
     }

@@ -72,10 +72,10 @@ __device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01
 // words: lane = 2 * row + half moves 8 consecutive bytes (three aligned loads, two funnel shifts, one 64-bit
 // shared store).  The third word may reach 3 bytes past the window: into the same row, the next row, or the slack
 // every level allocation carries.  Windows that touch the border take the REFLECT_101 byte path.
-__device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ J, int w, int h, int ox, int oy, int lane) {
+__device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ J, int pitch, int w, int h, int ox, int oy, int lane) {
     if (ox >= 0 && oy >= 0 && ox + 16 <= w && oy + 16 <= h) {
         const int r = lane >> 1, c0 = (lane & 1) * 8;
-        const uint8_t* p = J + (size_t)(oy + r) * w + ox + c0;
+        const uint8_t* p = J + (size_t)(oy + r) * pitch + ox + c0;
         const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
         const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
         const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
@@ -84,7 +84,7 @@ __device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int idx = lane + 32 * k, r = idx >> 4, c = idx & 15;
-            s.J[r][c] = __ldg(J + (size_t)reflect101(oy + r, h) * w + reflect101(ox + c, w));
+            s.J[r][c] = __ldg(J + (size_t)reflect101(oy + r, h) * pitch + reflect101(ox + c, w));
         }
     }
     __syncwarp();
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
     }
 
     for (int l = top; l >= 0; --l) {
-        const int w = a.prev.w[l], h = a.prev.h[l];
+        const int w = a.prev.w[l], h = a.prev.h[l], pitch = a.prev.pitch[l];   // prev and next sets share one geometry
         const uint8_t* __restrict__ I = a.prev.lvl[l] + (size_t)fprev * a.prev.lvl_stride[l];
         const uint8_t* __restrict__ J = a.next.lvl[l] + (size_t)fnext * a.next.lvl_stride[l];
         const float sc = 1.f / (float)(1 << l);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
         if (ipx >= 1 && ipy >= 1 && ipx + 17 <= w && ipy + 17 <= h) {
             // interior: lane r < 18 moves row r (18 bytes -> five words of the 20-byte shared row) from aligned loads
             if (lane < 18) {
-                const uint8_t* p = I + (size_t)(ipy - 1 + lane) * w + (ipx - 1);
+                const uint8_t* p = I + (size_t)(ipy - 1 + lane) * pitch + (ipx - 1);
                 const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
                 const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
                 uint32_t q[6];
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
         } else {
             for (int idx = lane; idx < 18 * 18; idx += 32) {
                 const int r = idx / 18, c = idx - r * 18;
-                s.I[r][c] = __ldg(I + (size_t)reflect101(ipy - 1 + r, h) * w + reflect101(ipx - 1 + c, w));
+                s.I[r][c] = __ldg(I + (size_t)reflect101(ipy - 1 + r, h) * pitch + reflect101(ipx - 1 + c, w));
             }
         }
         __syncwarp();
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
             // sub-pixel updates usually keep the integer window origin: the staged window is still the right one
             if (inx != jx || iny != jy) {
                 __syncwarp();
-                load_J(s, J, w, h, inx, iny, lane);
+                load_J(s, J, pitch, w, h, inx, iny, lane);
                 jx = inx; jy = iny;
             }
             int b1 = 0, b2 = 0;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                 q14_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
                 if (iex != jx || iey != jy) {
                     __syncwarp();
-                    load_J(s, J, w, h, iex, iey, lane);
+                    load_J(s, J, pitch, w, h, iex, iey, lane);
                 }
                 int e = 0;
 #pragma unroll
