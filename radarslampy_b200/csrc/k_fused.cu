@@ -28,6 +28,12 @@
 // |fl(out*255) - V/1024| < 1.1e-4 < 1/1024.  V/1024 has a fractional part that is a multiple of 1/1024,
 // so unless that part is 0 the truncation of both is the same integer.  (tests: bit-exact against the
 // plain-C restatement of cv2 on real Oxford scans, where 2.8 % of the pixels take the exact path.)
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 
 #define FT_TW1 64
@@ -514,6 +520,142 @@ k_pyr_down_w(const uint8_t* __restrict__ src, size_t src_stride, int sp, int sw,
 }
 
 // ------------------------------------------------------------------------------------
+// pyrDown for the higher levels, source tiles staged by TMA.
+// Every pyramid level has a 16-byte row pitch, so a level is one 3-D tensor map (x, y, frame) and a warp's
+// FT_PYR_RH x 132-byte source region arrives as ONE cp.async.bulk.tensor box: no address arithmetic, no re-alignment
+// shifts, no per-row loads.  The innermost box coordinate must be a multiple of 16 bytes (measured with
+// tools/probe/tma_probe.cu: an unaligned x raises an illegal-instruction fault; y and the frame index are free), so the
+// box starts 16 bytes left of the tile, at (2*ox1 - 16, 2*oy1 - 2), and is 160 bytes wide; the 1-4-6-4-1 taps are taken
+// from three aligned words per lane instead of two.  Bytes outside the image arrive as zeros; the (at most two) columns /
+// rows REFLECT_101 needs on a border tile are then copied inside the staged tile.  Each warp walks its tiles with two
+// buffers: the box of tile i + 1 is in flight while tile i is filtered.
+// ------------------------------------------------------------------------------------
+#define FT_TMA_ROW 160                                        // box width in bytes: source columns 128 tx - 16 .. 128 tx + 143
+#define FT_TMA_X0 14                                          // byte of a staged row that holds region column 0 (source 2*ox1 - 2)
+#define FT_TMA_WW (FT_TMA_ROW / 4)
+#define FT_TMA_BOX_BYTES (FT_PYR_RH * FT_TMA_ROW)             // 2736
+#define FT_TMA_BUF_BYTES ((FT_TMA_BOX_BYTES + 127) & ~127)    // buffers start on 128-byte boundaries
+#define FT_TMA_WARPS 4
+#ifndef FT_PYR_TMA_CTAS_PER_SM
+#define FT_PYR_TMA_CTAS_PER_SM 8
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// pyrDown of one TMA-staged tile: rows of FT_TMA_WW words, word 3 + 4c/4 ... holds source columns 2*ox1 - 4 + ...;
+// lane k owns destination columns ox1 + 2k, 2k + 1 and reads the aligned words A | B | C = source columns
+// 2*ox1 + 4k - 4 .. + 4k + 7.
+template <bool INTERIOR>
+__device__ __forceinline__ void warp_pyr_staged_impl(const uint32_t* __restrict__ tile, uint8_t* __restrict__ dst, int dp, int dw, int dh,
+                                                     int ox1, int oy1, int lane) {
+    const int x = ox1 + 2 * lane;
+    const bool x_ok = INTERIOR || x < dw;
+    const int rows1 = INTERIOR ? FT_PYR_TH1 : min(FT_PYR_TH1, dh - oy1);
+    uint8_t* q1 = dst + (size_t)oy1 * dp + x;
+    const uint32_t* tp = tile + 3 + lane;
+    uint32_t h[5];
+#pragma unroll
+    for (int r = 0; r < FT_PYR_RH; ++r) {
+        const uint32_t A = tp[r * FT_TMA_WW], B = tp[r * FT_TMA_WW + 1], C = tp[r * FT_TMA_WW + 2];
+        const uint32_t he = __dp4a(B, 0x00010406u, __dp4a(A, 0x04010000u, 0u));   // columns 4k - 2 .. 4k + 2
+        const uint32_t ho = __dp4a(C, 0x00000001u, __dp4a(B, 0x04060401u, 0u));   // columns 4k .. 4k + 4
+        h[r % 5] = he | (ho << 16);
+        if (r >= 4 && (r & 1) == 0) {
+            const uint32_t px2 = pyr_vsum(h[(r - 4) % 5], h[(r - 3) % 5], h[(r - 2) % 5], h[(r - 1) % 5], h[r % 5]);
+            if (INTERIOR || ((r - 4) / 2 < rows1 && x_ok)) *reinterpret_cast<uint16_t*>(q1) = (uint16_t)px2;
+            q1 += dp;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * FT_TMA_WARPS)
+k_pyr_down_tma(const __grid_constant__ CUtensorMap src_map, int sw, int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dp, int dw,
+               int dh, int tiles_x, int tiles_per_frame, int n_tiles) {
+    __shared__ __align__(128) uint8_t s_buf[FT_TMA_WARPS][2][FT_TMA_BUF_BYTES];
+    __shared__ __align__(8) uint64_t s_bar[FT_TMA_WARPS][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = gridDim.x * FT_TMA_WARPS;
+    int t = blockIdx.x * FT_TMA_WARPS + warp;
+    if (t >= n_tiles) return;
+    const uint32_t bar0 = smem_u32(&s_bar[warp][0]), bar1 = smem_u32(&s_bar[warp][1]);
+    const uint32_t buf0 = smem_u32(&s_buf[warp][0][0]), buf1 = smem_u32(&s_buf[warp][1][0]);
+    auto issue = [&](int tile, int b) {   // lane 0 only
+        const int frame = tile / tiles_per_frame, tt = tile - frame * tiles_per_frame;
+        const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
+        const uint32_t bar = b ? bar1 : bar0;
+        mbar_expect_tx(bar, FT_TMA_BOX_BYTES);
+        tma_load_3d(b ? buf1 : buf0, &src_map, bar, 2 * tx * FT_TW1 - 16, 2 * ty * FT_PYR_TH1 - 2, frame);
+    };
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(t, 0);
+    }
+    __syncwarp();
+    for (int i = 0; t < n_tiles; t += stride, ++i) {
+        const int b = i & 1;
+        if (lane == 0 && t + stride < n_tiles) {
+            // buffer b ^ 1 was read (and maybe patched) by this warp in the previous round: order those generic-proxy
+            // accesses before the async-proxy write that refills it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(t + stride, b ^ 1);
+        }
+        const uint32_t bar = b ? bar1 : bar0, parity = (uint32_t)(i >> 1) & 1u;
+        int spins = 0;
+        while (!mbar_try_wait(bar, parity))
+            if (++spins > (1 << 22)) __trap();   // a lost transaction must not hang the device
+        const int frame = t / tiles_per_frame, tt = t - frame * tiles_per_frame;
+        const int ty = tt / tiles_x, tx = tt - ty * tiles_x;
+        const int ox1 = tx * FT_TW1, oy1 = ty * FT_PYR_TH1;
+        const int x0 = 2 * ox1 - 2, y0 = 2 * oy1 - 2;
+        uint32_t* tw = reinterpret_cast<uint32_t*>(&s_buf[warp][b][0]);
+        uint8_t* tb = &s_buf[warp][b][0];
+        const int jr = sw - x0, rb = sh - y0;   // first region column / row outside the image
+        if (x0 < 0 || y0 < 0 || jr <= FT_RW - 1 || rb <= FT_PYR_RH - 1) {
+            // REFLECT_101 inside the staged tile: columns first (on the rows that exist), then whole rows
+            if (lane < FT_PYR_RH) {
+                uint8_t* row = tb + lane * FT_TMA_ROW + FT_TMA_X0;   // region column 0
+                if (x0 < 0) { row[0] = row[4]; row[1] = row[3]; }
+                if (jr <= FT_RW - 1) {
+                    row[jr] = row[jr - 2];
+                    if (jr + 1 <= FT_RW - 1 && jr >= 3) row[jr + 1] = row[jr - 3];
+                }
+            }
+            __syncwarp();
+            for (int wd = lane; wd < FT_TMA_WW; wd += 32) {
+                if (y0 < 0) { tw[wd] = tw[4 * FT_TMA_WW + wd]; tw[FT_TMA_WW + wd] = tw[3 * FT_TMA_WW + wd]; }
+                if (rb <= FT_PYR_RH - 1 && rb >= 2) {
+                    tw[rb * FT_TMA_WW + wd] = tw[(rb - 2) * FT_TMA_WW + wd];
+                    if (rb + 1 <= FT_PYR_RH - 1 && rb >= 3) tw[(rb + 1) * FT_TMA_WW + wd] = tw[(rb - 3) * FT_TMA_WW + wd];
+                }
+            }
+            __syncwarp();
+        }
+        if (ox1 + FT_TW1 <= dw && oy1 + FT_PYR_TH1 <= dh) warp_pyr_staged_impl<true>(tw, dst + (size_t)frame * dst_stride, dp, dw, dh, ox1, oy1, lane);
+        else warp_pyr_staged_impl<false>(tw, dst + (size_t)frame * dst_stride, dp, dw, dh, ox1, oy1, lane);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
 int rf_fused_wp(const rf_handle* h) { return ((h->cfg.range_bins + 1) + 3) & ~3; }   // >= W + 1, multiple of 4
@@ -568,14 +710,63 @@ int rf_launch_scan_to_l0l1(rf_handle* h, const uint32_t* d_rawi, const FrameSet&
     return RF_OK;
 }
 
+// tensor map of one pyramid level: (x, y, frame) u8, box FT_TMA_ROW x FT_PYR_RH x 1, zero fill outside the image.
+// Encoded once per distinct (base, geometry) and kept for the life of the process: a map is a pure function of its key.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static const CUtensorMap* level_tmap(rf_handle* h, const FrameSet& fs, int l) {
+    typedef std::tuple<const void*, int, int, int, size_t, int> Key;
+    static std::map<Key, CUtensorMap> cache;
+    static std::mutex mu;
+    static PFN_encodeTiled encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            rf_fail(h, RF_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+            return nullptr;
+        }
+        encode = (PFN_encodeTiled)fn;
+    }
+    const Key key(fs.lvl[l], fs.w[l], fs.h[l], fs.pitch[l], fs.lvl_stride[l], fs.count);
+    auto it = cache.find(key);
+    if (it != cache.end()) return &it->second;
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)fs.w[l], (cuuint64_t)fs.h[l], (cuuint64_t)fs.count};
+    const cuuint64_t strides[2] = {(cuuint64_t)fs.pitch[l], (cuuint64_t)fs.lvl_stride[l]};
+    const cuuint32_t box[3] = {FT_TMA_ROW, FT_PYR_RH, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, fs.lvl[l], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rf_fail(h, RF_E_CUDA, "cuTensorMapEncodeTiled failed (%d) for level %d: %d x %d, pitch %d", (int)r, l, fs.w[l], fs.h[l], fs.pitch[l]);
+        return nullptr;
+    }
+    return &cache.emplace(key, tm).first->second;
+}
+
 // levels first_level .. n_levels-1 from their predecessors
 int rf_launch_pyr_levels(rf_handle* h, const FrameSet& fs, int first_level, int n_frames) {
+    static const bool no_tma = getenv("RADARFE_NO_TMA") != nullptr;   // diagnostic: the plain-load kernel
     for (int l = first_level; l < fs.n_levels; ++l) {
         const int tiles_x = (fs.w[l] + FT_TW1 - 1) / FT_TW1, tiles_y = (fs.h[l] + FT_PYR_TH1 - 1) / FT_PYR_TH1;
         const int n_tiles = tiles_x * tiles_y * n_frames;
-        k_pyr_down_w<<<(n_tiles + 3) / 4, 128, 0, h->stream>>>(fs.lvl[l - 1], fs.lvl_stride[l - 1], fs.pitch[l - 1], fs.w[l - 1], fs.h[l - 1],
-                                                               fs.lvl[l], fs.lvl_stride[l], fs.pitch[l], fs.w[l], fs.h[l], tiles_x,
-                                                               tiles_x * tiles_y, n_tiles);
+        if (n_tiles == 0) continue;
+        // the in-tile border fix-up needs the reflected columns / rows inside the same box
+        if (!no_tma && fs.w[l - 1] >= 8 && fs.h[l - 1] >= 8) {
+            const CUtensorMap* tm = level_tmap(h, fs, l - 1);
+            if (!tm) return RF_E_CUDA;
+            int ctas = (n_tiles + FT_TMA_WARPS - 1) / FT_TMA_WARPS;
+            const int cap = h->sm_count * FT_PYR_TMA_CTAS_PER_SM;   // persistent: every warp walks its tiles with a prefetch in flight
+            if (ctas > cap) ctas = cap;
+            k_pyr_down_tma<<<ctas, 32 * FT_TMA_WARPS, 0, h->stream>>>(*tm, fs.w[l - 1], fs.h[l - 1], fs.lvl[l], fs.lvl_stride[l], fs.pitch[l],
+                                                                      fs.w[l], fs.h[l], tiles_x, tiles_x * tiles_y, n_tiles);
+        } else {
+            k_pyr_down_w<<<(n_tiles + 3) / 4, 128, 0, h->stream>>>(fs.lvl[l - 1], fs.lvl_stride[l - 1], fs.pitch[l - 1], fs.w[l - 1], fs.h[l - 1],
+                                                                   fs.lvl[l], fs.lvl_stride[l], fs.pitch[l], fs.w[l], fs.h[l], tiles_x,
+                                                                   tiles_x * tiles_y, n_tiles);
+        }
         RF_CHECK_LAUNCH(h);
     }
     return RF_OK;
