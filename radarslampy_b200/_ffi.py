@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libradarfe.so")
+LIB_PATH = os.environ.get("RADARFE_LIB") or os.path.join(_PKG, "libradarfe.so")   # RADARFE_LIB: A/B builds of the same library
 
 RF_OK, RF_E_BADARG, RF_E_CAPACITY, RF_E_CUDA, RF_E_WORKLIMIT, RF_E_NOMEM = 0, -1, -2, -3, -4, -5
 
