@@ -42,6 +42,101 @@
 // =====================================================================================
 #define ME_TW 32
 #define ME_TH 32
+struct MinEigSmem {
+    float tile[ME_TH + 4][ME_TW + 4 + 1];
+    // gradient products (f32) and their horizontal 3-sums (f64).  cv::boxFilter sums f32 planes in double, rows first and
+    // then columns; the same split costs 3 + 3 shared-memory loads per plane and pixel instead of 9 64-bit ones.
+    float gxx[ME_TH + 2][ME_TW + 2 + 1], gxy[ME_TH + 2][ME_TW + 2 + 1], gyy[ME_TH + 2][ME_TW + 2 + 1];
+    double hxx[ME_TH + 2][ME_TW], hxy[ME_TH + 2][ME_TW], hyy[ME_TH + 2][ME_TW];
+};
+
+// scaled Sobel products at one gradient position from its eight neighbours
+__device__ __forceinline__ void me_products(float a00, float a01, float a02, float a10, float a12, float a20, float a21, float a22, float k0,
+                                            float k1, float& pxx, float& pxy, float& pyy) {
+    // Dx: row filter [-1 0 1], column filter [k1 k0 k1] (the smoothing taps carry the scale)
+    const float rx0 = __fsub_rn(a02, a00), rx1 = __fsub_rn(a12, a10), rx2 = __fsub_rn(a22, a20);
+    const float dx = __fmaf_rn(k1, __fadd_rn(rx0, rx2), __fmul_rn(k0, rx1));
+    // Dy: row filter [k1 k0 k1], column filter [-1 0 1]
+    const float ry0 = __fmaf_rn(k1, __fadd_rn(a00, a02), __fmul_rn(k0, a01));
+    const float ry2 = __fmaf_rn(k1, __fadd_rn(a20, a22), __fmul_rn(k0, a21));
+    const float dy = __fsub_rn(ry2, ry0);
+    pxx = __fmul_rn(dx, dx); pxy = __fmul_rn(dx, dy); pyy = __fmul_rn(dy, dy);
+}
+
+// One 32 x 32 output tile.  INTERIOR: the 36 x 36 input neighbourhood lies inside the image, so no position is reflected
+// and rows / columns are walked with the 32 x 8 thread grid directly (the general path spends most of its instructions
+// on index arithmetic: divisions by the staging widths and the REFLECT_101 chains of the tile, gradient and tap positions).
+template <bool INTERIOR>
+__device__ __forceinline__ void me_tile(MinEigSmem& sm, const float* __restrict__ img, float* __restrict__ resp, int n, int ox, int oy, float k0,
+                                        float k1) {
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+    if (INTERIOR) {
+        const float* __restrict__ p = img + (size_t)(oy - 2) * n + (ox - 2);
+        for (int r = ty; r < ME_TH + 4; r += 8) {
+            sm.tile[r][tx] = __ldg(p + (size_t)r * n + tx);
+            if (tx < 4) sm.tile[r][32 + tx] = __ldg(p + (size_t)r * n + 32 + tx);
+        }
+        __syncthreads();
+        for (int r = ty; r < ME_TH + 2; r += 8) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = tx + 32 * h;
+                if (h == 1 && tx >= 2) break;
+                float pxx, pxy, pyy;
+                me_products(sm.tile[r][c], sm.tile[r][c + 1], sm.tile[r][c + 2], sm.tile[r + 1][c], sm.tile[r + 1][c + 2], sm.tile[r + 2][c],
+                            sm.tile[r + 2][c + 1], sm.tile[r + 2][c + 2], k0, k1, pxx, pxy, pyy);
+                sm.gxx[r][c] = pxx; sm.gxy[r][c] = pxy; sm.gyy[r][c] = pyy;
+            }
+        }
+    } else {
+        // tile position (r, c) holds img at clamp-reflected (oy - 2 + r, ox - 2 + c); positions are looked up
+        // through T() so gradients at reflected locations read the taps a full-image Sobel would read
+        for (int i = tid; i < (ME_TH + 4) * (ME_TW + 4); i += 256) {
+            const int r = i / (ME_TW + 4), c = i - r * (ME_TW + 4);
+            int y = oy - 2 + r, x = ox - 2 + c;
+            y = min(max(y, -2), n + 1); x = min(max(x, -2), n + 1);
+            sm.tile[r][c] = __ldg(img + (size_t)reflect101(y, n) * n + reflect101(x, n));
+        }
+        __syncthreads();
+        for (int i = tid; i < (ME_TH + 2) * (ME_TW + 2); i += 256) {
+            const int r = i / (ME_TW + 2), c = i - r * (ME_TW + 2);
+            // gradient-image position, reflected into the image (cv::boxFilter border on the gradient products)
+            int y = oy - 1 + r, x = ox - 1 + c;
+            y = min(max(y, -1), n); x = min(max(x, -1), n);
+            const int qy = reflect101(y, n), qx = reflect101(x, n);
+            // taps of the full-image Sobel at (qy, qx): neighbours at reflect101(q +- 1)
+            const int ym = reflect101(qy - 1, n), yp = reflect101(qy + 1, n);
+            const int xm = reflect101(qx - 1, n), xp = reflect101(qx + 1, n);
+#define T(yy, xx) sm.tile[(yy) - (oy - 2)][(xx) - (ox - 2)]
+            float pxx, pxy, pyy;
+            me_products(T(ym, xm), T(ym, qx), T(ym, xp), T(qy, xm), T(qy, xp), T(yp, xm), T(yp, qx), T(yp, xp), k0, k1, pxx, pxy, pyy);
+#undef T
+            sm.gxx[r][c] = pxx; sm.gxy[r][c] = pxy; sm.gyy[r][c] = pyy;
+        }
+    }
+    __syncthreads();
+    // horizontal sums of the (ME_TH + 2) x ME_TW positions the outputs need
+    for (int r = ty; r < ME_TH + 2; r += 8) {
+        sm.hxx[r][tx] = ((double)sm.gxx[r][tx] + (double)sm.gxx[r][tx + 1]) + (double)sm.gxx[r][tx + 2];
+        sm.hxy[r][tx] = ((double)sm.gxy[r][tx] + (double)sm.gxy[r][tx + 1]) + (double)sm.gxy[r][tx + 2];
+        sm.hyy[r][tx] = ((double)sm.gyy[r][tx] + (double)sm.gyy[r][tx + 1]) + (double)sm.gyy[r][tx + 2];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ME_TH / 8; ++k) {
+        const int r = ty + 8 * k, c = tx;
+        const int y = oy + r, x = ox + c;
+        if (!INTERIOR && (y >= n || x >= n)) continue;
+        const double sxx = (sm.hxx[r][c] + sm.hxx[r + 1][c]) + sm.hxx[r + 2][c];
+        const double sxy = (sm.hxy[r][c] + sm.hxy[r + 1][c]) + sm.hxy[r + 2][c];
+        const double syy = (sm.hyy[r][c] + sm.hyy[r + 1][c]) + sm.hyy[r + 2][c];
+        const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
+        const float d = __fsub_rn(a, cc);
+        resp[(size_t)y * n + x] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
+    }
+    __syncthreads();           // the next tile overwrites the staging arrays
+}
+
 __global__ void __launch_bounds__(256)
 k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0, float k1, float* __restrict__ resp_base,
           size_t resp_stride, const int32_t* __restrict__ flags) {
@@ -50,61 +145,13 @@ k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0
     if (flags && !flags[blockIdx.y]) return;
     const float* __restrict__ img = img_base + (size_t)blockIdx.y * img_stride;
     float* __restrict__ resp = resp_base + (size_t)blockIdx.y * resp_stride;
-    __shared__ float tile[ME_TH + 4][ME_TW + 4 + 1];
-    __shared__ float gxx[ME_TH + 2][ME_TW + 2 + 1], gxy[ME_TH + 2][ME_TW + 2 + 1], gyy[ME_TH + 2][ME_TW + 2 + 1];
+    __shared__ MinEigSmem sm;
     const int tiles_x = (n + ME_TW - 1) / ME_TW, ntiles = tiles_x * ((n + ME_TH - 1) / ME_TH);
-    const int tid = threadIdx.y * 32 + threadIdx.x;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int ox = (t % tiles_x) * ME_TW, oy = (t / tiles_x) * ME_TH;
-    // tile position (r, c) holds img at clamp-reflected (oy - 2 + r, ox - 2 + c); positions are looked up
-    // through T() so gradients at reflected locations read the taps a full-image Sobel would read
-    for (int i = tid; i < (ME_TH + 4) * (ME_TW + 4); i += 256) {
-        const int r = i / (ME_TW + 4), c = i - r * (ME_TW + 4);
-        int y = oy - 2 + r, x = ox - 2 + c;
-        y = min(max(y, -2), n + 1); x = min(max(x, -2), n + 1);
-        tile[r][c] = __ldg(img + (size_t)reflect101(y, n) * n + reflect101(x, n));
-    }
-    __syncthreads();
-    for (int i = tid; i < (ME_TH + 2) * (ME_TW + 2); i += 256) {
-        const int r = i / (ME_TW + 2), c = i - r * (ME_TW + 2);
-        // gradient-image position, reflected into the image (cv::boxFilter border on the gradient products)
-        int y = oy - 1 + r, x = ox - 1 + c;
-        y = min(max(y, -1), n); x = min(max(x, -1), n);
-        const int qy = reflect101(y, n), qx = reflect101(x, n);
-        // taps of the full-image Sobel at (qy, qx): neighbours at reflect101(q +- 1)
-        const int ym = reflect101(qy - 1, n), yp = reflect101(qy + 1, n);
-        const int xm = reflect101(qx - 1, n), xp = reflect101(qx + 1, n);
-#define T(yy, xx) tile[(yy) - (oy - 2)][(xx) - (ox - 2)]
-        const float a00 = T(ym, xm), a01 = T(ym, qx), a02 = T(ym, xp);
-        const float a10 = T(qy, xm), a12 = T(qy, xp);
-        const float a20 = T(yp, xm), a21 = T(yp, qx), a22 = T(yp, xp);
-#undef T
-        // Dx: row filter [-1 0 1], column filter [k1 k0 k1] (the smoothing taps carry the scale)
-        const float rx0 = __fsub_rn(a02, a00), rx1 = __fsub_rn(a12, a10), rx2 = __fsub_rn(a22, a20);
-        const float dx = __fmaf_rn(k1, __fadd_rn(rx0, rx2), __fmul_rn(k0, rx1));
-        // Dy: row filter [k1 k0 k1], column filter [-1 0 1]
-        const float ry0 = __fmaf_rn(k1, __fadd_rn(a00, a02), __fmul_rn(k0, a01));
-        const float ry2 = __fmaf_rn(k1, __fadd_rn(a20, a22), __fmul_rn(k0, a21));
-        const float dy = __fsub_rn(ry2, ry0);
-        gxx[r][c] = __fmul_rn(dx, dx); gxy[r][c] = __fmul_rn(dx, dy); gyy[r][c] = __fmul_rn(dy, dy);
-    }
-    __syncthreads();
-    for (int k = 0; k < ME_TH / 8; ++k) {
-        const int r = threadIdx.y + 8 * k, c = threadIdx.x;
-        const int y = oy + r, x = ox + c;
-        if (y >= n || x >= n) continue;
-        double sxx = 0, sxy = 0, syy = 0;  // cv::boxFilter accumulates f32 planes in double
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                sxx += (double)gxx[r + dy][c + dx]; sxy += (double)gxy[r + dy][c + dx]; syy += (double)gyy[r + dy][c + dx];
-            }
-        const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
-        const float d = __fsub_rn(a, cc);
-        resp[(size_t)y * n + x] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
-    }
-    __syncthreads();           // the next tile overwrites the staging arrays
+        const int ty_ = t / tiles_x;
+        const int ox = (t - ty_ * tiles_x) * ME_TW, oy = ty_ * ME_TH;
+        if (ox >= 2 && oy >= 2 && ox + ME_TW + 2 <= n && oy + ME_TH + 2 <= n) me_tile<true>(sm, img, resp, n, ox, oy, k0, k1);
+        else me_tile<false>(sm, img, resp, n, ox, oy, k0, k1);
     }
 }
 
