@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=4096, help="strong leg: total independent pairs (BASELINE configs[3])")
     ap.add_argument("--chain-seq", type=int, default=256, help="chained leg: sequences per GPU in lock step")
     ap.add_argument("--chain-steps", type=int, default=12)
+    ap.add_argument("--gather-every", type=int, default=8, help="multi-GPU: steps whose pose records travel in one NCCL gather")
     ap.add_argument("--chain-runners", type=int, default=4, help="chained leg: rf_seq runners (streams) the sequences are split over")
     return ap.parse_args()
 
@@ -476,7 +477,14 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     counts_p = pin(np.asarray(counts, np.int32), np.int32)
     prev_pose = pin(poses[:-1], np.float64)
     outs = [b.alloc_outputs(pinned=True) for b in batches]
-    gatherer = _shard.PoseGatherer(world * P, world, rank, device="cuda") if world > 1 else None
+    # trajectory concatenation over NCCL: the records of --gather-every steps travel in one dist.gather, queued without
+    # blocking the host (_shard.PoseGatherer.gather_async).  A blocking gather per step staged its records through a
+    # pageable H2D copy that waits behind every queued scan upload, and cost a quarter of the 2-GPU e2e rate (99 k vs
+    # 129 k frames/s without any gather; box ceiling 131 k).
+    G_EVERY = max(1, args.gather_every)
+    gatherer = _shard.PoseGatherer(world * P * G_EVERY, world, rank, device="cuda") if world > 1 else None
+    gather_buf = np.zeros((P * G_EVERY, _shard.RECORD_WIDTH), np.float64)
+    gather_fill = [0]
     with_mds = bool(args.mds)
 
     def barrier():
@@ -485,10 +493,18 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
         torch.cuda.synchronize()
         fe.sync()
 
-    def gather_poses(res_host):
-        """trajectory concatenation: poses of every rank to rank 0 over NCCL"""
+    def gather_poses(res_host, flush=False):
+        """trajectory concatenation: poses of every rank to rank 0 over NCCL, G_EVERY steps per message"""
         if world > 1 and not args.no_gather:
-            gatherer.gather(_shard.pack_records(res_host))
+            if res_host is not None:
+                j = gather_fill[0]
+                gather_buf[j * P:(j + 1) * P] = _shard.pack_records(res_host)
+                gather_fill[0] = j + 1
+            if gather_fill[0] == G_EVERY or (flush and gather_fill[0] > 0):
+                gatherer.gather_async(gather_buf)       # queued; the host goes on feeding uploads
+                gather_fill[0] = 0
+            if flush:
+                gatherer.result()                       # every pose has reached rank 0
 
     def upload(b):
         b.upload(raw, pair_idx_p, feats_p, counts_p, prev_pose=prev_pose, sync=False)
@@ -522,7 +538,20 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
             stage_ms[k] = stage_ms.get(k, 0.0) + v
     res, nxt, corr = batches[0].download(outs[0])
     fe.sync()
-    gather_poses(res)
+    gather_poses(res, flush=True)
+    barrier()
+    # the same kernels timed ALONE: one batch at a time with a full sync between passes, so nothing of another batch
+    # (clique / solve tail, uploads) shares the SMs -- the in-step figures above carry that interference
+    alone_ms, alone_runs = {}, 0
+    for _ in range(3):
+        batches[0].run_async(with_mds=with_mds)
+        fe.sync()
+    batches[0].stage_times()
+    for _ in range(8):
+        batches[0].run_async(with_mds=with_mds)
+        fe.sync()
+    sm_a, alone_runs = batches[0].stage_times()
+    alone_ms = {k: v / max(alone_runs, 1) for k, v in sm_a.items()}
     barrier()
 
     # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region ------
@@ -543,6 +572,7 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
         for i in range(max(0, n - NB), n):
             batches[i % NB].wait()
             gather_poses(outs[i % NB][0][:P])
+        gather_poses(None, flush=True)                  # the last partial message: every pose has reached rank 0
 
     e2e_loop(max(args.warmup, NB))
     barrier()
@@ -555,12 +585,24 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     if world > 1:                                 # the NCCL gather runs on torch's stream: bound it by the host clock
         ms_e2e = max(ms_e2e, (time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop()
+    # H2D ceiling of the e2e arm: the same uploads (2-D used-column copies from the same pinned buffers, all ranks at once)
+    # with nothing else queued -- what the box's PCIe / host-memory system gives this job
+    n_up = max(8, min(args.steps, 32))
+    for i in range(NB):
+        upload(batches[i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_up):
+        upload(batches[i % NB])
+    fe.sync()
+    ms_h2d = (time.perf_counter() - t0) * 1e3 / n_up
+    barrier()
 
     # ---- reduce over ranks (max time) ---------------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, ms_e2e, ms_h2d], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_h2d = float(t[0]), float(t[1]), float(t[2])
     res = {k: np.array(res[k]) for k in res.dtype.names}      # detach from the pinned output buffers
     for b in batches:
         b.close()
@@ -577,6 +619,10 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     for name, tot in stage_ms.items():
         per = tot / max(runs, 1)
         stages[name] = {"ms": per, "alg_bytes": sb[name], "gbs": (sb[name] / (per * 1e-3) / 1e9) if per > 0 else None}
+        am = alone_ms.get(name, 0.0)
+        if am > 0:
+            stages[name]["ms_alone"] = am
+            stages[name]["gbs_alone"] = sb[name] / (am * 1e-3) / 1e9
     # dominant kernel = the HBM-streaming stage with the largest share of the step (the clique search is a
     # latency-bound combinatorial kernel with ~3 KB of traffic per pair; it has no bandwidth roofline and is
     # reported in `stages` and `clique`)
@@ -598,11 +644,19 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
         "pipelining": f"{NB} batches alternate on one handle (copy / image+KLT / rejection+solve streams)",
         "klt_tracks_per_s": world * K_total * args.steps / (ms * 1e-3),
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-                "ms_per_step": ms_e2e / args.steps, "note": "bytes are the whole job's (all ranks) per step"},
+                "ms_per_step": ms_e2e / args.steps, "note": "bytes are the whole job's (all ranks) per step",
+                # the uploads alone (same pinned buffers, same 2-D copies, every rank at once): the H2D ceiling of this job on this box
+                "h2d_only": {"ms_per_step": ms_h2d, "gbs": int(h2d) * world / (ms_h2d * 1e-3) / 1e9,
+                             "frames_per_s_ceiling": world * P / (ms_h2d * 1e-3),
+                             "e2e_fraction_of_ceiling": (e2e / (world * P / (ms_h2d * 1e-3))) if ms_h2d > 0 else None}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(dom, S), "peak_source": peak_src,
                      "alg_bytes_per_launch": sb[dom], "ms_per_launch": stages[dom]["ms"],
+                     # `achieved` / `frac` are in-step (other batches' clique / solve kernels and uploads share the SMs: the
+                     # sustained figure); the same launch with the device to itself:
+                     "alone": {"ms_per_launch": stages[dom].get("ms_alone"), "achieved": stages[dom].get("gbs_alone"),
+                               "frac": (stages[dom]["gbs_alone"] / peak) if stages[dom].get("gbs_alone") else None},
                      # SURVEY.md §8(d) counts the reference's materialised f32 Cartesian image (4 n^2 per frame) plus the
                      # whole u8 pyramid as mandated outputs of the conversion; this kernel never writes the f32 image and
                      # produces levels 0-1 only, so `achieved` / `frac` above use the smaller, actual figure
