@@ -40,15 +40,19 @@
 // products (+1 halo, evaluated at REFLECT_101 positions of the gradient image like
 // cv::boxFilter does) are staged in shared memory.  blockIdx.z = problem.
 // =====================================================================================
-#define ME_TW 32
-#define ME_TH 32
-struct MinEigSmem {
-    float tile[ME_TH + 4][ME_TW + 4 + 1];
-    // gradient products (f32) and their horizontal 3-sums (f64).  cv::boxFilter sums f32 planes in double, rows first and
-    // then columns; the same split costs 3 + 3 shared-memory loads per plane and pixel instead of 9 64-bit ones.
-    float gxx[ME_TH + 2][ME_TW + 2 + 1], gxy[ME_TH + 2][ME_TW + 2 + 1], gyy[ME_TH + 2][ME_TW + 2 + 1];
-    double hxx[ME_TH + 2][ME_TW], hxy[ME_TH + 2][ME_TW], hyy[ME_TH + 2][ME_TW];
-};
+// One warp owns a strip of ME_COLS output columns and walks ME_ROWS output rows down it.  Lane l stands on gradient
+// column x0 - 1 + l (lanes 1 .. 30 also own an output column); per gradient row it reads its 3 x 3 image taps straight
+// from global memory (each image row is touched by three consecutive gradient rows and three neighbouring lanes: L1
+// hits), forms the three gradient products, widens them once, takes the horizontal 3-sums from its neighbours with
+// shuffles and keeps the last three rows of sums in registers for the vertical 3-sum.  Nothing is staged in shared
+// memory: the tiled version of this kernel (36 x 36 image tile, three product planes, three f64 planes of row sums) spent
+// 74 % of the L1 data pipe on shared-memory wavefronts and 188 instructions per pixel, half of them index arithmetic.
+// Border rule as before: a gradient position outside the image is the gradient AT its REFLECT_101 position
+// (cv::boxFilter's border on the product planes), whose taps are again reflected (cv::Sobel's border); the box sums are
+// f64, rows first, then columns (cv::boxFilter's order).
+#define ME_COLS 30
+#define ME_ROWS 64
+#define ME_WARPS 4
 
 // scaled Sobel products at one gradient position from its eight neighbours
 __device__ __forceinline__ void me_products(float a00, float a01, float a02, float a10, float a12, float a20, float a21, float a22, float k0,
@@ -63,95 +67,50 @@ __device__ __forceinline__ void me_products(float a00, float a01, float a02, flo
     pxx = __fmul_rn(dx, dx); pxy = __fmul_rn(dx, dy); pyy = __fmul_rn(dy, dy);
 }
 
-// One 32 x 32 output tile.  INTERIOR: the 36 x 36 input neighbourhood lies inside the image, so no position is reflected
-// and rows / columns are walked with the 32 x 8 thread grid directly (the general path spends most of its instructions
-// on index arithmetic: divisions by the staging widths and the REFLECT_101 chains of the tile, gradient and tap positions).
-template <bool INTERIOR>
-__device__ __forceinline__ void me_tile(MinEigSmem& sm, const float* __restrict__ img, float* __restrict__ resp, int n, int ox, int oy, float k0,
-                                        float k1) {
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    if (INTERIOR) {
-        const float* __restrict__ p = img + (size_t)(oy - 2) * n + (ox - 2);
-        for (int r = ty; r < ME_TH + 4; r += 8) {
-            sm.tile[r][tx] = __ldg(p + (size_t)r * n + tx);
-            if (tx < 4) sm.tile[r][32 + tx] = __ldg(p + (size_t)r * n + 32 + tx);
-        }
-        __syncthreads();
-        for (int r = ty; r < ME_TH + 2; r += 8) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = tx + 32 * h;
-                if (h == 1 && tx >= 2) break;
-                float pxx, pxy, pyy;
-                me_products(sm.tile[r][c], sm.tile[r][c + 1], sm.tile[r][c + 2], sm.tile[r + 1][c], sm.tile[r + 1][c + 2], sm.tile[r + 2][c],
-                            sm.tile[r + 2][c + 1], sm.tile[r + 2][c + 2], k0, k1, pxx, pxy, pyy);
-                sm.gxx[r][c] = pxx; sm.gxy[r][c] = pxy; sm.gyy[r][c] = pyy;
-            }
-        }
-    } else {
-        // tile position (r, c) holds img at clamp-reflected (oy - 2 + r, ox - 2 + c); positions are looked up
-        // through T() so gradients at reflected locations read the taps a full-image Sobel would read
-        for (int i = tid; i < (ME_TH + 4) * (ME_TW + 4); i += 256) {
-            const int r = i / (ME_TW + 4), c = i - r * (ME_TW + 4);
-            int y = oy - 2 + r, x = ox - 2 + c;
-            y = min(max(y, -2), n + 1); x = min(max(x, -2), n + 1);
-            sm.tile[r][c] = __ldg(img + (size_t)reflect101(y, n) * n + reflect101(x, n));
-        }
-        __syncthreads();
-        for (int i = tid; i < (ME_TH + 2) * (ME_TW + 2); i += 256) {
-            const int r = i / (ME_TW + 2), c = i - r * (ME_TW + 2);
-            // gradient-image position, reflected into the image (cv::boxFilter border on the gradient products)
-            int y = oy - 1 + r, x = ox - 1 + c;
-            y = min(max(y, -1), n); x = min(max(x, -1), n);
-            const int qy = reflect101(y, n), qx = reflect101(x, n);
-            // taps of the full-image Sobel at (qy, qx): neighbours at reflect101(q +- 1)
-            const int ym = reflect101(qy - 1, n), yp = reflect101(qy + 1, n);
-            const int xm = reflect101(qx - 1, n), xp = reflect101(qx + 1, n);
-#define T(yy, xx) sm.tile[(yy) - (oy - 2)][(xx) - (ox - 2)]
-            float pxx, pxy, pyy;
-            me_products(T(ym, xm), T(ym, qx), T(ym, xp), T(qy, xm), T(qy, xp), T(yp, xm), T(yp, qx), T(yp, xp), k0, k1, pxx, pxy, pyy);
-#undef T
-            sm.gxx[r][c] = pxx; sm.gxy[r][c] = pxy; sm.gyy[r][c] = pyy;
-        }
-    }
-    __syncthreads();
-    // horizontal sums of the (ME_TH + 2) x ME_TW positions the outputs need
-    for (int r = ty; r < ME_TH + 2; r += 8) {
-        sm.hxx[r][tx] = ((double)sm.gxx[r][tx] + (double)sm.gxx[r][tx + 1]) + (double)sm.gxx[r][tx + 2];
-        sm.hxy[r][tx] = ((double)sm.gxy[r][tx] + (double)sm.gxy[r][tx + 1]) + (double)sm.gxy[r][tx + 2];
-        sm.hyy[r][tx] = ((double)sm.gyy[r][tx] + (double)sm.gyy[r][tx + 1]) + (double)sm.gyy[r][tx + 2];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < ME_TH / 8; ++k) {
-        const int r = ty + 8 * k, c = tx;
-        const int y = oy + r, x = ox + c;
-        if (!INTERIOR && (y >= n || x >= n)) continue;
-        const double sxx = (sm.hxx[r][c] + sm.hxx[r + 1][c]) + sm.hxx[r + 2][c];
-        const double sxy = (sm.hxy[r][c] + sm.hxy[r + 1][c]) + sm.hxy[r + 2][c];
-        const double syy = (sm.hyy[r][c] + sm.hyy[r + 1][c]) + sm.hyy[r + 2][c];
-        const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
-        const float d = __fsub_rn(a, cc);
-        resp[(size_t)y * n + x] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
-    }
-    __syncthreads();           // the next tile overwrites the staging arrays
-}
-
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * ME_WARPS)
 k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0, float k1, float* __restrict__ resp_base,
           size_t resp_stride, const int32_t* __restrict__ flags) {
-    // grid = (tile workers, problems): a CTA walks the tiles of its problem, so the un-flagged problems of a lock-step
-    // batch cost gridDim.x empty CTAs each instead of one per tile
+    // grid = (strip workers, problems): a CTA walks the strips of its problem, so the un-flagged problems of a lock-step
+    // batch cost gridDim.x empty CTAs each instead of one per strip
     if (flags && !flags[blockIdx.y]) return;
     const float* __restrict__ img = img_base + (size_t)blockIdx.y * img_stride;
     float* __restrict__ resp = resp_base + (size_t)blockIdx.y * resp_stride;
-    __shared__ MinEigSmem sm;
-    const int tiles_x = (n + ME_TW - 1) / ME_TW, ntiles = tiles_x * ((n + ME_TH - 1) / ME_TH);
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int ty_ = t / tiles_x;
-        const int ox = (t - ty_ * tiles_x) * ME_TW, oy = ty_ * ME_TH;
-        if (ox >= 2 && oy >= 2 && ox + ME_TW + 2 <= n && oy + ME_TH + 2 <= n) me_tile<true>(sm, img, resp, n, ox, oy, k0, k1);
-        else me_tile<false>(sm, img, resp, n, ox, oy, k0, k1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strips_x = (n + ME_COLS - 1) / ME_COLS, nstrips = strips_x * ((n + ME_ROWS - 1) / ME_ROWS);
+    for (int t = blockIdx.x * ME_WARPS + warp; t < nstrips; t += gridDim.x * ME_WARPS) {
+        const int sy = t / strips_x, sx = t - sy * strips_x;
+        const int x0 = sx * ME_COLS, y0 = sy * ME_ROWS;
+        // this lane's gradient column and the columns of its three taps
+        const int gx = min(max(x0 - 1 + lane, -1), n);
+        const int qx = reflect101(gx, n);
+        const int xm = reflect101(qx - 1, n), xp = reflect101(qx + 1, n);
+        const int x = x0 + lane - 1;                                    // output column of lanes 1 .. ME_COLS
+        const bool x_ok = lane >= 1 && lane <= ME_COLS && x < n;
+        const int rows = min(ME_ROWS, n - y0);
+        double hxx0 = 0, hxy0 = 0, hyy0 = 0, hxx1 = 0, hxy1 = 0, hyy1 = 0;   // row sums of gradient rows gy - 2, gy - 1
+        for (int r = 0; r < rows + 2; ++r) {
+            const int gy = min(max(y0 - 1 + r, -1), n);                 // <= n: y0 + rows <= n
+            const int qy = reflect101(gy, n);
+            const float* __restrict__ rm = img + (size_t)reflect101(qy - 1, n) * n;
+            const float* __restrict__ rq = img + (size_t)qy * n;
+            const float* __restrict__ rp = img + (size_t)reflect101(qy + 1, n) * n;
+            float pxx, pxy, pyy;
+            me_products(__ldg(rm + xm), __ldg(rm + qx), __ldg(rm + xp), __ldg(rq + xm), __ldg(rq + xp), __ldg(rp + xm), __ldg(rp + qx),
+                        __ldg(rp + xp), k0, k1, pxx, pxy, pyy);
+            const double dxx = (double)pxx, dxy = (double)pxy, dyy = (double)pyy;
+            // horizontal 3-sum centred on this lane's gradient column: (left + centre) + right
+            const double hxx2 = (__shfl_up_sync(FULLM, dxx, 1) + dxx) + __shfl_down_sync(FULLM, dxx, 1);
+            const double hxy2 = (__shfl_up_sync(FULLM, dxy, 1) + dxy) + __shfl_down_sync(FULLM, dxy, 1);
+            const double hyy2 = (__shfl_up_sync(FULLM, dyy, 1) + dyy) + __shfl_down_sync(FULLM, dyy, 1);
+            if (r >= 2 && x_ok) {
+                const double sxx = (hxx0 + hxx1) + hxx2, sxy = (hxy0 + hxy1) + hxy2, syy = (hyy0 + hyy1) + hyy2;
+                const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
+                const float d = __fsub_rn(a, cc);
+                resp[(size_t)(y0 + r - 2) * n + x] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
+            }
+            hxx0 = hxx1; hxy0 = hxy1; hyy0 = hyy1;
+            hxx1 = hxx2; hxy1 = hxy2; hyy1 = hyy2;
+        }
     }
 }
 
@@ -569,9 +528,9 @@ int rf_detect_prepare(rf_handle* h) {
 int rf_launch_min_eig(rf_handle* h, const float* d_img, size_t img_stride, int n, float* d_resp, size_t resp_stride, int S,
                       const int32_t* d_flags) {
     const double scale = 1.0 / ((double)(1 << 2) * 3.0);  // ksize 3, blockSize 3, f32 input
-    const int ntiles = ((n + ME_TW - 1) / ME_TW) * ((n + ME_TH - 1) / ME_TH);
-    dim3 blk(32, 8), grd(rf_tile_workers(h, ntiles, S), S);
-    k_min_eig<<<grd, blk, 0, h->stream>>>(d_img, img_stride, n, (float)(2.0 * scale), (float)(1.0 * scale), d_resp, resp_stride, d_flags);
+    const int nstrips = ((n + ME_COLS - 1) / ME_COLS) * ((n + ME_ROWS - 1) / ME_ROWS);
+    dim3 grd(rf_tile_workers(h, (nstrips + ME_WARPS - 1) / ME_WARPS, S), S);
+    k_min_eig<<<grd, 32 * ME_WARPS, 0, h->stream>>>(d_img, img_stride, n, (float)(2.0 * scale), (float)(1.0 * scale), d_resp, resp_stride, d_flags);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
