@@ -142,9 +142,24 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
         q14_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
         __syncwarp();
+        // The next-image window of the FIRST iteration sits at floor(nextPt - halfWin), known now: when it and the
+        // previous-image neighbourhood are both interior, their loads are issued together, so the level pays one global
+        // round trip before its first iteration instead of two (this kernel is latency-bound at 25 % occupancy).
+        int jx = INT_MIN, jy = INT_MIN;          // origin of the next-image window currently staged in s.J (none yet at this level)
+        const int jx0 = cv_floor(__fsub_rn(nx, half)), jy0 = cv_floor(__fsub_rn(ny, half));
+        const bool j_early = jx0 >= 0 && jy0 >= 0 && jx0 + 16 <= w && jy0 + 16 <= h;
         // 1. 18x18 neighbourhood (324 bytes)
         if (ipx >= 1 && ipy >= 1 && ipx + 17 <= w && ipy + 17 <= h) {
             // interior: lane r < 18 moves row r (18 bytes -> five words of the 20-byte shared row) from aligned loads
+            uint32_t jw0 = 0, jw1 = 0, jw2 = 0;
+            unsigned jm = 0;
+            const int jr = lane >> 1, jc0 = (lane & 1) * 8;
+            if (j_early) {
+                const uint8_t* pj = J + (size_t)(jy0 + jr) * pitch + jx0 + jc0;
+                jm = (unsigned)(reinterpret_cast<uintptr_t>(pj) & 3u);
+                const uint32_t* apj = reinterpret_cast<const uint32_t*>(pj - jm);
+                jw0 = __ldg(apj); jw1 = __ldg(apj + 1); jw2 = __ldg(apj + 2);
+            }
             if (lane < 18) {
                 const uint8_t* p = I + (size_t)(ipy - 1 + lane) * pitch + (ipx - 1);
                 const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
@@ -155,6 +170,10 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                 uint32_t* dst = reinterpret_cast<uint32_t*>(&s.I[lane][0]);
 #pragma unroll
                 for (int i = 0; i < 5; ++i) dst[i] = __funnelshift_r(q[i], q[i + 1], 8 * m);
+            }
+            if (j_early) {
+                *reinterpret_cast<uint2*>(&s.J[jr][jc0]) = make_uint2(__funnelshift_r(jw0, jw1, 8 * jm), __funnelshift_r(jw1, jw2, 8 * jm));
+                jx = jx0; jy = jy0;
             }
         } else {
             for (int idx = lane; idx < 18 * 18; idx += 32) {
@@ -211,7 +230,6 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
         D = __fdiv_rn(1.f, D);
         float qx = __fsub_rn(nx, half), qy = __fsub_rn(ny, half);  // nextPt -= halfWin
         float pdx = 0.f, pdy = 0.f;
-        int jx = INT_MIN, jy = INT_MIN;          // origin of the next-image window currently staged in s.J (none yet at this level)
         // 4. iterations
         for (int it = 0; it < a.max_iters; ++it) {
             const int inx = cv_floor(qx), iny = cv_floor(qy);
