@@ -1,7 +1,7 @@
 // k_detect.cu — feature detection and adaptive non-maximal suppression, entirely on the device.
 //
 // Replaces (reference file:line):
-//   getFeatures.py:22-53     getBlobsFromCart (detector front half)        -> k_min_eig / k_doh_* + k_nms_select + k_sort_keys
+//   getFeatures.py:22-53     getBlobsFromCart (detector front half)        -> k_min_eig / k_doh_* + k_nms_select + k_sort_tiles / k_sort_global / k_sort_merge
 //   getFeatures.py:66-72     adaptiveNMS (argsort + ssc)                   -> k_ssc_prepare_* + k_ssc_bisect
 //   ANMS.py:5-102            ssc (Suppression via Square Covering)         -> k_ssc_bisect (the WHOLE binary search)
 //
@@ -179,68 +179,110 @@ k_keys_to_rows(const unsigned long long* __restrict__ keys, unsigned n, int cols
 }
 
 // =====================================================================================
-// Ascending sort of each problem's keys: one CTA per problem, bitonic network, strides below
-// SORT_TILE inside shared memory.  The size follows the problem's own candidate count (device
-// memory), so the launch is static and graph-capturable.  Keys are unique (the low word is the
-// pixel index), so the result does not depend on the network.
+// Ascending sort of each problem's keys: a bitonic network spread over the machine.  The size follows the problem's
+// own candidate count (device memory), so the launches are static and graph-capturable: every launch is sized for the
+// key capacity and CTAs beyond a problem's padded size exit.  Keys are unique (the low word is the pixel index), so the
+// result does not depend on the network.
+//   k_sort_tiles    every tile of SORT_TILE keys fully sorted in shared memory (alternating direction = the network
+//                   up to stage k = SORT_TILE), padding with ~0 up to the next power of two
+//   k_sort_global   one stage (k, j >= SORT_TILE) of the network, one compare-exchange per thread
+//   k_sort_merge    the stages j < SORT_TILE of step k, per tile in shared memory
+// (Round 2's first version ran the whole network in ONE CTA per problem: 2.4 ms for 131 072 keys, the longest link of
+// the chained step's latency chain.)
 // =====================================================================================
 __device__ __forceinline__ void cswap(unsigned long long& a, unsigned long long& b, bool up) {
     if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
 }
 
+__device__ __forceinline__ unsigned sort_np2(unsigned n) {
+    unsigned np2 = 2;
+    while (np2 < n) np2 <<= 1;
+    return np2;
+}
+
 __global__ void __launch_bounds__(1024)
-k_sort_keys(unsigned long long* __restrict__ keys_base, unsigned cap, const unsigned* __restrict__ count,
-            const int32_t* __restrict__ flags) {
-    const int p = blockIdx.x;
+k_sort_tiles(unsigned long long* __restrict__ keys_base, unsigned cap, const unsigned* __restrict__ count,
+             const int32_t* __restrict__ flags) {
+    const int p = blockIdx.y;
     if (flags && !flags[p]) return;
-    __shared__ unsigned long long s[SORT_TILE];
-    unsigned long long* __restrict__ a = keys_base + (size_t)p * cap;
     const unsigned n = min(count[p], cap);
     if (n < 2) return;
-    unsigned np2 = 2;
-    while (np2 < n) np2 <<= 1;                    // <= cap (cap is a power of two)
-    const unsigned tid = threadIdx.x;
-    for (unsigned i = n + tid; i < np2; i += 1024) a[i] = ~0ull;
-    __syncthreads();
+    const unsigned np2 = sort_np2(n);                 // <= cap (cap is a power of two)
     const unsigned T = np2 < SORT_TILE ? np2 : SORT_TILE;
-    // tiles of T keys, fully sorted in shared memory (alternating direction = stage k = 2T of the network)
-    for (unsigned base = 0; base < np2; base += T) {
-        for (unsigned i = tid; i < T; i += 1024) s[i] = a[base + i];
-        __syncthreads();
-        for (unsigned k = 2; k <= T; k <<= 1)
-            for (unsigned j = k >> 1; j > 0; j >>= 1) {
-                for (unsigned t = tid; t < (T >> 1); t += 1024) {
-                    const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    cswap(s[i], s[i | j], ((base + i) & k) == 0);
-                }
-                __syncthreads();
-            }
-        for (unsigned i = tid; i < T; i += 1024) a[base + i] = s[i];
-        __syncthreads();
-    }
-    for (unsigned k = 2 * T; k <= np2; k <<= 1) {
-        for (unsigned j = k >> 1; j >= T; j >>= 1) {
-            for (unsigned t = tid; t < (np2 >> 1); t += 1024) {
+    const unsigned base = blockIdx.x * SORT_TILE;
+    if (base >= np2) return;
+    __shared__ unsigned long long s[SORT_TILE];
+    unsigned long long* __restrict__ a = keys_base + (size_t)p * cap;
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < T; i += 1024) s[i] = base + i < n ? a[base + i] : ~0ull;
+    __syncthreads();
+    for (unsigned k = 2; k <= T; k <<= 1)
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned t = tid; t < (T >> 1); t += 1024) {
                 const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                unsigned long long x = a[i], y = a[i | j];
-                if ((x > y) == ((i & k) == 0)) { a[i] = y; a[i | j] = x; }
+                cswap(s[i], s[i | j], ((base + i) & k) == 0);
             }
             __syncthreads();
         }
-        for (unsigned base = 0; base < np2; base += T) {
-            for (unsigned i = tid; i < T; i += 1024) s[i] = a[base + i];
-            __syncthreads();
-            for (unsigned j = T >> 1; j > 0; j >>= 1) {
-                for (unsigned t = tid; t < (T >> 1); t += 1024) {
-                    const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    cswap(s[i], s[i | j], ((base + i) & k) == 0);
-                }
-                __syncthreads();
-            }
-            for (unsigned i = tid; i < T; i += 1024) a[base + i] = s[i];
-            __syncthreads();
+    for (unsigned i = tid; i < T; i += 1024) a[base + i] = s[i];
+}
+
+__global__ void __launch_bounds__(1024)
+k_sort_global(unsigned long long* __restrict__ keys_base, unsigned cap, const unsigned* __restrict__ count, unsigned k, unsigned j,
+              const int32_t* __restrict__ flags) {
+    const int p = blockIdx.y;
+    if (flags && !flags[p]) return;
+    const unsigned n = min(count[p], cap);
+    if (n < 2) return;
+    const unsigned np2 = sort_np2(n);
+    if (k > np2) return;
+    const unsigned t = blockIdx.x * 1024 + threadIdx.x;
+    if (t >= (np2 >> 1)) return;
+    unsigned long long* __restrict__ a = keys_base + (size_t)p * cap;
+    const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const unsigned long long x = a[i], y = a[i | j];
+    if ((x > y) == ((i & k) == 0)) { a[i] = y; a[i | j] = x; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_sort_merge(unsigned long long* __restrict__ keys_base, unsigned cap, const unsigned* __restrict__ count, unsigned k,
+             const int32_t* __restrict__ flags) {
+    const int p = blockIdx.y;
+    if (flags && !flags[p]) return;
+    const unsigned n = min(count[p], cap);
+    if (n < 2) return;
+    const unsigned np2 = sort_np2(n);
+    const unsigned base = blockIdx.x * SORT_TILE;
+    if (k > np2 || base >= np2) return;
+    __shared__ unsigned long long s[SORT_TILE];
+    unsigned long long* __restrict__ a = keys_base + (size_t)p * cap;
+    const unsigned tid = threadIdx.x;
+    for (unsigned i = tid; i < SORT_TILE; i += 1024) s[i] = a[base + i];
+    __syncthreads();
+    for (unsigned j = SORT_TILE >> 1; j > 0; j >>= 1) {
+        for (unsigned t = tid; t < (SORT_TILE >> 1); t += 1024) {
+            const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            cswap(s[i], s[i | j], ((base + i) & k) == 0);
         }
+        __syncthreads();
     }
+    for (unsigned i = tid; i < SORT_TILE; i += 1024) a[base + i] = s[i];
+}
+
+// the whole network for S problems of capacity `cap` (a power of two)
+static int launch_sort_keys(rf_handle* h, unsigned long long* keys, unsigned cap, const unsigned* count, int S, const int32_t* d_flags) {
+    const unsigned tiles = cap > SORT_TILE ? cap / SORT_TILE : 1;
+    k_sort_tiles<<<dim3(tiles, S), 1024, 0, h->stream>>>(keys, cap, count, d_flags);
+    RF_CHECK_LAUNCH(h);
+    for (unsigned k = 2 * SORT_TILE; k <= cap; k <<= 1) {
+        for (unsigned j = k >> 1; j >= SORT_TILE; j >>= 1) {
+            k_sort_global<<<dim3((cap / 2 + 1023) / 1024, S), 1024, 0, h->stream>>>(keys, cap, count, k, j, d_flags);
+            RF_CHECK_LAUNCH(h);
+        }
+        k_sort_merge<<<dim3(tiles, S), 1024, 0, h->stream>>>(keys, cap, count, k, d_flags);
+        RF_CHECK_LAUNCH(h);
+    }
+    return RF_OK;
 }
 
 // sorted keys -> keypoints (row, col) for SSC: the strongest min(count, max_kp) candidates
@@ -551,9 +593,7 @@ int rf_launch_select_sorted(rf_handle* h, const DetectWs& ws, const float* d_res
     k_nms_select<<<grd, blk, 0, h->stream>>>(d_resp, resp_stride, ws.rows, ws.cols, threshold, rel, ws.maxbits, ws.keys, ws.key_cap,
                                              ws.count, d_flags);
     RF_CHECK_LAUNCH(h);
-    k_sort_keys<<<S, 1024, 0, h->stream>>>(ws.keys, ws.key_cap, ws.count, d_flags);
-    RF_CHECK_LAUNCH(h);
-    return RF_OK;
+    return launch_sort_keys(h, ws.keys, ws.key_cap, ws.count, S, d_flags);
 }
 
 int rf_launch_ssc(rf_handle* h, const DetectWs& ws, int num_ret, double tol, int cols, int rows, const int32_t* d_flags) {
