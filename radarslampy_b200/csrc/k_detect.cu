@@ -31,6 +31,7 @@
 #define CELL_EMPTY 0xffffffffu
 #define SSC_THREADS 1024
 #define SSC_SMEM_CELLS 40960            // 160 KB of shared cover grid
+#define SSC_COV_WORDS 8192               // coverage bits for up to 262 144 cells (cells_cap of the workspaces is 1 << 18)
 #define SORT_TILE 4096                  // u64 keys sorted inside shared memory (32 KB)
 
 // =====================================================================================
@@ -321,6 +322,10 @@ struct SscArgs {
 
 __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
     extern __shared__ uint32_t s_grid[];           // SSC_SMEM_CELLS words
+    // cells within reach of a keypoint selected so far in this probe, one bit per cell: a selected keypoint marks its
+    // (2 reach + 1)^2 cells once, and a live keypoint then dies on ONE bit test instead of scanning that neighbourhood
+    // for selected keypoints (25 grid reads + 25 mask reads per live keypoint and round, the bulk of this kernel)
+    __shared__ uint32_t s_cov[SSC_COV_WORDS];
     __shared__ int s_w[32];
     __shared__ int s_nsel, s_next;
     const int p = blockIdx.x;
@@ -372,6 +377,8 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
             const bool in_smem = cells <= SSC_SMEM_CELLS;
             uint32_t* g = in_smem ? s_grid : ggrid;
             if (in_smem) for (unsigned i = tid; i < cells; i += SSC_THREADS) s_grid[i] = CELL_EMPTY;
+            const bool use_cov = cells <= 32u * SSC_COV_WORDS;
+            if (use_cov) for (unsigned i = tid; i < (cells + 31) / 32; i += SSC_THREADS) s_cov[i] = 0u;
             for (int i = tid; i < n; i += SSC_THREADS) {
                 const double2 q = rc[i];
                 cell[i] = (unsigned)((int)floor(q.x / c) * stride + (int)floor(q.y / c));     // ANMS.py:52-59
@@ -398,7 +405,12 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
                     for (int rr = r0; rr <= r1 && best; ++rr)
                         for (int c2 = c0; c2 <= c1; ++c2)
                             if (g[rr * stride + c2] < i) { best = false; break; }
-                    if (best) { atomicOr(&mask[i >> 5], 1u << (i & 31)); atomicAdd(&s_nsel, 1); }
+                    if (best) {
+                        atomicOr(&mask[i >> 5], 1u << (i & 31)); atomicAdd(&s_nsel, 1);
+                        if (use_cov)
+                            for (int rr = r0; rr <= r1; ++rr)
+                                for (int c2 = c0; c2 <= c1; ++c2) { const unsigned cj = (unsigned)(rr * stride + c2); atomicOr(&s_cov[cj >> 5], 1u << (cj & 31)); }
+                    }
                 }
                 __syncthreads();
                 // C: survivors = live keypoints not within reach of a keypoint selected this round
@@ -410,7 +422,10 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
                     if (t < nal) {
                         i = first ? (unsigned)t : src[t];
                         keep = !((mask[i >> 5] >> (i & 31)) & 1u);
-                        if (keep) {
+                        if (keep && use_cov) {
+                            const unsigned ci = cell[i];
+                            keep = !((s_cov[ci >> 5] >> (ci & 31)) & 1u);
+                        } else if (keep) {
                             const unsigned ci = cell[i];
                             const int r = (int)(ci / (unsigned)stride), cc = (int)(ci - (unsigned)r * (unsigned)stride);
                             const int r0 = max(r - reach, 0), r1 = min(r + reach, ncr), c0 = max(cc - reach, 0), c1 = min(cc + reach, ncc);
