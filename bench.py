@@ -68,7 +68,7 @@ def parse_args():
     ap.add_argument("--chain-seq", type=int, default=256, help="chained leg: sequences per GPU in lock step")
     ap.add_argument("--chain-steps", type=int, default=12)
     ap.add_argument("--gather-every", type=int, default=8, help="multi-GPU: steps whose pose records travel in one NCCL gather")
-    ap.add_argument("--chain-runners", type=int, default=4, help="chained leg: rf_seq runners (streams) the sequences are split over")
+    ap.add_argument("--chain-runners", type=int, default=16, help="chained leg: rf_seq runners (streams) the sequences are split over")
     return ap.parse_args()
 
 

@@ -45,11 +45,16 @@ int rf_detect_ws_init(rf_handle* h, const DetectWs& ws);
 int rf_detect_prepare(rf_handle* h);   // kernel attributes (call once per device before any stream capture)
 
 // response of mode 0 (structure-tensor minimum eigenvalue) for every flagged problem: img [S][n][n] f32
+// d_maxbits (optional, [S] u32 cleared by the caller): the maximum response of every problem, accumulated while the
+// response is written (saves the separate pass over the response plane a relative threshold would need)
 int rf_launch_min_eig(rf_handle* h, const float* d_img, size_t img_stride, int n, float* d_resp, size_t resp_stride, int S,
-                      const int32_t* d_flags);
-// threshold (absolute if >= 0, else -threshold x max response) + 3x3 NMS -> sortable keys, then sort them
+                      const int32_t* d_flags, unsigned* d_maxbits = nullptr);
+// clear the candidate counters and the response maxima of a workspace (first launch of a detection)
+int rf_launch_detect_clear(rf_handle* h, const DetectWs& ws);
+// threshold (absolute if >= 0, else -threshold x max response) + 3x3 NMS -> sortable keys, then sort them.
+// have_max: ws.count / ws.maxbits were cleared by rf_launch_detect_clear and ws.maxbits filled by rf_launch_min_eig
 int rf_launch_select_sorted(rf_handle* h, const DetectWs& ws, const float* d_resp, size_t resp_stride, float threshold,
-                            const int32_t* d_flags);
+                            const int32_t* d_flags, bool have_max = false);
 // keys -> (row, col) keypoints (at most RF_SSC_MAX_CANDIDATES strongest), then the SSC bisection
 int rf_launch_ssc_from_keys(rf_handle* h, const DetectWs& ws, int num_ret, double tol, const int32_t* d_flags);
 // SSC bisection on keypoints already in ws.rc / ws.n_kp

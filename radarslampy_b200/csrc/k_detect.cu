@@ -70,7 +70,7 @@ __device__ __forceinline__ void me_products(float a00, float a01, float a02, flo
 
 __global__ void __launch_bounds__(32 * ME_WARPS)
 k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0, float k1, float* __restrict__ resp_base,
-          size_t resp_stride, const int32_t* __restrict__ flags) {
+          size_t resp_stride, const int32_t* __restrict__ flags, unsigned* __restrict__ maxbits) {
     // grid = (strip workers, problems): a CTA walks the strips of its problem, so the un-flagged problems of a lock-step
     // batch cost gridDim.x empty CTAs each instead of one per strip
     if (flags && !flags[blockIdx.y]) return;
@@ -78,6 +78,7 @@ k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0
     float* __restrict__ resp = resp_base + (size_t)blockIdx.y * resp_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int strips_x = (n + ME_COLS - 1) / ME_COLS, nstrips = strips_x * ((n + ME_ROWS - 1) / ME_ROWS);
+    float vmax = 0.f;    // maximum of the responses this lane wrote (k_max_resp's rule: the maximum of max(resp, 0))
     for (int t = blockIdx.x * ME_WARPS + warp; t < nstrips; t += gridDim.x * ME_WARPS) {
         const int sy = t / strips_x, sx = t - sy * strips_x;
         const int x0 = sx * ME_COLS, y0 = sy * ME_ROWS;
@@ -107,11 +108,18 @@ k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0
                 const double sxx = (hxx0 + hxx1) + hxx2, sxy = (hxy0 + hxy1) + hxy2, syy = (hyy0 + hyy1) + hyy2;
                 const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, cc = __fmul_rn((float)syy, 0.5f);
                 const float d = __fsub_rn(a, cc);
-                resp[(size_t)(y0 + r - 2) * n + x] = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
+                const float v = __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(__fmaf_rn(d, d, __fmul_rn(b, b))));
+                resp[(size_t)(y0 + r - 2) * n + x] = v;
+                vmax = fmaxf(vmax, v);
             }
             hxx0 = hxx1; hxy0 = hxy1; hyy0 = hyy1;
             hxx1 = hxx2; hxy1 = hxy2; hyy1 = hyy2;
         }
+    }
+    if (maxbits) {   // bit pattern order == value order for floats >= 0
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULLM, vmax, d));
+        if (lane == 0) atomicMax(maxbits + blockIdx.y, __float_as_uint(vmax));
     }
 }
 
@@ -139,30 +147,45 @@ __global__ void k_clear_u32(unsigned* __restrict__ a, unsigned* __restrict__ b, 
 // high word = ~bits(resp) (so ascending key = descending response), low word = ~pixel index
 // (ties: descending index, the order cv::goodFeaturesToTrack's pointer comparison produces).
 // thr_rel != 0: threshold = (float)((double)max * thr_rel), cv's maxVal * qualityLevel.
-__global__ void __launch_bounds__(256)
+// Warp strips like k_min_eig: lane l stands on column x0 - 1 + l, reads ONE response per row, takes the horizontal
+// 3-maximum from its neighbours by shuffle and keeps the last rows in registers for the vertical one (the per-pixel
+// version read 10 responses for every pixel above the threshold: 25 us per 1996^2 frame).
+#define NMS_COLS 30
+#define NMS_ROWS 64
+#define NMS_WARPS 4
+__global__ void __launch_bounds__(32 * NMS_WARPS)
 k_nms_select(const float* __restrict__ resp_base, size_t resp_stride, int rows, int cols, float thr_abs, double thr_rel,
              const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ keys_base, unsigned cap,
              unsigned* __restrict__ count, const int32_t* __restrict__ flags) {
-    const int p = blockIdx.y;      // grid = (tile workers, problems), see k_min_eig
+    const int p = blockIdx.y;      // grid = (strip workers, problems), see k_min_eig
     if (flags && !flags[p]) return;
     const float* __restrict__ resp = resp_base + (size_t)p * resp_stride;
     const float thr = thr_rel != 0.0 ? (float)((double)__uint_as_float(maxbits[p]) * thr_rel) : thr_abs;
-    const int tiles_x = (cols + 31) / 32, ntiles = tiles_x * ((rows + 7) / 8);
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int x = (t % tiles_x) * 32 + threadIdx.x, y = (t / tiles_x) * 8 + threadIdx.y;
-        if (x < 1 || y < 1 || x >= cols - 1 || y >= rows - 1) continue;
-        const float v = __ldg(resp + (size_t)y * cols + x);
-        if (!(v > thr)) continue;
-        float mx = v;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) mx = fmaxf(mx, __ldg(resp + (size_t)(y + dy) * cols + (x + dx)));
-        if (v != mx) continue;
-        const unsigned slot = atomicAdd(count + p, 1u);
-        if (slot < cap) {
-            const unsigned idx = (unsigned)y * (unsigned)cols + (unsigned)x;
-            keys_base[(size_t)p * cap + slot] = ((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned long long)(~idx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strips_x = (cols + NMS_COLS - 1) / NMS_COLS, nstrips = strips_x * ((rows + NMS_ROWS - 1) / NMS_ROWS);
+    const float NEG = -3.402823466e+38f;
+    for (int t = blockIdx.x * NMS_WARPS + warp; t < nstrips; t += gridDim.x * NMS_WARPS) {
+        const int sy = t / strips_x, sx = t - sy * strips_x;
+        const int x0 = sx * NMS_COLS, y0 = sy * NMS_ROWS;
+        const int x = x0 - 1 + lane;                                  // this lane's column
+        const bool x_in = x >= 0 && x < cols;
+        const bool x_out = lane >= 1 && lane <= NMS_COLS && x >= 1 && x < cols - 1;   // interior output column of this strip
+        const int nr = min(NMS_ROWS, rows - y0);
+        float h0 = NEG, h1 = NEG, vc = NEG;     // horizontal maxima of rows y - 2, y - 1; the centre value of row y - 1
+        for (int r = 0; r < nr + 2; ++r) {
+            const int y = y0 - 1 + r;
+            const float v = (x_in && y >= 0 && y < rows) ? __ldg(resp + (size_t)y * cols + x) : NEG;
+            const float h2 = fmaxf(fmaxf(__shfl_up_sync(FULLM, v, 1), v), __shfl_down_sync(FULLM, v, 1));
+            // centre row y - 1 (an output row of this strip for r >= 2), interior rows only
+            const int yc = y - 1;
+            if (r >= 2 && x_out && yc >= 1 && yc < rows - 1 && vc > thr && vc == fmaxf(fmaxf(h0, h1), h2)) {
+                const unsigned slot = atomicAdd(count + p, 1u);
+                if (slot < cap) {
+                    const unsigned idx = (unsigned)yc * (unsigned)cols + (unsigned)x;
+                    keys_base[(size_t)p * cap + slot] = ((unsigned long long)(~__float_as_uint(vc)) << 32) | (unsigned long long)(~idx);
+                }
+            }
+            h0 = h1; h1 = h2; vc = v;
         }
     }
 }
@@ -583,30 +606,42 @@ int rf_detect_prepare(rf_handle* h) {
 }
 
 int rf_launch_min_eig(rf_handle* h, const float* d_img, size_t img_stride, int n, float* d_resp, size_t resp_stride, int S,
-                      const int32_t* d_flags) {
+                      const int32_t* d_flags, unsigned* d_maxbits) {
     const double scale = 1.0 / ((double)(1 << 2) * 3.0);  // ksize 3, blockSize 3, f32 input
     const int nstrips = ((n + ME_COLS - 1) / ME_COLS) * ((n + ME_ROWS - 1) / ME_ROWS);
     dim3 grd(rf_tile_workers(h, (nstrips + ME_WARPS - 1) / ME_WARPS, S), S);
-    k_min_eig<<<grd, 32 * ME_WARPS, 0, h->stream>>>(d_img, img_stride, n, (float)(2.0 * scale), (float)(1.0 * scale), d_resp, resp_stride, d_flags);
+    k_min_eig<<<grd, 32 * ME_WARPS, 0, h->stream>>>(d_img, img_stride, n, (float)(2.0 * scale), (float)(1.0 * scale), d_resp, resp_stride, d_flags,
+                                                    d_maxbits);
+    RF_CHECK_LAUNCH(h);
+    return RF_OK;
+}
+
+int rf_launch_detect_clear(rf_handle* h, const DetectWs& ws) {
+    k_clear_u32<<<(ws.S + 255) / 256, 256, 0, h->stream>>>(ws.count, ws.maxbits, ws.S);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
 
 int rf_launch_select_sorted(rf_handle* h, const DetectWs& ws, const float* d_resp, size_t resp_stride, float threshold,
-                            const int32_t* d_flags) {
+                            const int32_t* d_flags, bool have_max) {
     const int S = ws.S;
-    k_clear_u32<<<(S + 255) / 256, 256, 0, h->stream>>>(ws.count, ws.maxbits, S);
-    RF_CHECK_LAUNCH(h);
+    if (!have_max) {
+        int rc = rf_launch_detect_clear(h, ws);
+        if (rc) return rc;
+    }
     double rel = 0.0;
     if (threshold < 0) {   // relative: -threshold is cv2.goodFeaturesToTrack's qualityLevel (fraction of the maximum)
-        dim3 g(h->sm_count * 2 > 64 ? 64 : h->sm_count * 2, S);
-        k_max_resp<<<g, 256, 0, h->stream>>>(d_resp, resp_stride, (size_t)ws.rows * ws.cols, ws.maxbits, d_flags);
-        RF_CHECK_LAUNCH(h);
+        if (!have_max) {
+            dim3 g(h->sm_count * 2 > 64 ? 64 : h->sm_count * 2, S);
+            k_max_resp<<<g, 256, 0, h->stream>>>(d_resp, resp_stride, (size_t)ws.rows * ws.cols, ws.maxbits, d_flags);
+            RF_CHECK_LAUNCH(h);
+        }
         rel = (double)(-threshold);
     }
-    dim3 blk(32, 8), grd(rf_tile_workers(h, ((ws.cols + 31) / 32) * ((ws.rows + 7) / 8), S), S);
-    k_nms_select<<<grd, blk, 0, h->stream>>>(d_resp, resp_stride, ws.rows, ws.cols, threshold, rel, ws.maxbits, ws.keys, ws.key_cap,
-                                             ws.count, d_flags);
+    const int nstrips = ((ws.cols + NMS_COLS - 1) / NMS_COLS) * ((ws.rows + NMS_ROWS - 1) / NMS_ROWS);
+    dim3 grd(rf_tile_workers(h, (nstrips + NMS_WARPS - 1) / NMS_WARPS, S), S);
+    k_nms_select<<<grd, 32 * NMS_WARPS, 0, h->stream>>>(d_resp, resp_stride, ws.rows, ws.cols, threshold, rel, ws.maxbits, ws.keys, ws.key_cap,
+                                                        ws.count, d_flags);
     RF_CHECK_LAUNCH(h);
     return launch_sort_keys(h, ws.keys, ws.key_cap, ws.count, S, d_flags);
 }

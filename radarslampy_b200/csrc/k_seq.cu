@@ -508,8 +508,9 @@ static int seq_enqueue_detect(rf_handle* h, rf_seq* q) {
                                                h->n, q->d_cart, n2, q->d_flags);
     RF_CHECK_LAUNCH(h);
     if (q->detector_mode == 0) {
-        if ((rc = rf_launch_min_eig(h, q->d_cart, n2, h->n, q->det.resp, q->det.resp_stride, q->S, q->d_flags))) return rc;
-        if ((rc = rf_launch_select_sorted(h, q->det, q->det.resp, q->det.resp_stride, (float)-c.detect_quality, q->d_flags))) return rc;
+        if ((rc = rf_launch_detect_clear(h, q->det))) return rc;
+        if ((rc = rf_launch_min_eig(h, q->d_cart, n2, h->n, q->det.resp, q->det.resp_stride, q->S, q->d_flags, q->det.maxbits))) return rc;
+        if ((rc = rf_launch_select_sorted(h, q->det, q->det.resp, q->det.resp_stride, (float)-c.detect_quality, q->d_flags, true))) return rc;
         if ((rc = rf_launch_ssc_from_keys(h, q->det, c.ssc_num_ret, c.ssc_tolerance, q->d_flags))) return rc;
     } else {
         // the reference's detector: blob_doh -> adaptiveNMS' argsort by sigma -> ssc (getFeatures.py:47-51,66-72)
