@@ -720,6 +720,7 @@ def _fe_config(args, rb, max_frames, max_pairs, max_features):
     cfg.cart_res_m = 2 * args.res
     cfg.dist_thr_px = 0.5 / (2 * args.res)
     cfg.max_frames, cfg.max_pairs, cfg.max_features = max_frames, max(max_pairs, 1), max_features
+    cfg.write_cart_f32 = args.write_f32      # 0: the fused image path of the headline (the library default materialises the f32 image)
     return cfg
 
 

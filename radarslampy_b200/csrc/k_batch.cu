@@ -243,6 +243,7 @@ static int batch_create_sized(rf_handle* h, int max_frames, int max_pairs, rf_ba
     }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // tail streams run above the image kernels of later batches
+    { const char* e = getenv("RADARFE_TAIL_PRIO"); if (e && e[0] == 'l') prio_hi = prio_lo; }   // diagnostic: tail at the image kernels' priority
     if (cudaStreamCreateWithPriority(&b->tail, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_uploaded, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
