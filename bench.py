@@ -24,6 +24,7 @@ Further legs inside the same JSON line (--legs, default all):
   mds         configs[2]: motion-distorted scans + the motion-distortion solve (value and e2e)
   stress      configs[4]: dense 2000^2 grid, 10 k SSC features, 4-level KLT -> tracks/s
   detect_ssc / fmt / peaks   on-device detection + SSC bisection, FMT rotation prior, polar peak extraction
+  clique_real rejectOutliers on the real data/tiny graphs and the reference's outlier_test.npz, one at a time
   parity_sample   GPU poses / inlier counts of the first pairs against what the cpu_baseline leg just computed
 
 --impl reference times the reference's own CPU path (the third-party calls the reference
@@ -63,7 +64,7 @@ def parse_args():
     ap.add_argument("--batches", type=int, default=5, help="batches in flight on one handle (pipeline depth; the clique + MDS tail of a batch lasts about three steps)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (multi-GPU runs)")
     ap.add_argument("--no-gather", action="store_true", help="diagnostic: skip the per-step NCCL pose gather")
-    ap.add_argument("--legs", default="all", help="comma list of extra legs: chained,strong,mds,stress,detect_ssc,fmt,peaks (all | none)")
+    ap.add_argument("--legs", default="all", help="comma list of extra legs: chained,strong,mds,stress,detect_ssc,fmt,peaks,clique_real (all | none)")
     ap.add_argument("--pairs", type=int, default=4096, help="strong leg: total independent pairs (BASELINE configs[3])")
     ap.add_argument("--chain-seq", type=int, default=256, help="chained leg: sequences per GPU in lock step")
     ap.add_argument("--chain-steps", type=int, default=12)
@@ -72,7 +73,7 @@ def parse_args():
     return ap.parse_args()
 
 
-ALL_LEGS = ("chained", "strong", "mds", "stress", "detect_ssc", "fmt", "peaks")
+ALL_LEGS = ("chained", "strong", "mds", "stress", "detect_ssc", "fmt", "peaks", "clique_real")
 CHAIN_WARMUP = 3
 
 
@@ -432,6 +433,8 @@ def main():
                 out = leg_fmt(ctx, raw_np)
             elif name == "peaks":
                 out = leg_peaks(ctx, raw_np)
+            elif name == "clique_real":
+                out = leg_clique_real(ctx)
         except Exception as e:                 # a failing leg must not take the headline down with it
             out = {"error": f"{type(e).__name__}: {e}"}
         if out is not None:
@@ -1223,6 +1226,36 @@ def leg_peaks(ctx, raw_np):
     fe.close()
     return {"workload": f"getPointCloudPolarInd (getPointCloud.py:10-60) on one {polar.shape[0]} x {polar.shape[1]} f32 polar scan, host in / host out",
             "value": 1.0 / dt, "unit": "scans/s", "ms_per_scan": 1e3 * dt, "peaks": int(len(pk))}
+
+
+def leg_clique_real(ctx):
+    """a6 on REAL graphs: the 10 data/tiny pairs (edge density 0.24-0.82, up to 36 k maximal cliques) and the reference's
+    outlier_test.npz fixture (139 nodes, 8 097 maximal cliques), each through rf_reject_outliers alone on the device (CUDA events:
+    H2D of the points, k_adjacency, k_maxclique, k_clique, D2H of the mask), masks against the goldens recorded from the
+    unmodified reference (tests/golden).  The synthetic batches of the headline are inlier-dominated; these are not."""
+    from radarslampy_b200 import _ffi
+    g = os.path.join(ROOT, "tests", "golden")
+    st, fx = np.load(os.path.join(g, "tiny_stages.npz")), np.load(os.path.join(g, "clique_fixture.npz"))
+    cases = [(f"tiny pair {i}", st[f"klt_good_old_{i}"], st[f"klt_good_new_{i}"], st[f"rej_mask_{i}"]) for i in range(10)]
+    cases.append(("outlier_test.npz", fx["prev"], fx["new"], fx["mask"]))
+    fe = _ffi.RadarFE(device=ctx["local_rank"])        # the reference's own constants (0.0432 m/bin: threshold 5.79 px)
+    rows = []
+    for name, prev, new, want in cases:
+        fe.reject_outliers(prev, new)
+        best = 1e9
+        for _ in range(5):
+            fe.timer_start()
+            mask, n_in, nodes = fe.reject_outliers(prev, new)
+            best = min(best, fe.timer_stop_ms())
+        rows.append({"case": name, "nodes": int(len(prev)), "clique_size": int(n_in), "descents": int(nodes), "ms": round(best, 4),
+                     "mask_exact": bool(np.array_equal(mask, want.astype(bool)))})
+    fe.close()
+    ms = [r["ms"] for r in rows]
+    return {"workload": "rejectOutliers (outlierRejection.py:16-95) on the 10 data/tiny pairs and the reference's outlier_test.npz, one graph "
+                        "at a time, device-timed",
+            "value": 1e3 / float(np.mean(ms)), "unit": "graphs/s (one at a time)", "worst_tiny_ms": max(ms[:10]), "median_ms": float(np.median(ms)),
+            "fixture_ms": ms[-1], "all_masks_exact": all(r["mask_exact"] for r in rows), "rows": rows,
+            "networkx_ms": "22-729 ms per graph on one host core (profiles/r02f_clique_table.json)"}
 
 
 if __name__ == "__main__":
