@@ -49,7 +49,9 @@ struct __align__(16) WarpSmem {
     uint8_t I[18][20];   // previous-image neighbourhood, origin (ip.x-1, ip.y-1); rows are 5 aligned words
     uint8_t pad_[8];     // keeps D and J 16-byte aligned (vector stores in the staging fast paths)
     short2 D[16][16];    // Scharr (dx, dy) at (ip.x + c, ip.y + r)
-    uint8_t J[16][16];   // next-image window, origin (in.x, in.y)
+    uint16_t J[16][16];  // next-image window as horizontal PAIRS: J[y][x] = pixel (y, x) | pixel (y, x + 1) << 8, origin (in.x, in.y);
+                         // a bilinear sample is then two 16-bit loads and two dp2a (signed Q14 weights x unsigned bytes)
+                         // instead of four byte loads and four multiplies; column 15 pairs with a byte that is never sampled
 };
 
 // exact warp sum of int32 values whose total may exceed 32 bits
@@ -72,6 +74,11 @@ __device__ __forceinline__ void q14_weights(float a, float b, int& w00, int& w01
 // words: lane = 2 * row + half moves 8 consecutive bytes (three aligned loads, two funnel shifts, one 64-bit
 // shared store).  The third word may reach 3 bytes past the window: into the same row, the next row, or the slack
 // every level allocation carries.  Windows that touch the border take the REFLECT_101 byte path.
+// the eight pixel pairs starting at bytes 0 .. 7 of (lo | hi << 32), `nxt` holding byte 8: one 128-bit shared store
+__device__ __forceinline__ uint4 j_pairs(uint32_t lo, uint32_t hi, uint32_t nxt) {
+    return make_uint4(__byte_perm(lo, hi, 0x2110), __byte_perm(lo, hi, 0x4332), __byte_perm(hi, nxt, 0x2110), __byte_perm(hi, nxt, 0x4332));
+}
+
 __device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ J, int pitch, int w, int h, int ox, int oy, int lane) {
     if (ox >= 0 && oy >= 0 && ox + 16 <= w && oy + 16 <= h) {
         const int r = lane >> 1, c0 = (lane & 1) * 8;
@@ -79,21 +86,31 @@ __device__ __forceinline__ void load_J(WarpSmem& s, const uint8_t* __restrict__ 
         const unsigned m = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u);
         const uint32_t* ap = reinterpret_cast<const uint32_t*>(p - m);
         const uint32_t w0 = __ldg(ap), w1 = __ldg(ap + 1), w2 = __ldg(ap + 2);
-        *reinterpret_cast<uint2*>(&s.J[r][c0]) = make_uint2(__funnelshift_r(w0, w1, 8 * m), __funnelshift_r(w1, w2, 8 * m));
+        *reinterpret_cast<uint4*>(&s.J[r][c0]) = j_pairs(__funnelshift_r(w0, w1, 8 * m), __funnelshift_r(w1, w2, 8 * m), __funnelshift_r(w2, 0u, 8 * m));
     } else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int idx = lane + 32 * k, r = idx >> 4, c = idx & 15;
-            s.J[r][c] = __ldg(J + (size_t)reflect101(oy + r, h) * pitch + reflect101(ox + c, w));
+            const uint8_t* row = J + (size_t)reflect101(oy + r, h) * pitch;
+            // (the partner of column 15 is never sampled; any in-row byte will do)
+            s.J[r][c] = (uint16_t)(__ldg(row + reflect101(ox + c, w)) | ((unsigned)__ldg(row + reflect101(min(ox + c + 1, ox + 15), w)) << 8));
         }
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ int j_sample(const WarpSmem& s, int y, int x, int w00, int w01, int w10, int w11) {
-    const int v = s.J[y][x] * w00 + s.J[y][x + 1] * w01 + s.J[y + 1][x] * w10 + s.J[y + 1][x + 1] * w11;
+// wtop = w00 | w01 << 16, wbot = w10 | w11 << 16 as signed 16-bit halves (w11 = 2^14 - w00 - w01 - w10 can be -1)
+// signed 16-bit halves of `a` x unsigned bytes 0, 1 of `b`, accumulated into c (the CUDA intrinsics only offer same-signedness forms)
+__device__ __forceinline__ int dp2a_lo_s16_u8(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int j_sample(const WarpSmem& s, int y, int x, int wtop, int wbot) {
+    const int v = dp2a_lo_s16_u8(wbot, (unsigned)s.J[y + 1][x], dp2a_lo_s16_u8(wtop, (unsigned)s.J[y][x], 0));
     return (v + (1 << 8)) >> 9;
 }
+__device__ __forceinline__ int pack_w(int lo, int hi) { return (lo & 0xFFFF) | (hi << 16); }
 
 __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const KltArgs a) {
     __shared__ WarpSmem smem[KLT_WARPS];
@@ -172,7 +189,8 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                 for (int i = 0; i < 5; ++i) dst[i] = __funnelshift_r(q[i], q[i + 1], 8 * m);
             }
             if (j_early) {
-                *reinterpret_cast<uint2*>(&s.J[jr][jc0]) = make_uint2(__funnelshift_r(jw0, jw1, 8 * jm), __funnelshift_r(jw1, jw2, 8 * jm));
+                *reinterpret_cast<uint4*>(&s.J[jr][jc0]) = j_pairs(__funnelshift_r(jw0, jw1, 8 * jm), __funnelshift_r(jw1, jw2, 8 * jm),
+                                                                   __funnelshift_r(jw2, 0u, 8 * jm));
                 jx = jx0; jy = jy0;
             }
         } else {
@@ -245,10 +263,11 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                 jx = inx; jy = iny;
             }
             int b1 = 0, b2 = 0;
+            const int wtop = pack_w(w00, w01), wbot = pack_w(w10, w11);
 #pragma unroll
             for (int j = 0; j < KLT_PER_LANE; ++j) {
                 if (lane + 32 * j < KLT_NPIX) {
-                    const int diff = j_sample(s, wy[j], wx[j], w00, w01, w10, w11) - Iw[j];
+                    const int diff = j_sample(s, wy[j], wx[j], wtop, wbot) - Iw[j];
                     b1 += diff * Ix[j]; b2 += diff * Iy[j];
                 }
             }
@@ -278,9 +297,10 @@ __global__ void __launch_bounds__(KLT_WARPS * 32, KLT_MIN_BLOCKS) k_klt(const Kl
                     load_J(s, J, pitch, w, h, iex, iey, lane);
                 }
                 int e = 0;
+                const int wtop = pack_w(w00, w01), wbot = pack_w(w10, w11);
 #pragma unroll
                 for (int j = 0; j < KLT_PER_LANE; ++j)
-                    if (lane + 32 * j < KLT_NPIX) e += abs(j_sample(s, wy[j], wx[j], w00, w01, w10, w11) - Iw[j]);
+                    if (lane + 32 * j < KLT_NPIX) e += abs(j_sample(s, wy[j], wx[j], wtop, wbot) - Iw[j]);
                 err = __fdiv_rn((float)warp_sum_exact(e), (float)(32 * KLT_NPIX));
             }
         }
