@@ -76,6 +76,12 @@ def _worker(rank, world, port, n_pairs, q):
         g = _shard.PoseGatherer(n_pairs, world, rank)
         for _ in range(2):                       # buffers are reused across steps
             out = g.gather(rec)
+        # the queued form bench.py uses (on CPU tensors it degrades to the blocking gather): same result
+        g.gather_async(rec)
+        out2 = g.result()
+        assert (out2 is None) == (rank != 0)
+        if rank == 0:
+            assert np.array_equal(out, out2)
         if rank == 0:
             q.put(out)
         dist.barrier()
