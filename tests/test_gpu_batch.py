@@ -303,3 +303,16 @@ def test_other_scan_geometries_bit_exact(A, bins, n_frames):
         b.close()
     finally:
         fe.close()
+
+
+def test_plain_load_pyramid_fallback_bit_exact():
+    """RADARFE_NO_TMA=1 selects k_pyr_down_w (aligned-word loads) for the upper levels instead of the TMA-staged
+    kernel; the switch is read once per process, so the same bit-exact level tests run in a child process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, RADARFE_NO_TMA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_batch.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "fused_image_path_all_levels_bit_exact or other_scan_geometries_bit_exact"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
