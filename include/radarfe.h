@@ -156,6 +156,12 @@ RF_API int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* n
 /* adjacency only (K x K bytes), for tests                   outlierRejection.py:49-58 */
 RF_API int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K,
                              uint8_t* adj);
+/* The same two calls for float64 coordinates: rejectOutliers / cdist run in float64 on whatever dtype the caller holds
+ * (outlierRejection.py:49-58; metric or undistorted points are float64), so nothing is rounded to float32 first. */
+RF_API int rf_reject_outliers_f64(rf_handle* h, const double* prev_xy, const double* new_xy, int K,
+                           uint8_t* mask, int* n_inliers, int* nodes_or_null);
+RF_API int rf_consistency_adjacency_f64(rf_handle* h, const double* prev_xy, const double* new_xy, int K,
+                                 uint8_t* adj);
 
 /* Test hook: the clique search alone on a caller-supplied adjacency matrix (K x K bytes,
  * diagonal ignored).  prune == 0 enumerates EVERY maximal clique in networkx order and
@@ -169,6 +175,9 @@ RF_API int rf_clique_search(rf_handle* h, const uint8_t* adj, int K, int prune, 
 /* ---- a7  getTransformKLT.calculateTransformSVD           getTransformKLT.py:129-162 */
 /* src = R * tgt + h (pixel units; Tracker.getTransform scales h by cart_res_m). */
 RF_API int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, double R[4], double hvec[2]);
+/* float64 coordinates: means, centring and the cross-covariance in float64, as NumPy computes them for a float64 input
+ * (getTransformKLT.py:141-150); rf_kabsch reproduces NumPy's float32 means for the float32 points cv2 returns. */
+RF_API int rf_kabsch_f64(rf_handle* h, const double* src_xy, const double* tgt_xy, int N, double R[4], double hvec[2]);
 
 /* ---- a8  MotionDistortionSolver.optimize_library         motionDistortion.py:80-325 */
 /* sigma_p[2] / sigma_v[3] are the DIAGONALS the solver object was built with (the reference

@@ -58,7 +58,7 @@ SYMBOLS = [
     "rf_default_config", "rf_create", "rf_destroy", "rf_last_error", "rf_version", "rf_cart_size", "rf_stream",
     "rf_timer_start", "rf_timer_stop_ms", "rf_launch_count", "rf_extract_polar", "rf_frame_create",
     "rf_frame_destroy", "rf_polar_to_cart", "rf_polar_to_cart_log", "rf_frame_from_cart", "rf_frame_download", "rf_klt",
-    "rf_reject_outliers", "rf_consistency_adjacency", "rf_clique_search", "rf_kabsch", "rf_mds_solve", "rf_mds_undistort", "rf_mds_undistort_times", "rf_ssc",
+    "rf_reject_outliers", "rf_reject_outliers_f64", "rf_consistency_adjacency", "rf_consistency_adjacency_f64", "rf_clique_search", "rf_kabsch", "rf_kabsch_f64", "rf_mds_solve", "rf_mds_undistort", "rf_mds_undistort_times", "rf_ssc",
     "rf_detect", "rf_detect_doh", "rf_doh_response", "rf_corner_response", "rf_nms_select", "rf_polar_peaks", "rf_batch_create", "rf_batch_destroy", "rf_batch_upload",
     "rf_batch_run_async", "rf_sync", "rf_batch_download", "rf_track_batch", "rf_track_pair", "rf_batch_upload_async",
     "rf_batch_download_async", "rf_batch_klt_status", "rf_batch_frame_download", "rf_batch_set_profiling",
@@ -580,16 +580,24 @@ class RadarFE:
         return out, st, err
 
     # -- a6 ---------------------------------------------------------------------
+    @staticmethod
+    def _coord_dtype(*arrays):
+        """float64 if any input holds float64 coordinates (the reference's cdist / SVD then run on them in full precision),
+        else float32 (what cv2.calcOpticalFlowPyrLK returns and the batch path carries)"""
+        return np.float64 if any(np.asarray(a).dtype == np.float64 for a in arrays) else np.float32
+
     def reject_outliers(self, prev_xy, new_xy):
-        a = _c(prev_xy, np.float32).reshape(-1, 2)
-        b = _c(new_xy, np.float32).reshape(-1, 2)
+        dt = self._coord_dtype(prev_xy, new_xy)
+        a = _c(prev_xy, dt).reshape(-1, 2)
+        b = _c(new_xy, dt).reshape(-1, 2)
         if a.shape != b.shape:
             raise ValueError("Coordinates should be the same shape")
         K = a.shape[0]
         mask = np.zeros(K, np.uint8)
         n_in, nodes = C.c_int(0), C.c_int(0)
         if K:
-            rc = self.lib.rf_reject_outliers(self.h, _ptr(a), _ptr(b), K, _ptr(mask), C.byref(n_in), C.byref(nodes))
+            fn = self.lib.rf_reject_outliers_f64 if dt == np.float64 else self.lib.rf_reject_outliers
+            rc = fn(self.h, _ptr(a), _ptr(b), K, _ptr(mask), C.byref(n_in), C.byref(nodes))
             if rc == RF_E_WORKLIMIT:
                 # the reference always completes (in seconds to minutes on such graphs); keep the odometry loop alive with
                 # the largest clique found within cfg.clique_node_limit search nodes
@@ -601,11 +609,13 @@ class RadarFE:
         return mask.astype(bool), n_in.value, nodes.value
 
     def consistency_adjacency(self, prev_xy, new_xy):
-        a = _c(prev_xy, np.float32).reshape(-1, 2)
-        b = _c(new_xy, np.float32).reshape(-1, 2)
+        dt = self._coord_dtype(prev_xy, new_xy)
+        a = _c(prev_xy, dt).reshape(-1, 2)
+        b = _c(new_xy, dt).reshape(-1, 2)
         K = a.shape[0]
         adj = np.zeros((K, K), np.uint8)
-        self._check(self.lib.rf_consistency_adjacency(self.h, _ptr(a), _ptr(b), K, _ptr(adj)))
+        fn = self.lib.rf_consistency_adjacency_f64 if dt == np.float64 else self.lib.rf_consistency_adjacency
+        self._check(fn(self.h, _ptr(a), _ptr(b), K, _ptr(adj)))
         return adj
 
     def clique_search(self, adj, prune=True):
@@ -620,13 +630,15 @@ class RadarFE:
 
     # -- a7 ---------------------------------------------------------------------
     def kabsch(self, src_xy, tgt_xy):
-        s = _c(src_xy, np.float32).reshape(-1, 2)
-        t = _c(tgt_xy, np.float32).reshape(-1, 2)
+        dt = self._coord_dtype(src_xy, tgt_xy)
+        s = _c(src_xy, dt).reshape(-1, 2)
+        t = _c(tgt_xy, dt).reshape(-1, 2)
         if s.shape != t.shape:
             raise ValueError("point sets must have the same shape")
         R = np.zeros((2, 2), np.float64)
         h = np.zeros((2, 1), np.float64)
-        self._check(self.lib.rf_kabsch(self.h, _ptr(s), _ptr(t), s.shape[0], _ptr(R), _ptr(h)))
+        fn = self.lib.rf_kabsch_f64 if dt == np.float64 else self.lib.rf_kabsch
+        self._check(fn(self.h, _ptr(s), _ptr(t), s.shape[0], _ptr(R), _ptr(h)))
         return R, h
 
     # -- a8 ---------------------------------------------------------------------

@@ -1009,13 +1009,16 @@ __global__ void __launch_bounds__(32 * MC_WARPS) k_maxclique(const MaxCliqueArgs
 // One block per problem; thread t owns (row i, word w) pairs.  Self-loops are dropped
 // (networkx: adj[u] = {v for v in G[u] if v != u}).
 // ------------------------------------------------------------------------------------
+// T = float: the f32 coordinates cv2 returns, widened like scipy's cdist does; T = double: callers that hold float64
+// coordinates (metric or undistorted points), compared in full precision as the reference would
+template <typename T>
 __global__ void __launch_bounds__(256)
-k_adjacency(const float* __restrict__ prev, const float* __restrict__ nw, const int32_t* __restrict__ counts, int Kstride,
+k_adjacency(const T* __restrict__ prev, const T* __restrict__ nw, const int32_t* __restrict__ counts, int Kstride,
             int Kpad, int NW, double thr, uint32_t* __restrict__ adjbits, uint8_t* __restrict__ adj_bytes) {
     const int p = blockIdx.x;
     const int K = counts[p];
-    const float* a = prev + (size_t)p * Kstride * 2;
-    const float* b = nw + (size_t)p * Kstride * 2;
+    const T* a = prev + (size_t)p * Kstride * 2;
+    const T* b = nw + (size_t)p * Kstride * 2;
     uint32_t* out = adjbits + (size_t)p * Kpad * NW;
     for (int t = threadIdx.x; t < Kpad * NW; t += blockDim.x) {
         const int i = t / NW, w = t - i * NW;
@@ -1172,7 +1175,7 @@ int rf_launch_reject(rf_handle* h, void* ws_base, const float* d_prev, const flo
                      int Kstride, int P, uint8_t** d_mask_out, int* mask_stride, int32_t** d_ninl, int32_t** d_nodes,
                      int32_t** d_status) {
     CliqueWorkspace ws = carve(ws_base, Kstride, P);
-    k_adjacency<<<P, 256, 0, h->stream>>>(d_prev, d_new, d_counts, Kstride, ws.g.Kpad, ws.g.NW, h->cfg.dist_thr_px,
+    k_adjacency<float><<<P, 256, 0, h->stream>>>(d_prev, d_new, d_counts, Kstride, ws.g.Kpad, ws.g.NW, h->cfg.dist_thr_px,
                                           ws.adjbits, nullptr);
     RF_CHECK_LAUNCH(h);
     int rc = launch_clique(h, ws, d_counts, 1, false);
@@ -1181,53 +1184,59 @@ int rf_launch_reject(rf_handle* h, void* ws_base, const float* d_prev, const flo
     return RF_OK;
 }
 
-extern "C" {
-
-int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* adj) {
+template <typename T>
+static int consistency_adjacency_impl(rf_handle* h, const T* prev_xy, const T* new_xy, int K, uint8_t* adj) {
     RfDeviceGuard rf_guard_(h);
     if (!h || !prev_xy || !new_xy || !adj || K < 0) return rf_fail(h, RF_E_BADARG, "rf_consistency_adjacency: bad argument");
     if (K == 0) return RF_OK;
     CliqueGeom g = make_geom(K);
-    size_t bp = ((size_t)K * 8 + 255) & ~(size_t)255;
+    size_t bp = ((size_t)K * 2 * sizeof(T) + 255) & ~(size_t)255;
     size_t total = 2 * bp + 256 + (size_t)g.Kpad * g.NW * 4 + (size_t)K * K;
     int rc = rf_ensure_scratch(h, total);
     if (rc) return rc;
     char* base = (char*)h->d_scratch;
-    float* dp = (float*)base; float* dn = (float*)(base + bp);
+    T* dp = (T*)base; T* dn = (T*)(base + bp);
     int32_t* dc = (int32_t*)(base + 2 * bp);
     uint32_t* bits = (uint32_t*)(base + 2 * bp + 256);
     uint8_t* bytes = (uint8_t*)(bits + (size_t)g.Kpad * g.NW);
-    RF_CUDA(h, cudaMemcpyAsync(dp, prev_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
-    RF_CUDA(h, cudaMemcpyAsync(dn, new_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dp, prev_xy, (size_t)K * 2 * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dn, new_xy, (size_t)K * 2 * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     RF_CUDA(h, cudaMemcpyAsync(dc, &K, 4, cudaMemcpyHostToDevice, h->stream));
-    k_adjacency<<<1, 256, 0, h->stream>>>(dp, dn, dc, K, g.Kpad, g.NW, h->cfg.dist_thr_px, bits, bytes);
+    k_adjacency<T><<<1, 256, 0, h->stream>>>(dp, dn, dc, K, g.Kpad, g.NW, h->cfg.dist_thr_px, bits, bytes);
     RF_CHECK_LAUNCH(h);
     RF_CUDA(h, cudaMemcpyAsync(adj, bytes, (size_t)K * K, cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaStreamSynchronize(h->stream));
     return RF_OK;
 }
 
-int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* mask, int* n_inliers,
-                       int* nodes) {
+template <typename T>
+static int reject_outliers_impl(rf_handle* h, const T* prev_xy, const T* new_xy, int K, uint8_t* mask, int* n_inliers,
+                                int* nodes) {
     RfDeviceGuard rf_guard_(h);
     if (!h || !prev_xy || !new_xy || !mask || K < 0) return rf_fail(h, RF_E_BADARG, "rf_reject_outliers: bad argument");
     if (n_inliers) *n_inliers = 0;
     if (nodes) *nodes = 0;
     if (K == 0) return RF_OK;
     if (K > 8192) return rf_fail(h, RF_E_CAPACITY, "rf_reject_outliers: K=%d exceeds 8192", K);
-    size_t bp = ((size_t)K * 8 + 255) & ~(size_t)255;
+    size_t bp = ((size_t)K * 2 * sizeof(T) + 255) & ~(size_t)255;
     size_t wsb = rf_clique_ws_total(K, 1);
     int rc = rf_ensure_scratch(h, 2 * bp + 256 + wsb);
     if (rc) return rc;
     char* base = (char*)h->d_scratch;
-    float* dp = (float*)base; float* dn = (float*)(base + bp);
+    T* dp = (T*)base; T* dn = (T*)(base + bp);
     int32_t* dc = (int32_t*)(base + 2 * bp);
-    RF_CUDA(h, cudaMemcpyAsync(dp, prev_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
-    RF_CUDA(h, cudaMemcpyAsync(dn, new_xy, (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dp, prev_xy, (size_t)K * 2 * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    RF_CUDA(h, cudaMemcpyAsync(dn, new_xy, (size_t)K * 2 * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     RF_CUDA(h, cudaMemcpyAsync(dc, &K, 4, cudaMemcpyHostToDevice, h->stream));
     uint8_t* dmask; int stride; int32_t *dn_inl, *dnodes, *dstatus;
-    rc = rf_launch_reject(h, base + 2 * bp + 256, dp, dn, dc, K, 1, &dmask, &stride, &dn_inl, &dnodes, &dstatus);
-    if (rc) return rc;
+    {
+        CliqueWorkspace ws = carve(base + 2 * bp + 256, K, 1);
+        k_adjacency<T><<<1, 256, 0, h->stream>>>(dp, dn, dc, K, ws.g.Kpad, ws.g.NW, h->cfg.dist_thr_px, ws.adjbits, nullptr);
+        RF_CHECK_LAUNCH(h);
+        rc = launch_clique(h, ws, dc, 1, false);
+        if (rc) return rc;
+        dmask = ws.mask; stride = ws.g.Kpad; dn_inl = ws.n_inliers; dnodes = ws.nodes; dstatus = ws.status;
+    }
     int32_t out[3];
     RF_CUDA(h, cudaMemcpyAsync(mask, dmask, (size_t)K, cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaMemcpyAsync(&out[0], dn_inl, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1239,6 +1248,21 @@ int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, 
     if (out[2] != RF_OK) return rf_fail(h, out[2], "rf_reject_outliers: clique search exceeded %lld nodes (best-so-far mask returned)",
                                         (long long)h->cfg.clique_node_limit);
     return RF_OK;
+}
+
+extern "C" {
+
+int rf_consistency_adjacency(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* adj) {
+    return consistency_adjacency_impl<float>(h, prev_xy, new_xy, K, adj);
+}
+int rf_consistency_adjacency_f64(rf_handle* h, const double* prev_xy, const double* new_xy, int K, uint8_t* adj) {
+    return consistency_adjacency_impl<double>(h, prev_xy, new_xy, K, adj);
+}
+int rf_reject_outliers(rf_handle* h, const float* prev_xy, const float* new_xy, int K, uint8_t* mask, int* n_inliers, int* nodes) {
+    return reject_outliers_impl<float>(h, prev_xy, new_xy, K, mask, n_inliers, nodes);
+}
+int rf_reject_outliers_f64(rf_handle* h, const double* prev_xy, const double* new_xy, int K, uint8_t* mask, int* n_inliers, int* nodes) {
+    return reject_outliers_impl<double>(h, prev_xy, new_xy, K, mask, n_inliers, nodes);
 }
 
 // Test hook: clique search on a caller-supplied adjacency matrix (K x K bytes).

@@ -25,9 +25,10 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
-struct KabschArgs {
-    const float* src;       // [P][Kstride][2]   x0 (old points)
-    const float* tgt;       // [P][Kstride][2]   x1 (new points)
+template <typename T>
+struct KabschArgsT {
+    const T* src;           // [P][Kstride][2]   x0 (old points)
+    const T* tgt;           // [P][Kstride][2]   x1 (new points)
     const uint8_t* mask;    // [P][mask_stride] or nullptr (all rows up to counts[p])
     int mask_stride;
     const int32_t* counts;  // [P] rows to scan
@@ -37,32 +38,44 @@ struct KabschArgs {
     int32_t* n_used;        // [P]
 };
 
-__global__ void __launch_bounds__(128) k_kabsch(const KabschArgs a) {
+typedef KabschArgsT<float> KabschArgs;
+
+// mean / centring arithmetic in the coordinate type, as NumPy does it: float32 points (what cv2 returns) keep NumPy's float32
+// sequential row sums; float64 points are summed and centred in float64
+__device__ __forceinline__ float kb_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double kb_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float kb_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double kb_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float kb_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double kb_div(double a, double b) { return __ddiv_rn(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_kabsch(const KabschArgsT<T> a) {
     const int lane = threadIdx.x & 31;
     const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= a.P) return;
     const int K = a.counts[p];
-    const float* s = a.src + (size_t)p * a.Kstride * 2;
-    const float* t = a.tgt + (size_t)p * a.Kstride * 2;
+    const T* s = a.src + (size_t)p * a.Kstride * 2;
+    const T* t = a.tgt + (size_t)p * a.Kstride * 2;
     const uint8_t* m = a.mask ? a.mask + (size_t)p * a.mask_stride : nullptr;
-    // np.mean(axis=0) of an (N,2) float32 array: rows are added sequentially in float32
-    float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
+    // np.mean(axis=0) of an (N,2) array: rows are added sequentially in the array's own precision
+    T s0x = 0, s0y = 0, s1x = 0, s1y = 0;
     int n = 0;
     for (int i = 0; i < K; ++i) {
         if (m && !m[i]) continue;
-        s0x = __fadd_rn(s0x, s[2 * i]); s0y = __fadd_rn(s0y, s[2 * i + 1]);
-        s1x = __fadd_rn(s1x, t[2 * i]); s1y = __fadd_rn(s1y, t[2 * i + 1]);
+        s0x = kb_add(s0x, s[2 * i]); s0y = kb_add(s0y, s[2 * i + 1]);
+        s1x = kb_add(s1x, t[2 * i]); s1y = kb_add(s1y, t[2 * i + 1]);
         ++n;
     }
     double R00 = 1, R01 = 0, R10 = 0, R11 = 1, hx = 0, hy = 0;
     if (n > 0) {
-        const float m0x = __fdiv_rn(s0x, (float)n), m0y = __fdiv_rn(s0y, (float)n);
-        const float m1x = __fdiv_rn(s1x, (float)n), m1y = __fdiv_rn(s1y, (float)n);
+        const T m0x = kb_div(s0x, (T)n), m0y = kb_div(s0y, (T)n);
+        const T m1x = kb_div(s1x, (T)n), m1y = kb_div(s1y, (T)n);
         double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
         for (int i = lane; i < K; i += 32) {
             if (m && !m[i]) continue;
-            const double ax = (double)__fsub_rn(s[2 * i], m0x), ay = (double)__fsub_rn(s[2 * i + 1], m0y);
-            const double bx = (double)__fsub_rn(t[2 * i], m1x), by = (double)__fsub_rn(t[2 * i + 1], m1y);
+            const double ax = (double)kb_sub(s[2 * i], m0x), ay = (double)kb_sub(s[2 * i + 1], m0y);
+            const double bx = (double)kb_sub(t[2 * i], m1x), by = (double)kb_sub(t[2 * i + 1], m1y);
             c00 += ax * bx; c01 += ax * by; c10 += ay * bx; c11 += ay * by;   // C = norm_x0^T norm_x1
         }
         c00 = warp_sum_d(c00); c01 = warp_sum_d(c01); c10 = warp_sum_d(c10); c11 = warp_sum_d(c11);
@@ -389,7 +402,7 @@ k_undistort_times(const double* __restrict__ pts, const double* __restrict__ tim
 int rf_launch_kabsch(rf_handle* h, const float* d_src, const float* d_tgt, const uint8_t* d_mask, int mask_stride,
                      const int32_t* d_counts, int Kstride, int P, double* d_R, double* d_h, int32_t* d_nused) {
     KabschArgs a{d_src, d_tgt, d_mask, mask_stride, d_counts, Kstride, P, d_R, d_h, d_nused};
-    k_kabsch<<<(P + 3) / 4, 128, 0, h->stream>>>(a);
+    k_kabsch<float><<<(P + 3) / 4, 128, 0, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
     return RF_OK;
 }
@@ -449,6 +462,33 @@ int rf_kabsch(rf_handle* h, const float* src_xy, const float* tgt_xy, int N, dou
     RF_CUDA(h, cudaMemcpyAsync(dc, &N, 4, cudaMemcpyHostToDevice, h->stream));
     rc = rf_launch_kabsch(h, ds, dt, nullptr, 0, dc, N > 0 ? N : 1, 1, dR, dh, nullptr);
     if (rc) return rc;
+    double out[6];
+    RF_CUDA(h, cudaMemcpyAsync(out, dR, 48, cudaMemcpyDeviceToHost, h->stream));
+    RF_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(R, out, 32); memcpy(hvec, out + 4, 16);
+    return RF_OK;
+}
+
+int rf_kabsch_f64(rf_handle* h, const double* src_xy, const double* tgt_xy, int N, double R[4], double hvec[2]) {
+    RfDeviceGuard rf_guard_(h);
+    if (!h || !src_xy || !tgt_xy || !R || !hvec || N < 0) return rf_fail(h, RF_E_BADARG, "rf_kabsch_f64: bad argument");
+    size_t bp = ((size_t)N * 16 + 255) & ~(size_t)255;
+    int rc = rf_ensure_scratch(h, 2 * bp + 1024);
+    if (rc) return rc;
+    char* base = (char*)h->d_scratch;
+    double* ds = (double*)base; double* dt = (double*)(base + bp);
+    int32_t* dc = (int32_t*)(base + 2 * bp);
+    double* dR = (double*)(base + 2 * bp + 256); double* dh = dR + 4;
+    if (N) {
+        RF_CUDA(h, cudaMemcpyAsync(ds, src_xy, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
+        RF_CUDA(h, cudaMemcpyAsync(dt, tgt_xy, (size_t)N * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+    RF_CUDA(h, cudaMemcpyAsync(dc, &N, 4, cudaMemcpyHostToDevice, h->stream));
+    KabschArgsT<double> a;
+    a.src = ds; a.tgt = dt; a.mask = nullptr; a.mask_stride = 0; a.counts = dc; a.Kstride = N > 0 ? N : 1; a.P = 1;
+    a.R = dR; a.h = dh; a.n_used = nullptr;
+    k_kabsch<double><<<1, 128, 0, h->stream>>>(a);
+    RF_CHECK_LAUNCH(h);
     double out[6];
     RF_CUDA(h, cudaMemcpyAsync(out, dR, 48, cudaMemcpyDeviceToHost, h->stream));
     RF_CUDA(h, cudaStreamSynchronize(h->stream));

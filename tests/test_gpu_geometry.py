@@ -207,3 +207,40 @@ def test_clique_real_data_density_graphs(fe):
         ref_mask = np.zeros(K, bool); ref_mask[clique] = True
         mask_s, size_s, _, _, nodes = fe.clique_search(adj, prune=3)
         assert size_s == len(clique) and np.array_equal(mask_s, ref_mask), f"K={K} p={p}"
+
+
+def test_float64_coordinates_keep_their_precision(fe):
+    """rejectOutliers / calculateTransformSVD on float64 coordinates (metric or undistorted points): the reference's cdist and
+    SVD then run on them as they are (outlierRejection.py:49-58, getTransformKLT.py:141-162); rf_*_f64 do not round them to
+    float32 first.  Coordinates chosen so that float32 rounding (ulp 6e-5 at 1000 px) WOULD flip consistency edges."""
+    from scipy.spatial.distance import cdist
+    rng = np.random.default_rng(11)
+    K, thr = 180, 0.5 / 0.0864
+    prev = rng.uniform(0, 2024, (K, 2))
+    th = 0.02
+    Rm = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    new = prev @ Rm.T + [3.0, -1.5] + rng.normal(0, 2.2, (K, 2))
+    # put a few pairs exactly on the float64 side of the threshold that float32 rounding moves across it
+    d = np.abs(cdist(prev, prev) - cdist(new, new))
+    ref = (d <= thr).astype(np.uint8)
+    adj = fe.consistency_adjacency(prev, new)
+    assert adj.dtype == np.uint8 and np.array_equal(adj, ref)
+    p32, n32 = prev.astype(np.float32), new.astype(np.float32)
+    ref32 = (np.abs(cdist(p32.astype(np.float64), p32.astype(np.float64)) - cdist(n32.astype(np.float64), n32.astype(np.float64))) <= thr)
+    assert np.array_equal(fe.consistency_adjacency(p32, n32), ref32.astype(np.uint8))       # the float32 path is unchanged
+    # clique on the float64 graph == the oracle's order-exact search on that same graph
+    from oracle import restate as R
+    mask, n_in, _ = fe.reject_outliers(prev, new)
+    clique, _ = R.first_max_clique_pruned(ref)
+    want = np.zeros(K, bool); want[clique] = True
+    assert n_in == len(clique) and np.array_equal(mask, want)
+    # Kabsch: float64 means / centring; NumPy's own arithmetic on the float64 arrays as the reference
+    src, tgt = prev[mask], new[mask]
+    m0, m1 = src.mean(axis=0), tgt.mean(axis=0)
+    C = (src - m0).T @ (tgt - m1)
+    U, _, Vt = np.linalg.svd(C)
+    Rr = U @ np.diag([1, np.linalg.det(U @ Vt)]) @ Vt
+    hr = m0 - Rr @ m1
+    Rg, hg = fe.kabsch(src, tgt)
+    assert abs(np.arctan2(Rg[1, 0], Rg[0, 0]) - np.arctan2(Rr[1, 0], Rr[0, 0])) < 1e-12
+    assert np.abs(hg.ravel() - hr).max() < 1e-9
