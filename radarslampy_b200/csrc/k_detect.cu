@@ -153,17 +153,35 @@ __global__ void k_clear_u32(unsigned* __restrict__ a, unsigned* __restrict__ b, 
 #define NMS_COLS 30
 #define NMS_ROWS 64
 #define NMS_WARPS 4
+// Candidates are collected per warp in shared memory and appended to the problem's key list 32 or more at a time: one
+// atomicAdd per batch instead of one per candidate.  The counters of all problems share a few cache lines, i.e. one L2
+// slice, and with 130 k candidates per frame the per-candidate atomics of a lock-step batch serialised there (2.0 ms per
+// 75 re-detecting frames, five times the kernel's memory time).
+#define NMS_BUF 64
 __global__ void __launch_bounds__(32 * NMS_WARPS)
 k_nms_select(const float* __restrict__ resp_base, size_t resp_stride, int rows, int cols, float thr_abs, double thr_rel,
              const unsigned* __restrict__ maxbits, unsigned long long* __restrict__ keys_base, unsigned cap,
              unsigned* __restrict__ count, const int32_t* __restrict__ flags) {
     const int p = blockIdx.y;      // grid = (strip workers, problems), see k_min_eig
     if (flags && !flags[p]) return;
+    __shared__ unsigned long long s_keys[NMS_WARPS][NMS_BUF];
     const float* __restrict__ resp = resp_base + (size_t)p * resp_stride;
     const float thr = thr_rel != 0.0 ? (float)((double)__uint_as_float(maxbits[p]) * thr_rel) : thr_abs;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* __restrict__ buf = s_keys[warp];
+    unsigned long long* __restrict__ keys = keys_base + (size_t)p * cap;
     const int strips_x = (cols + NMS_COLS - 1) / NMS_COLS, nstrips = strips_x * ((rows + NMS_ROWS - 1) / NMS_ROWS);
     const float NEG = -3.402823466e+38f;
+    int nbuf = 0;                               // warp-uniform fill of buf
+    auto flush = [&]() {                        // append buf[0 .. nbuf) to the problem's list (slots past `cap` are dropped, still counted)
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(count + p, (unsigned)nbuf);
+        base = __shfl_sync(FULLM, base, 0);
+        for (int i = lane; i < nbuf; i += 32)
+            if (base + i < cap) keys[base + i] = buf[i];
+        nbuf = 0;
+        __syncwarp();
+    };
     for (int t = blockIdx.x * NMS_WARPS + warp; t < nstrips; t += gridDim.x * NMS_WARPS) {
         const int sy = t / strips_x, sx = t - sy * strips_x;
         const int x0 = sx * NMS_COLS, y0 = sy * NMS_ROWS;
@@ -178,16 +196,21 @@ k_nms_select(const float* __restrict__ resp_base, size_t resp_stride, int rows, 
             const float h2 = fmaxf(fmaxf(__shfl_up_sync(FULLM, v, 1), v), __shfl_down_sync(FULLM, v, 1));
             // centre row y - 1 (an output row of this strip for r >= 2), interior rows only
             const int yc = y - 1;
-            if (r >= 2 && x_out && yc >= 1 && yc < rows - 1 && vc > thr && vc == fmaxf(fmaxf(h0, h1), h2)) {
-                const unsigned slot = atomicAdd(count + p, 1u);
-                if (slot < cap) {
+            const bool emit = r >= 2 && x_out && yc >= 1 && yc < rows - 1 && vc > thr && vc == fmaxf(fmaxf(h0, h1), h2);
+            const unsigned bm = __ballot_sync(FULLM, emit);
+            if (bm) {
+                if (emit) {
                     const unsigned idx = (unsigned)yc * (unsigned)cols + (unsigned)x;
-                    keys_base[(size_t)p * cap + slot] = ((unsigned long long)(~__float_as_uint(vc)) << 32) | (unsigned long long)(~idx);
+                    buf[nbuf + __popc(bm & ((1u << lane) - 1u))] = ((unsigned long long)(~__float_as_uint(vc)) << 32) | (unsigned long long)(~idx);
                 }
+                nbuf += __popc(bm);
+                __syncwarp();
+                if (nbuf > NMS_BUF - 32) flush();
             }
             h0 = h1; h1 = h2; vc = v;
         }
     }
+    if (nbuf) flush();
 }
 
 __global__ void __launch_bounds__(256)
