@@ -34,7 +34,10 @@ struct DetectWs {
 // flag): enough to fill the machine 16 deep when every problem is live, never fewer than 64 nor more than the tiles
 static inline int rf_tile_workers(const rf_handle* h, int ntiles, int S) {
     int w = (h->sm_count * 16 + S - 1) / (S > 0 ? S : 1);
-    w = w < 64 ? 64 : w;
+    // In a lock-step step only a quarter of the problems is live, and a live problem's strips are walked by its own CTAs
+    // only: with 64 of them each warp walked 8 strips row by row, one exposed load latency per row (k_min_eig / k_nms_select at
+    // 1.2 TB/s).  256 per problem; the CTAs of a switched-off problem exit on their first instruction.
+    w = w < 256 ? 256 : w;
     return w > ntiles ? ntiles : w;
 }
 

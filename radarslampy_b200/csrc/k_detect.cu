@@ -90,6 +90,7 @@ k_min_eig(const float* __restrict__ img_base, size_t img_stride, int n, float k0
         const bool x_ok = lane >= 1 && lane <= ME_COLS && x < n;
         const int rows = min(ME_ROWS, n - y0);
         double hxx0 = 0, hxy0 = 0, hyy0 = 0, hxx1 = 0, hxy1 = 0, hyy1 = 0;   // row sums of gradient rows gy - 2, gy - 1
+#pragma unroll 2
         for (int r = 0; r < rows + 2; ++r) {
             const int gy = min(max(y0 - 1 + r, -1), n);                 // <= n: y0 + rows <= n
             const int qy = reflect101(gy, n);
@@ -190,6 +191,7 @@ k_nms_select(const float* __restrict__ resp_base, size_t resp_stride, int rows, 
         const bool x_out = lane >= 1 && lane <= NMS_COLS && x >= 1 && x < cols - 1;   // interior output column of this strip
         const int nr = min(NMS_ROWS, rows - y0);
         float h0 = NEG, h1 = NEG, vc = NEG;     // horizontal maxima of rows y - 2, y - 1; the centre value of row y - 1
+#pragma unroll 4
         for (int r = 0; r < nr + 2; ++r) {
             const int y = y0 - 1 + r;
             const float v = (x_in && y >= 0 && y < rows) ? __ldg(resp + (size_t)y * cols + x) : NEG;
