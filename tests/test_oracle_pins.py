@@ -219,3 +219,20 @@ def test_corner_response_and_selection_match_live_cv2(tiny):
     sel = R.nms_select(ref, float(ref.max()) * 0.01)
     assert len(sel) == len(pts) > 1000
     assert np.array_equal(sel[:, 1], pts[:, 0]) and np.array_equal(sel[:, 0], pts[:, 1])
+
+
+# ---- the toolchain the goldens were recorded with ------------------------------------------
+def test_golden_toolchain_versions():
+    """Clique order is CPython-set-layout and networkx specific (oracle/c/oracle_c.c restates CPython 3.12's
+    setobject.c and networkx 3.x's find_cliques): the goldens and the live-library pins of this file are only
+    comparable under the interpreter / wheels that recorded them (tests/golden/VERSIONS.json)."""
+    import json
+    import os
+    from oracle import toolchain_versions as T
+    assert os.path.exists(T.PATH), "tests/golden/VERSIONS.json missing: run python -m oracle.toolchain_versions"
+    rec, cur = json.load(open(T.PATH)), T.current()
+    mm = lambda v: tuple(v.split(".")[:2])
+    assert mm(rec["cpython"]) == mm(cur["cpython"]), f"goldens recorded under CPython {rec['cpython']}, running {cur['cpython']}: set iteration order may differ"
+    assert mm(rec["networkx"])[0] == mm(cur["networkx"])[0], f"goldens recorded with networkx {rec['networkx']}, running {cur['networkx']}"
+    for k in ("scipy", "opencv", "numpy"):
+        assert mm(rec[k])[0] == mm(cur[k])[0], f"goldens recorded with {k} {rec[k]}, running {cur[k]}"
