@@ -6,10 +6,12 @@
 
 Headline workload (BASELINE.json configs[1] data; configs[2] with --mds 1): a seeded synthetic Oxford-shaped
 sequence (400 azimuths x 3768 range bins uint8 + 11 metadata bytes, 0.0438 m/bin) of
---frames scans per GPU.  One step = one pass of the hot path over that batch: scan decode +
+--frames scans per GPU.  One pass = the hot path over that device batch: scan decode +
 polar->Cartesian + u8 pyramid for every frame, then pyramidal LK, distance-consistency clique
 rejection, Kabsch (and the motion-distortion solve) for every consecutive pair -> one pose per
-pair; FEATURES ARE HANDED IN and the pairs are INDEPENDENT (operationally configs[3]'s pair batches).
+pair; one STEP = --passes-per-step (4) such passes, pipelined (1024 scans, 1020 poses per GPU), so that the
+K steps the driver asks for are long against the ~6 ms drain of the last passes' clique tail, which is inside the
+timed region; FEATURES ARE HANDED IN and the pairs are INDEPENDENT (operationally configs[3]'s pair batches).
 `value` = poses/s with the scans resident in HBM; `e2e` = the same through the C ABI with
 host buffers (pinned H2D of every scan + D2H of the poses inside the timed region).
 Multi-GPU: every rank owns an independent sequence (weak scaling, no data-path collective);
@@ -51,7 +53,12 @@ L2_BYTES = 126e6
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200, help="timed steps (the pipeline drains inside the timed region: ~6 ms of clique tail after the last step)")
+    ap.add_argument("--steps", type=int, default=50, help="timed steps (the pipeline drains inside the timed region: ~6 ms of clique tail after the last step)")
+    ap.add_argument("--passes-per-step", type=int, default=4,
+                    help="device batches (passes of --frames scans through the pipeline) that make up one step: a step is "
+                         "passes x frames scans per GPU.  One 256-scan pass lasts ~2 ms, so 20 one-pass steps would be a 41 ms "
+                         "timed region of which the ~6 ms drain of the last passes' clique tail is 13 %; four passes per step "
+                         "make the same 20 steps 164 ms")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=256, help="scans per GPU per step")
@@ -293,12 +300,15 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, rb, kmax):
-    return {"workload": f"BASELINE configs[1] data as independent pair batches: synthetic Oxford-shaped sequence, {args.frames} scans/GPU/step "
+    M = max(1, args.passes_per_step)
+    return {"workload": f"BASELINE configs[1] data as independent pair batches: synthetic Oxford-shaped sequence, {M * args.frames} scans/GPU/step "
+                        f"as {M} pipelined device batches of {args.frames} "
                         f"(400x3768 u8 + 11 metadata bytes, {args.res} m/bin -> {rb} used bins, {2 * (rb // 2)}^2 Cartesian), "
                         f"{args.features} features/pair HANDED IN (ground-truth scatterers), consecutive pairs treated as INDEPENDENT, "
                         f"KLT 15x15 x 4 levels, clique rejection, Kabsch" + (", scans rendered with intra-scan motion distortion, motion-distortion LM" if args.mds else "")
                         + "; the chained odometry with on-device detection is the `chained` leg",
-            "frames_per_step_per_gpu": args.frames, "pairs_per_step_per_gpu": args.frames - 1, "features_per_pair": args.features,
+            "frames_per_step_per_gpu": M * args.frames, "pairs_per_step_per_gpu": M * (args.frames - 1), "passes_per_step": M,
+            "frames_per_pass": args.frames, "features_per_pair": args.features,
             "range_res_m": args.res, "mds": bool(args.mds), "write_cart_f32": bool(args.write_f32),
             "l2": "inputs larger than L2: each step streams >= 1.3 GB of scans + pyramids per GPU (L2 = 126 MB)"}
 
@@ -456,6 +466,8 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     from radarslampy_b200 import _ffi, _shard
 
     S, P = args.frames, args.frames - 1
+    M = max(1, args.passes_per_step)          # passes (device batches of S scans) per step
+    n_pass = args.steps * M                    # passes inside the timed region
     cfg = _ffi.default_config()
     cfg.range_bins = rb
     cfg.cart_res_m = 2 * args.res
@@ -517,7 +529,7 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
         upload(b)
         b.set_profiling(True)
     fe.sync()
-    for i in range(max(args.warmup, NB)):
+    for i in range(max(args.warmup * M, NB)):
         batches[i % NB].run_async(with_mds=with_mds)
     fe.sync()
     for b in batches:
@@ -528,7 +540,7 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     sampler.start()
     n0 = fe.launch_count()
     fe.timer_start()
-    for i in range(args.steps):
+    for i in range(n_pass):
         batches[i % NB].run_async(with_mds=with_mds)
     ms = fe.timer_stop_ms()          # joins the tail streams: every step's poses are complete
     launches = fe.launch_count() - n0
@@ -577,11 +589,11 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
             gather_poses(outs[i % NB][0][:P])
         gather_poses(None, flush=True)                  # the last partial message: every pose has reached rank 0
 
-    e2e_loop(max(args.warmup, NB))
+    e2e_loop(max(args.warmup * M, NB))
     barrier()
     t0 = time.perf_counter()
     fe.timer_start()
-    e2e_loop(args.steps)
+    e2e_loop(n_pass)
     ms_e2e = fe.timer_stop_ms()
     barrier()
     ms_e2e = max(ms_e2e, 0.0)
@@ -590,7 +602,7 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     clocks = sampler.stop()
     # H2D ceiling of the e2e arm: the same uploads (2-D used-column copies from the same pinned buffers, all ranks at once)
     # with nothing else queued -- what the box's PCIe / host-memory system gives this job
-    n_up = max(8, min(args.steps, 32))
+    n_up = max(8, min(n_pass, 32))
     for i in range(NB):
         upload(batches[i])
     barrier()
@@ -598,7 +610,7 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     for i in range(n_up):
         upload(batches[i % NB])
     fe.sync()
-    ms_h2d = (time.perf_counter() - t0) * 1e3 / n_up
+    ms_h2d = (time.perf_counter() - t0) * 1e3 / n_up          # per pass
     barrier()
 
     # ---- reduce over ranks (max time) ---------------------------------------------------------
@@ -636,20 +648,22 @@ def weak_leg(ctx, raw_np, poses, pair_idx, feats, counts, cpu_line, cpu_out, num
     for _ in range(3):
         lv.append((lv[-1] + 1) // 2)
     survey_bytes = S * (cfg.azimuths * rb + 4 * fe_n * fe_n + sum(v * v for v in lv))      # per launch of the conversion
-    value = world * P * args.steps / (ms * 1e-3)
-    e2e = world * P * args.steps / (ms_e2e * 1e-3)
-    h2d = S * cfg.azimuths * (cfg.meta_bytes + rb) + P * (8 + kmax * 8 + 4 + 24)
+    value = world * P * n_pass / (ms * 1e-3)
+    e2e = world * P * n_pass / (ms_e2e * 1e-3)
+    h2d = S * cfg.azimuths * (cfg.meta_bytes + rb) + P * (8 + kmax * 8 + 4 + 24)      # per pass
     d2h = P * 120
     line = {
         "metric": "radar frames/sec polar->pose", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/f32/f64", "data": "synthetic", "config": workload_config(args, rb, kmax),
         "pipelining": f"{NB} batches alternate on one handle (copy / image+KLT / rejection+solve streams)",
-        "klt_tracks_per_s": world * K_total * args.steps / (ms * 1e-3),
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
-                "ms_per_step": ms_e2e / args.steps, "note": "bytes are the whole job's (all ranks) per step",
+        "passes_per_step": M, "ms_per_pass": ms / n_pass,
+        "klt_tracks_per_s": world * K_total * n_pass / (ms * 1e-3),
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world * M, "d2h_bytes_per_step": int(d2h) * world * M,
+                "ms_per_step": ms_e2e / args.steps, "ms_per_pass": ms_e2e / n_pass,
+                "note": "bytes are the whole job's (all ranks) per step",
                 # the uploads alone (same pinned buffers, same 2-D copies, every rank at once): the H2D ceiling of this job on this box
-                "h2d_only": {"ms_per_step": ms_h2d, "gbs": int(h2d) * world / (ms_h2d * 1e-3) / 1e9,
+                "h2d_only": {"ms_per_step": ms_h2d * M, "gbs": int(h2d) * world / (ms_h2d * 1e-3) / 1e9,
                              "frames_per_s_ceiling": world * P / (ms_h2d * 1e-3),
                              "e2e_fraction_of_ceiling": (e2e / (world * P / (ms_h2d * 1e-3))) if ms_h2d > 0 else None}},
         "gpu_launches": int(launches),
@@ -918,7 +932,7 @@ def leg_mds(ctx, data):
         return {"skipped": "the headline already runs with --mds 1"}
     rb, kmax, raw, poses, pair_idx, feats, counts = data
     args = ctx["args"]
-    m = measure_pair_chunks(ctx, [(raw, pair_idx, feats, counts, poses[:-1])], True, steps=max(5, min(args.steps, 40)), warmup=3,
+    m = measure_pair_chunks(ctx, [(raw, pair_idx, feats, counts, poses[:-1])], True, steps=max(5, min(args.steps * max(1, args.passes_per_step), 80)), warmup=3,
                             max_frames=args.frames, max_pairs=args.frames - 1)
     P = args.frames - 1
     r = m["results"]
