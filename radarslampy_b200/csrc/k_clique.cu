@@ -1162,7 +1162,12 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
         for (int p = 0; p < ws.P; ++p) { long long t = 0; for (int k = 0; k < 8; ++k) { tot[k] += hp[p * 8 + k]; t += hp[p * 8 + k]; } if (t > mx) { mx = t; arg = p; } }
         fprintf(stderr, "[clique profile] P=%d  mean cycles:", ws.P);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], tot[k] / ws.P);
-        fprintf(stderr, "\n[clique profile] slowest pair %d (%lld cycles):", arg, mx);
+        int kk = 0, nn = 0, ni = 0, ms = 0;
+        cudaMemcpy(&kk, d_counts + arg, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&nn, ws.nodes + arg, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&ni, ws.n_inliers + arg, 4, cudaMemcpyDeviceToHost);
+        if (a.max_size) cudaMemcpy(&ms, ws.max_size + arg, 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "\n[clique profile] slowest pair %d (%lld cycles; K=%d pops=%d clique=%d maxsize=%d):", arg, mx, kk, nn, ni, ms);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], hp[arg * 8 + k]);
         fprintf(stderr, "\n");
     }

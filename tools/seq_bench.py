@@ -40,15 +40,22 @@ def main():
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--detector", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--retrack", type=int, default=None, help="ablation: rf_config.retrack_threshold (-1 = never re-detect)")
+    ap.add_argument("--node-limit", type=int, default=None, help="ablation: rf_config.clique_node_limit")
     a = ap.parse_args()
     from radarslampy_b200 import _ffi
     S, NG, T = a.seq, a.runners, a.warmup + a.steps
     per = S // NG
+    S = per * NG          # the sequences that actually run
     raw = cached_sequence(S + T + 1, a.res, bool(a.mds))
     rb = int(87.5 / a.res)
     cfg = _ffi.default_config()
     cfg.range_bins, cfg.cart_res_m, cfg.dist_thr_px = rb, 2 * a.res, 0.5 / (2 * a.res)
     cfg.max_features, cfg.max_pairs, cfg.max_frames = 320, 2, 2
+    if a.retrack is not None:
+        cfg.retrack_threshold = a.retrack
+    if a.node_limit is not None:
+        cfg.clique_node_limit = a.node_limit
     fe = _ffi.RadarFE(cfg, device=0)
     runners = [fe.new_sequences(per, per + T + 1, detector_mode=a.detector) for _ in range(NG)]
     for g, r in enumerate(runners):
