@@ -312,7 +312,7 @@ struct CliqueArgs {
     int32_t* status;           // [P]
     long long* n_yields;       // [P] (may be null)
     unsigned long long* order_hash;  // [P] (may be null) FNV-1a over (size, members...) of every yield
-    long long* prof;           // [P][8] cycle counters per phase (null unless RF_CLIQUE_PROFILE is set)
+    long long* prof;           // [P][16] cycle counters per phase + event counts (null unless RF_CLIQUE_PROFILE is set)
 };
 
 __device__ __forceinline__ unsigned long long fnv_mix(unsigned long long hsh, int v) {
@@ -497,6 +497,12 @@ __device__ __forceinline__ int colour_bound(uint32_t Q, const uint32_t* __restri
 #define PROF_MARK(slot) do { if (a.prof) { const long long _t = clock64(); pc[slot] += _t - tprev; tprev = _t; } } while (0)
 __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef RF_CLIQUE_EVENTS
+    long long ev[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // diagnostic event counts: node entries, chains, chain vertices, clique shortcuts, pivots, descents, bound prunes, leaf yields
+#define EVT(i, n) (ev[i] += (n))
+#else
+#define EVT(i, n) ((void)0)
+#endif
     long long tprev = clock64();
     extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x;
@@ -618,6 +624,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
 
     auto enter_node = [&]() {
         for (;;) {
+            EVT(0, 1);
             // u = max(subg, key=lambda u: len(cand & adj[u])) — first maximum in subg's iteration order.
             // Iteration order = slot order; a lane scores the key of "its" slots, ties go to the lowest slot.
             const int size = subg.mask() + 1;
@@ -658,6 +665,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                 // if no excluded vertex (subg \ cand) is adjacent to all of cand — and leaves the parent's
                 // sets untouched, so its |cand| levels need not be walked.
                 if (n_univ == ncand) {
+                    EVT(3, 1);
                     if (max_out < ncand) {
                         ++ny;
                         const int csize = qn - 1 + ncand;
@@ -680,7 +688,128 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                 // set of universal candidates: |D| levels without any branching or yield.  While the sets
                 // stay in identity layout (table >= node count) their state after the chain is independent
                 // of the order in which D was consumed, so the chain is taken in one step.
-                if (ident && n_univ > 0 && max_out < ncand - 1) {
+                if (n_univ > 0 && max_out < ncand - 1 && NWe <= 32) {
+                    if (a.prune && qn - 1 + ncand <= best) {     // the single child cannot beat the best
+                        if (lane == 0) ext.used() = 0;
+                        __syncwarp();
+                        return;
+                    }
+                    // D by key, word `lane` in a register (the table builds below use `own` as scratch)
+                    uint32_t dreg = 0u;
+                    if (ident) dreg = lane < NWe ? D[lane] : 0u;
+                    else {
+                        for (int i0 = 0; i0 < K; i0 += 32) {
+                            const int v = i0 + lane;
+                            bool uv = false;
+                            if (v < K && ((cand.bits()[v >> 5] >> (v & 31)) & 1u)) {
+                                const uint32_t* row = adjbits + (size_t)v * RS;
+                                int c = 0;
+                                for (int w = 0; w < NWe; ++w) c += __popc(cand.bits()[w] & row[w]);
+                                uv = c == ncand - 1;
+                            }
+                            const unsigned bm = __ballot_sync(FULL, uv);
+                            if (lane == (i0 >> 5)) dreg = bm;
+                        }
+                    }
+                    int left = n_univ, ncur = ncand;
+                    // (3a) identity layout: the first m members of D (networkx consumes D in ascending order there) in ONE
+                    // step, m the largest count that leaves both sets in identity layout (|cand| - m elements still grow
+                    // a table of at least K slots)
+                    if (ident) {
+                        const int nmin = K <= 8 ? 0 : K <= 32 ? 5 : K <= 128 ? 19 : K <= 512 ? 77 : K <= 2048 ? 307 : 1229;
+                        const int m = min(left, ncur - nmin);
+                        if (m >= 1) {
+                            uint32_t dsel = dreg;
+                            if (m < left) {                      // keep the m lowest members
+                                const int c = __popc(dsel), incl = warp_incl_scan(c, lane), excl = incl - c;
+                                if (excl >= m) dsel = 0u;
+                                else while (excl + __popc(dsel) > m) dsel &= ~(0x80000000u >> __clz(dsel));
+                            }
+                            __syncwarp();
+                            if (lane < NWe) D[lane] = dsel;
+                            __syncwarp();
+                            const int nc2 = ncur - m;
+                            // subg'' = members of subg adjacent to all of the m
+                            uint32_t* S2 = own + NW;
+                            int ns2 = 0;
+                            for (int i0 = 0; i0 < K; i0 += 32) {
+                                const int v = i0 + lane;
+                                bool keep = false;
+                                if (v < K && ((subg.bits()[v >> 5] >> (v & 31)) & 1u)) {
+                                    const uint32_t* row = adjbits + (size_t)v * RS;
+                                    int c = 0;
+                                    for (int w = 0; w < NWe; ++w) c += __popc(D[w] & row[w]);
+                                    keep = c == m;
+                                }
+                                const unsigned bm = __ballot_sync(FULL, keep);
+                                ns2 += __popc(bm);
+                                if (lane == 0) S2[i0 >> 5] = bm;
+                            }
+                            __syncwarp();
+                            if (growth_size(nc2) >= K && growth_size(ns2) >= K) {
+                                EVT(1, 1); EVT(2, m);
+                                bits_to_seq(D, nullptr, true, NWe, Q + (qn - 1), lane);
+                                qn += m;
+                                pops += m;
+                                for (int w = lane; w < NWe; w += 32) { cand.bits()[w] &= ~D[w]; subg.bits()[w] = S2[w]; }
+                                if (lane == 0) {
+                                    Q[qn - 1] = -1;
+                                    cand.mask() = growth_size(nc2) - 1; cand.fill() = nc2; cand.used() = nc2; cand.finger() = 0;
+                                    subg.mask() = growth_size(ns2) - 1; subg.fill() = ns2; subg.used() = ns2; subg.finger() = 0;
+                                }
+                                __syncwarp();
+                                dreg &= ~dsel; left -= m; ncur -= m;
+                            }
+                        }
+                    }
+                    // (3b) the remaining members of D, one level each, WITHOUT re-scoring: the pivot of every level of the
+                    // chain is the first member of D in subg's iteration order (all of D tie at the maximum score and no
+                    // excluded vertex reaches it), ext = {pivot}, and D - pivot is the child's set of universal candidates.
+                    // Only the two child sets are built (their slot layout is what the next level iterates); scoring,
+                    // ext = cand - adj[u], ext.pop() and the frame push of the general path (two thirds of a level) are
+                    // skipped.  Stops when cand has become a clique: shortcut (2) finishes that on the next pass.
+                    while (left > 0 && left < ncur) {
+                        const int ssz = subg.mask() + 1;
+                        int u = -1;
+                        if (ssz >= K) {
+                            const unsigned bm = __ballot_sync(FULL, dreg != 0u);
+                            const int src = __ffs(bm) - 1;
+                            const uint32_t w = __shfl_sync(FULL, dreg, src);
+                            u = src * 32 + (__ffs(w) - 1);
+                        } else {
+                            const int16_t* t = subg.tab();
+                            for (int i0 = 0; i0 < ssz && u < 0; i0 += 32) {
+                                const int i = i0 + lane;
+                                const int k = i < ssz ? t[i] : -1;
+                                const uint32_t dw = __shfl_sync(FULL, dreg, (k >= 0 ? k : 0) >> 5);
+                                const bool hit = k >= 0 && ((dw >> (k & 31)) & 1u);
+                                const unsigned bm = __ballot_sync(FULL, hit);
+                                if (bm) u = __shfl_sync(FULL, k, __ffs(bm) - 1);
+                            }
+                        }
+                        EVT(1, 1); EVT(2, 1);
+                        ++pops;
+                        __syncwarp();
+                        set_remove(cand, K, u, lane);
+                        if (lane == 0) Q[qn - 1] = (int16_t)u;
+                        const uint32_t* adju = adjbits + (size_t)u * RS;
+                        const int nsub = bits_count2(subg.bits(), adju, false, NWe, lane);
+                        const int nc = bits_count2(cand.bits(), adju, false, NWe, lane);
+                        const int16_t* adjseq_u = adjseq + (size_t)u * g.SEQCAP;
+                        build_and_adj(chs, subg, nsub, K, NWe, adju, deg[u], adjseq_u, seq, tmp, own, lane);
+                        build_and_adj(chc, cand, nc, K, NWe, adju, deg[u], adjseq_u, seq, tmp, own, lane);
+                        if (lane == 0) Q[qn] = -1;
+                        __syncwarp();
+                        ++qn;
+                        set_copy(subg.w, chs, K, lane);
+                        set_copy(cand.w, chc, K, lane);
+                        __syncwarp();
+                        if (lane == (u >> 5)) dreg &= ~(1u << (u & 31));
+                        --left; --ncur;
+                    }
+                    continue;
+                }
+                if (ident && n_univ > 0 && max_out < ncand - 1) {   // NWe > 32: all of D or nothing
                     if (a.prune && qn - 1 + ncand <= best) {     // the single child cannot beat the best
                         if (lane == 0) ext.used() = 0;
                         __syncwarp();
@@ -705,6 +834,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     }
                     __syncwarp();
                     if (growth_size(nc2) >= K && growth_size(ns2) >= K) {
+                        EVT(1, 1); EVT(2, n_univ);
                         bits_to_seq(D, nullptr, true, NWe, Q + (qn - 1), lane);
                         qn += n_univ;
                         pops += n_univ;
@@ -721,6 +851,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
             }
             const int slot = 0xFFFF - (int)(bestkey & 0xFFFF);
             const int u = ident ? slot : subg.tab()[slot];
+            EVT(4, 1);
             PROF_MARK(3);   // pivot scoring / shortcut / chain
             set_sub_adj(ext, cand, K, NWe, adjbits + (size_t)u * RS, deg[u], seq, tmp, own, lane);
             PROF_MARK(4);   // ext = cand - adj[u]
@@ -741,7 +872,7 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
             const int nsub = bits_count2(subg.bits(), adjq, false, NWe, lane);
             PROF_MARK(5);   // pop + remove + count
             if (nsub == 0) {
-                ++ny;
+                ++ny; EVT(7, 1);
                 __syncwarp();
                 if (a.order_hash) { hsh = fnv_mix(hsh, qn); for (int i = 0; i < qn; ++i) hsh = fnv_mix(hsh, Q[i]); }
                 if (qn > best) {   // outlierRejection.py:73 strict '>'
@@ -759,7 +890,9 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                     const uint32_t cw = lane < NWe ? (cand.bits()[lane] & adjq[lane]) : 0u;
                     descend = qn + colour_bound(cw, adjbits, RS, NWe, best - qn + 1, lane) > best;
                 }
+                if (!descend) EVT(6, 1);
                 if (descend) {
+                    EVT(5, 1);
                     const int degq = deg[q];
                     const int16_t* adjseq_q = adjseq + (size_t)q * g.SEQCAP;
                     build_and_adj(chs, subg, nsub, K, NWe, adjq, degq, adjseq_q, seq, tmp, own, lane);
@@ -805,7 +938,14 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
         a.status[p] = status;
         if (a.n_yields) a.n_yields[p] = ny;
         if (a.order_hash) a.order_hash[p] = hsh;
-        if (a.prof) for (int k = 0; k < 8; ++k) a.prof[(size_t)p * 8 + k] = pc[k];
+        if (a.prof) for (int k = 0; k < 8; ++k) {
+            a.prof[(size_t)p * 16 + k] = pc[k];
+#ifdef RF_CLIQUE_EVENTS
+            a.prof[(size_t)p * 16 + 8 + k] = ev[k];
+#else
+            a.prof[(size_t)p * 16 + 8 + k] = 0;
+#endif
+        }
     }
 }
 
@@ -1141,7 +1281,7 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     }
     static const bool want_prof = getenv("RF_CLIQUE_PROFILE") != nullptr;
     long long* d_prof = nullptr;
-    if (want_prof && cudaMalloc(&d_prof, (size_t)ws.P * 64) == cudaSuccess) a.prof = d_prof;
+    if (want_prof && cudaMalloc(&d_prof, (size_t)ws.P * 128) == cudaSuccess) a.prof = d_prof;
     size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + (size_t)(2 * ws.g.NW > 128 ? 2 * ws.g.NW : 128) * 4;
     const size_t adj_bytes = (size_t)ws.g.Kpad * ws.g.RS * 4;
     a.adj_in_smem = smem + adj_bytes <= 96 * 1024;      // K <= 512: rows live next to the search frame
@@ -1153,13 +1293,13 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     k_clique<<<ws.P, 32, smem, h->stream>>>(a);
     RF_CHECK_LAUNCH(h);
     if (d_prof) {   // diagnostic only: synchronous dump of the per-phase cycle counters
-        std::vector<long long> hp((size_t)ws.P * 8);
+        std::vector<long long> hp((size_t)ws.P * 16);
         cudaMemcpyAsync(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaStreamSynchronize(h->stream);
         cudaFree(d_prof);
         static const char* names[8] = {"stage", "deg+adjseq", "greedy", "pivot", "ext", "pop", "children", "frames"};
         long long tot[8] = {0}, mx = 0; int arg = 0;
-        for (int p = 0; p < ws.P; ++p) { long long t = 0; for (int k = 0; k < 8; ++k) { tot[k] += hp[p * 8 + k]; t += hp[p * 8 + k]; } if (t > mx) { mx = t; arg = p; } }
+        for (int p = 0; p < ws.P; ++p) { long long t = 0; for (int k = 0; k < 8; ++k) { tot[k] += hp[p * 16 + k]; t += hp[p * 16 + k]; } if (t > mx) { mx = t; arg = p; } }
         fprintf(stderr, "[clique profile] P=%d  mean cycles:", ws.P);
         for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], tot[k] / ws.P);
         int kk = 0, nn = 0, ni = 0, ms = 0;
@@ -1168,7 +1308,10 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
         cudaMemcpy(&ni, ws.n_inliers + arg, 4, cudaMemcpyDeviceToHost);
         if (a.max_size) cudaMemcpy(&ms, ws.max_size + arg, 4, cudaMemcpyDeviceToHost);
         fprintf(stderr, "\n[clique profile] slowest pair %d (%lld cycles; K=%d pops=%d clique=%d maxsize=%d):", arg, mx, kk, nn, ni, ms);
-        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], hp[arg * 8 + k]);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", names[k], hp[arg * 16 + k]);
+        static const char* enames[8] = {"entries", "chains", "chain_vertices", "clique_shortcuts", "pivots", "descents", "bound_prunes", "leaf_yields"};
+        fprintf(stderr, "\n[clique profile] slowest pair events:");
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s=%lld", enames[k], hp[arg * 16 + 8 + k]);
         fprintf(stderr, "\n");
     }
     return RF_OK;
