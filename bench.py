@@ -75,6 +75,9 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=4096, help="strong leg: total independent pairs (BASELINE configs[3])")
     ap.add_argument("--chain-seq", type=int, default=256, help="chained leg: sequences per GPU in lock step")
     ap.add_argument("--chain-steps", type=int, default=12)
+    ap.add_argument("--chain-seq-large", type=int, default=512,
+                    help="chained leg: a second resident measurement with this many sequences per GPU (0 = off): the 256-sequence "
+                         "step is bound by per-runner launch latencies, twice the sequences show the machine's throughput")
     ap.add_argument("--gather-every", type=int, default=8, help="multi-GPU: steps whose pose records travel in one NCCL gather")
     ap.add_argument("--chain-runners", type=int, default=16, help="chained leg: rf_seq runners (streams) the sequences are split over")
     return ap.parse_args()
@@ -379,7 +382,7 @@ def main():
     numa = bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa) else {"node": None, "cpus": None}
     legs = wanted_legs(args)
     gen_workers = max(1, (os.cpu_count() or 1) // world)
-    chain_need = (args.chain_seq + CHAIN_WARMUP + args.chain_steps + 2) if "chained" in legs else 0
+    chain_need = (max(args.chain_seq, args.chain_seq_large) + CHAIN_WARMUP + args.chain_steps + 2) if "chained" in legs else 0
     # headline drive (configs[1]; rendered with motion distortion under --mds 1), and the motion-distorted drive of the
     # same world / poses that the `chained` and `mds` legs read (configs[2]); one render when they coincide
     rb, kmax, raw_long, poses_long, pair_idx, feats, counts = workload(args, rank, extra_frames=max(0, chain_need - args.frames) if args.mds else 0,
@@ -1050,6 +1053,37 @@ def leg_chained(ctx, raw_long, cpu):
     e2e_last = np.concatenate([res_host[g][T % SLOTS] for g in range(NG)])
     for r in runners:
         r.close()
+    # ---- the same resident measurement with more sequences per GPU (throughput rather than per-step latency) -------------
+    large = None
+    S2 = args.chain_seq_large
+    if S2 > S and len(raw_long) >= S2 + T + 1:
+        NG2 = max(1, S2 // per)
+        while S2 % NG2:
+            NG2 -= 1
+        per2, K2 = S2 // NG2, max(4, K // 2)
+        T2 = W + K2
+        runners = [fe.new_sequences(per2, per2 + T2 + 1) for _ in range(NG2)]
+        for g, r in enumerate(runners):
+            r.upload(0, raw_long[g * per2:g * per2 + per2 + T2 + 1])
+            r.reset(0, 1)
+        fe.sync()
+        for t in range(1, W + 1):
+            for r in runners:
+                r.step(t, 1, with_mds=with_mds, graph=True)
+        _barrier(ctx, fe)
+        fe.timer_start()
+        for t in range(W + 1, T2 + 1):
+            for r in runners:
+                r.step(t, 1, with_mds=with_mds, graph=True)
+        ms2 = fe.timer_stop_ms()
+        _barrier(ctx, fe)
+        rec2 = np.concatenate([r.results(T2) for r in runners])
+        for r in runners:
+            r.close()
+        (ms2,) = _reduce_max(ctx, ms2)
+        large = {"sequences_per_gpu": S2, "runners": NG2, "steps": K2, "value": world * S2 * K2 / (ms2 * 1e-3), "unit": "frames/s",
+                 "ms_per_step": ms2 / K2, "status_nonzero": int((rec2["status"] != 0).sum()),
+                 "note": "resident; sequence s = frames s, s + 1, ... of the same drive (every sequence a distinct window)"}
     # ---- single-sequence latency: one sequence, graph replay, no host sync between steps -------------------------------
     one = fe.new_sequences(1, T + 2)
     one.upload(0, raw_long[:T + 2])
@@ -1106,6 +1140,8 @@ def leg_chained(ctx, raw_long, cpu):
         "median_dtheta_rad": float(np.median(np.arctan2(recs["R"][..., 2], recs["R"][..., 0]))), "expected_dtheta_rad": 0.025,
         "e2e_status_nonzero": int((e2e_last["status"] != 0).sum()),
     })
+    if large is not None:
+        out["large"] = large
     if cpu is not None:
         out["cpu_baseline"] = {k: v for k, v in cpu.items() if k != "outs"}
     if parity is not None:

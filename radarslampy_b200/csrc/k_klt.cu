@@ -21,13 +21,13 @@
 #include "common.cuh"
 
 #ifndef KLT_WARPS
-#define KLT_WARPS 4
-#endif
+#define KLT_WARPS 2        // warps (features) per CTA.  2 x 8 resident CTAs: 0.637 ms in-step / 0.539 alone per 51 k tracks; 4 x 4: 0.649 / 0.551;
+#endif                     // 8 x 2: 0.734 / 0.822.  Small CTAs fill the register space one-warp clique CTAs of other batches leave on an SM
 #define KLT_WIN 15
 #define KLT_NPIX 225
 #define KLT_PER_LANE 8
 #ifndef KLT_MIN_BLOCKS
-#define KLT_MIN_BLOCKS 4   // resident CTAs per SM the register allocation is capped for; 4, 5 (96 regs) and 6 (80 regs, spills) measured equal
+#define KLT_MIN_BLOCKS 8   // resident CTAs per SM the register allocation is capped for (16 warps x 128 registers); 20 warps (96 regs) and 24 (80 regs, spills) measured equal
 #endif
 
 struct KltArgs {
