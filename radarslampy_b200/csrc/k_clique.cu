@@ -303,6 +303,8 @@ struct CliqueArgs {
     uint32_t* stack;           // [P][Kpad + 1][3 * SW + 1]  (subg | cand | ext | qn)
     int prune;
     const int32_t* max_size;   // [P] exact maximum clique size from k_maxclique (0 = unknown) or nullptr
+    const uint32_t* vstar;     // [P][vstar_stride] vertices that can belong to a clique of that size (k_viable), or nullptr
+    size_t vstar_stride;
     int adj_in_smem;           // adjacency rows staged in shared memory (row stride g.RS words)
     int adjseq_ready;          // adjseq was filled by k_adjseq (one warp per node) before this launch
     long long node_limit;
@@ -495,6 +497,69 @@ __device__ __forceinline__ int colour_bound(uint32_t Q, const uint32_t* __restri
     return k;
 }
 
+// V*: the vertices that can belong to a clique of the known maximum size M.  v stays only while its neighbourhood inside
+// the current V needs at least M - 1 colours (so can hold M - 1 pairwise adjacent vertices); every member of a clique of
+// size M survives every round (its M - 1 fellow members are in its neighbourhood and, by induction, still in V).  On the
+// sparse graphs of freshly re-detected pairs (230 nodes, maximum clique 24) this leaves little more than the consistent
+// set, and the order-exact walk stops descending into branches that only the contextual bound used to rule out — after
+// having built their child sets.  One CTA of VI_WARPS warps per problem, double-buffered V (a round reads one copy and
+// clears bits in the other).
+#define VI_WARPS 16
+__global__ void __launch_bounds__(32 * VI_WARPS) k_viable(CliqueGeom g, int P, const int32_t* __restrict__ counts,
+                                                           const uint32_t* __restrict__ adjbits_all, const int32_t* __restrict__ max_size,
+                                                           uint32_t* __restrict__ vstar_all, size_t vstar_stride) {
+    extern __shared__ uint32_t sm_vi[];
+    __shared__ uint32_t s_v[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    const int K = counts[p];
+    uint32_t* vs = vstar_all + (size_t)p * vstar_stride;
+    const int NWe = (K + 31) >> 5;
+    const int M = max_size[p];
+    if (K <= 0 || M <= 1 || NWe > 32) {                      // unknown size: every vertex stays
+        for (int w = tid; w < g.NW; w += 32 * VI_WARPS) vs[w] = 0xFFFFFFFFu;
+        return;
+    }
+    const int RS = g.RS;
+    const uint32_t* adj_gl = adjbits_all + (size_t)p * g.Kpad * g.NW;
+    for (int t = tid; t < K * NWe; t += 32 * VI_WARPS) {
+        const int r = t / NWe, w = t - r * NWe;
+        sm_vi[r * RS + w] = adj_gl[(size_t)r * g.NW + w];
+    }
+    if (tid < 32) {
+        const int lo = tid * 32;
+        const uint32_t v = K >= lo + 32 ? ~0u : (K > lo ? ((1u << (K - lo)) - 1u) : 0u);
+        s_v[0][tid] = v; s_v[1][tid] = v;
+    }
+    __syncthreads();
+    const int need = M - 1;
+    int cur = 0;
+    for (int round = 0; round < 4; ++round) {
+        const uint32_t* V = s_v[cur];
+        uint32_t* Vn = s_v[cur ^ 1];
+        for (int v = warp; v < K; v += VI_WARPS) {
+            if (!((V[v >> 5] >> (v & 31)) & 1u)) continue;
+            const uint32_t Q = lane < NWe ? (sm_vi[v * RS + lane] & V[lane]) : 0u;
+            bool ok = __reduce_add_sync(FULL, __popc(Q)) >= need;
+            if (ok) ok = colour_bound(Q, sm_vi, RS, NWe, need, lane) >= need;
+            if (!ok && lane == 0) atomicAnd(&Vn[v >> 5], ~(1u << (v & 31)));
+        }
+        __syncthreads();
+        // another round only pays while the set still shrinks fast (a round costs a colouring per vertex: ~0.1 ms on a dense
+        // 200-node graph, where it removes little)
+        int before = 0, after = 0;
+        for (int w = 0; w < NWe; ++w) { before += __popc(s_v[cur][w]); after += __popc(s_v[cur ^ 1][w]); }
+        __syncthreads();
+        // the next round reads what this one wrote; bring the other copy up to date
+        if (tid < 32) s_v[cur][tid] = s_v[cur ^ 1][tid];
+        cur ^= 1;
+        __syncthreads();
+        if ((before - after) * 8 < after) break;
+    }
+    if (tid < g.NW) vs[tid] = tid < 32 ? s_v[cur][tid] : 0u;
+}
+
 // Slot orders of the small-table adjacency sets (adj[v] = {x for x in G[v] if x != v}: ascending adds into a table
 // smaller than the node count), one WARP PER NODE.  Inside k_clique the same work is a sequential prologue of the one
 // search warp (4.5 k cycles per node: 13 % of the search of a sparse 232-node graph, a third of the mean pair of the
@@ -558,7 +623,8 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     int16_t* bestQ = Q + g.Kpad;
     int16_t* deg = bestQ + g.Kpad;
     uint32_t* own = (uint32_t*)(deg + g.Kpad);     // [max(128, 2 NW)] slot arbitration / bitset scratch
-    uint32_t* adj_sm = own + (2 * NW > 128 ? 2 * NW : 128);
+    uint32_t* vst = own + (2 * NW > 128 ? 2 * NW : 128);   // [NW] viable vertices (all ones unless k_viable ran)
+    uint32_t* adj_sm = vst + NW;
     const uint32_t* adj_gl = a.adjbits + (size_t)p * g.Kpad * NW;
     const uint32_t* adjbits = a.adj_in_smem ? adj_sm : adj_gl;
     const int RS = a.adj_in_smem ? g.RS : NW;       // row stride in words
@@ -659,6 +725,11 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
     // colouring bound instead of |cand|, and the search stops at the first clique of size M.
     const int Mmax = Mknown;
     if (Mmax > 0) best = Mmax - 1;
+    // (1c) vertices outside V* (k_viable) are in no clique of size M: a branch on one of them is never descended, and
+    // the colouring bound of a branch only counts candidates inside V*
+    const bool use_vst = Mmax > 0 && a.vstar != nullptr;
+    for (int w = lane; w < NW; w += 32) vst[w] = use_vst ? a.vstar[(size_t)p * a.vstar_stride + w] : 0xFFFFFFFFu;
+    __syncwarp();
     PROF_MARK(2);   // greedy bound
 
     auto enter_node = [&]() {
@@ -926,8 +997,12 @@ __global__ void __launch_bounds__(32) k_clique(const CliqueArgs a) {
                 // sets do not depend on that decision, so the order of later yields is unchanged
                 bool descend = ncand > 0 && !(a.prune && qn + ncand <= best);
                 if (descend && Mmax > 0) {
-                    const uint32_t cw = lane < NWe ? (cand.bits()[lane] & adjq[lane]) : 0u;
-                    descend = qn + colour_bound(cw, adjbits, RS, NWe, best - qn + 1, lane) > best;
+                    if (!((vst[q >> 5] >> (q & 31)) & 1u)) descend = false;
+                    else {
+                        const uint32_t cw = lane < NWe ? (cand.bits()[lane] & adjq[lane] & vst[lane]) : 0u;
+                        descend = qn + __reduce_add_sync(FULL, __popc(cw)) > best &&
+                                  qn + colour_bound(cw, adjbits, RS, NWe, best - qn + 1, lane) > best;
+                    }
                 }
                 if (!descend) EVT(6, 1);
                 if (descend) {
@@ -1303,6 +1378,7 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     a.n_yields = debug ? ws.n_yields : nullptr; a.order_hash = debug ? ws.hash : nullptr;
     a.prof = nullptr;
     a.max_size = nullptr;
+    a.vstar = nullptr; a.vstar_stride = 0;
     static const bool no_mc = getenv("RF_CLIQUE_NO_MAXSIZE") != nullptr;   // diagnostic: the round-1 search (greedy bound only)
     if (!debug && prune && ws.g.Kpad <= 1024 && !no_mc) {
         MaxCliqueArgs m;
@@ -1317,6 +1393,15 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
         k_maxclique<<<ws.P, 32 * MC_WARPS, msm, h->stream>>>(m);
         RF_CHECK_LAUNCH(h);
         a.max_size = ws.max_size;
+        static const bool no_vi = getenv("RF_CLIQUE_NO_VIABLE") != nullptr;   // diagnostic: contextual bounds only
+        const size_t vsm = (size_t)Kp * (NWp | 1) * 4;
+        if (!no_vi && vsm <= 40 * 1024) {
+            // V* lives in k_maxclique's level scratch, which is free once that kernel has finished
+            const size_t vstride = (size_t)MC_WARPS * Kp * NWp;
+            k_viable<<<ws.P, 32 * VI_WARPS, vsm, h->stream>>>(ws.g, ws.P, d_counts, ws.adjbits, ws.max_size, ws.mc_levels, vstride);
+            RF_CHECK_LAUNCH(h);
+            a.vstar = ws.mc_levels; a.vstar_stride = vstride;
+        }
     }
     a.adjseq_ready = 0;
     static const bool no_as = getenv("RF_CLIQUE_NO_ADJSEQ_KERNEL") != nullptr;   // diagnostic: the in-search prologue
@@ -1332,7 +1417,7 @@ static int launch_clique(rf_handle* h, const CliqueWorkspace& ws, const int32_t*
     static const bool want_prof = getenv("RF_CLIQUE_PROFILE") != nullptr;
     long long* d_prof = nullptr;
     if (want_prof && cudaMalloc(&d_prof, (size_t)ws.P * 128) == cudaSuccess) a.prof = d_prof;
-    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + (size_t)(2 * ws.g.NW > 128 ? 2 * ws.g.NW : 128) * 4;
+    size_t smem = (size_t)5 * ws.g.SW * 4 + (size_t)5 * ws.g.Kpad * 2 + (size_t)(2 * ws.g.NW > 128 ? 2 * ws.g.NW : 128) * 4 + (size_t)ws.g.NW * 4;
     const size_t adj_bytes = (size_t)ws.g.Kpad * ws.g.RS * 4;
     a.adj_in_smem = smem + adj_bytes <= 96 * 1024;      // K <= 512: rows live next to the search frame
     if (a.adj_in_smem) smem += adj_bytes;

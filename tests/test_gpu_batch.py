@@ -157,7 +157,7 @@ def test_batch_profiling_and_launch_count():
         for _ in range(3):
             b.run_async(with_mds=True)
         fe.sync()
-        assert fe.launch_count() - n0 == 3 * 13      # interleave, scan->L0+L1, 2 pyrDown levels, klt, compact, adjacency, adjacency slot orders, maxclique, clique, kabsch, mds, finish
+        assert fe.launch_count() - n0 == 3 * 14      # interleave, scan->L0+L1, 2 pyrDown levels, klt, compact, adjacency, maxclique, viable set, adjacency slot orders, clique, kabsch, mds, finish
         ms, runs = b.stage_times()
         assert runs == 3 and all(v >= 0 for v in ms.values()) and ms["polar2cart"] > 0 and ms["klt"] > 0
         b.close()
