@@ -209,6 +209,44 @@ def test_clique_real_data_density_graphs(fe):
         assert size_s == len(clique) and np.array_equal(mask_s, ref_mask), f"K={K} p={p}"
 
 
+def test_clique_sparse_graphs_with_near_maximum_cliques(fe):
+    """The two graph shapes of the chained step.  (a) A freshly re-detected pair: ~230 nodes at edge density
+    0.2-0.3, one maximum clique of 24 next to several planted cliques of 20-23 that share members with it (k_viable's V*, the
+    bound inside V*).  (b) A near-clique with a few "almost inliers" adjacent to most of it (partial identity-layout chains,
+    level-by-level chains in explicit tables, K on both sides of 128).  The production search must return networkx's first
+    maximum clique on every one of them."""
+    from oracle import restate as R
+    rng = np.random.default_rng(77)
+    cases = []
+    for K, p, big, others in [(232, .22, 24, (23, 22, 21, 20)), (200, .28, 24, (23, 23, 22)), (150, .25, 18, (17, 17, 16)),
+                              (232, .20, 24, ())]:
+        M = rng.random((K, K)) < p
+        core = rng.choice(K, big, replace=False)
+        M[np.ix_(core, core)] = True
+        for sz in others:                                   # near-maximum cliques overlapping the maximum one
+            keep = rng.choice(core, sz // 2, replace=False)
+            rest = rng.choice(np.setdiff1d(np.arange(K), core), sz - sz // 2, replace=False)
+            m = np.concatenate([keep, rest])
+            M[np.ix_(m, m)] = True
+        cases.append((f"sparse K={K} p={p}", M))
+    for K, n_out, p_out in [(101, 5, .9), (81, 1, .8), (140, 8, .85), (195, 38, .6), (128, 6, .9), (129, 6, .9)]:
+        M = np.ones((K, K), bool)
+        out = rng.choice(K, n_out, replace=False)
+        for o in out:                                       # an "almost inlier": adjacent to most, not all, of the clique
+            row = rng.random(K) < p_out
+            M[o, :] = row; M[:, o] = row
+        cases.append((f"near-clique K={K} out={n_out}", M))
+    for name, M in cases:
+        K = M.shape[0]
+        M = np.triu(M, 1); M = M | M.T
+        np.fill_diagonal(M, True)
+        adj = M.astype(np.uint8)
+        clique, _ = R.first_max_clique_pruned(adj)
+        ref_mask = np.zeros(K, bool); ref_mask[clique] = True
+        mask_s, size_s, _, _, nodes = fe.clique_search(adj, prune=3)
+        assert size_s == len(clique) and np.array_equal(mask_s, ref_mask), name
+
+
 def test_float64_coordinates_keep_their_precision(fe):
     """rejectOutliers / calculateTransformSVD on float64 coordinates (metric or undistorted points): the reference's cdist and
     SVD then run on them as they are (outlierRejection.py:49-58, getTransformKLT.py:141-162); rf_*_f64 do not round them to
