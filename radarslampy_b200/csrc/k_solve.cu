@@ -12,9 +12,10 @@
 // bit-for-bit, the 2x2 cross-covariance is then accumulated exactly in f64 and the SVD is
 // replaced by the closed-form 2-D optimum theta = atan2(C10 - C01, C00 + C11), which equals
 // U diag(1, det) V^T whenever that is unique.
-// MDS: Levenberg-Marquardt in f64 with an analytic Jacobian derived from the residual the
-// reference defines (its own jacobian() is inconsistent with error() and unused).  The
-// solve converges to the minimiser, which scipy's 'lm' reaches to ~1e-5 m.
+// MDS: damped Newton iteration in f64 with an analytic Jacobian derived from the residual the
+// reference defines (its own jacobian() is inconsistent with error() and unused) and the exact
+// curvature of the robust loss along each residual.  The solve converges to the
+// minimiser, which scipy's 'lm' reaches to ~1e-5 m.
 #include <math.h>
 
 #include "common.cuh"
@@ -137,7 +138,7 @@ struct MdsEval { double cost; double g[6]; double H[21]; };
 #define MDS_WARPS (MDS_THREADS / 32)
 #define MDS_SMEM_PTS 256     // problems with at most this many points keep them in shared memory
 
-// residual, gradient J^T r and Gauss-Newton matrix J^T J at x, reduced over the block (every thread gets the same
+// residual, gradient J^T r and curvature matrix (J^T J plus the loss's own second derivative) at x, reduced over the block (every thread gets the same
 // result: per-thread partial sums -> warp shuffles -> the MDS_WARPS partials added in warp order by every thread)
 __device__ void mds_eval(const double* __restrict__ pts, int N, const double x[6], const double T0inv[6], double th0,
                          const MdsArgs& a, MdsEval& o, double* red, int tid) {
