@@ -44,3 +44,30 @@ def test_algorithmic_bytes_match_design():
     assert sb["scan_to_l0l1"] == 256 * (400 * 1997 + 1996 * 1996 + 998 * 998) == 256 * 5778820
     assert sb["polar2cart"] == 256 * 2 * 400 * 1997
     assert sb["pyr_down"] == 256 * (998 * 998 + 499 * 499 + 499 * 499 + 250 * 250)
+
+
+@pytest.mark.gpu
+def test_product_arm_line_has_the_contract_keys():
+    """Structure of the one JSON line of the GPU arm at a toy size (no timing thresholds): the driver's keys, the
+    roofline / e2e objects, and the step = passes x device batch bookkeeping."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--frames", "32", "--steps", "2", "--warmup", "3",
+                        "--passes-per-step", "2", "--legs", "none", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["metric"] == "radar frames/sec polar->pose" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["data"] == "synthetic"
+    assert d["passes_per_step"] == 2 and abs(d["ms_per_step"] - 2 * d["ms_per_pass"]) <= 1e-9 * d["ms_per_step"]
+    cfg = d["config"]
+    assert cfg["frames_per_step_per_gpu"] == 64 and cfg["pairs_per_step_per_gpu"] == 62 and cfg["frames_per_pass"] == 32 and "workload" in cfg
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == "frames/s" and e["d2h_bytes_per_step"] == 2 * 31 * 120
+    assert e["h2d_bytes_per_step"] >= 2 * 32 * 400 * (11 + 1997)            # every scan of both passes is uploaded
+    ro = d["roofline"]
+    assert ro["bound"] == "hbm" and ro["unit"] == "GB/s" and ro["peak"] > 0 and abs(ro["frac"] - ro["achieved"] / ro["peak"]) < 1e-12
+    assert ro["alg_bytes_per_launch"] == 32 * (400 * 1997 + 1996 * 1996 + 998 * 998) or ro["kernel"] != "scan_to_l0l1"
+    # interleave, scan, 2 pyrDown, klt, compact, adjacency, maxclique, viable, adjseq, clique, kabsch, finish per pass (no MDS)
+    assert d["gpu_launches"] == 2 * 2 * 13
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
