@@ -427,9 +427,17 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
             if (in_smem) for (unsigned i = tid; i < cells; i += SSC_THREADS) s_grid[i] = CELL_EMPTY;
             const bool use_cov = cells <= 32u * SSC_COV_WORDS;
             if (use_cov) for (unsigned i = tid; i < (cells + 31) / 32; i += SSC_THREADS) s_cov[i] = 0u;
-            for (int i = tid; i < n; i += SSC_THREADS) {
-                const double2 q = rc[i];
-                cell[i] = (unsigned)((int)floor(q.x / c) * stride + (int)floor(q.y / c));     // ANMS.py:52-59
+            // (the passes over the live list are bound by the latency of their global loads on this one SM: four
+            // independent elements per trip keep four loads in flight per thread)
+            for (int i0 = tid; i0 < n; i0 += 4 * SSC_THREADS) {
+                double2 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * SSC_THREADS; q[u] = i < n ? rc[i] : make_double2(0.0, 0.0); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * SSC_THREADS;
+                    if (i < n) cell[i] = (unsigned)((int)floor(q[u].x / c) * stride + (int)floor(q[u].y / c));     // ANMS.py:52-59
+                }
             }
             __syncthreads();
             int nal = n;
@@ -437,15 +445,28 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
             uint32_t* src = alive0; uint32_t* dst = alive1;
             while (nal > 0) {
                 // A: best live keypoint of every cell
-                for (int t = tid; t < nal; t += SSC_THREADS) {
-                    const unsigned i = first ? (unsigned)t : src[t];
-                    atomicMin(&g[cell[i]], i);
+                for (int t0 = tid; t0 < nal; t0 += 4 * SSC_THREADS) {
+                    unsigned ii[4], cc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int t = t0 + u * SSC_THREADS; ii[u] = t < nal ? (first ? (unsigned)t : src[t]) : 0u; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cc[u] = (t0 + u * SSC_THREADS < nal) ? cell[ii[u]] : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (t0 + u * SSC_THREADS < nal) atomicMin(&g[cc[u]], ii[u]);
                 }
                 __syncthreads();
                 // B: a keypoint that is the best of its whole neighbourhood is selected
-                for (int t = tid; t < nal; t += SSC_THREADS) {
-                    const unsigned i = first ? (unsigned)t : src[t];
-                    const unsigned ci = cell[i];
+                for (int tb = tid; tb < nal; tb += 4 * SSC_THREADS) {
+                  unsigned bi[4], bc[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) { const int t = tb + u * SSC_THREADS; bi[u] = t < nal ? (first ? (unsigned)t : src[t]) : 0u; }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) bc[u] = (tb + u * SSC_THREADS < nal) ? cell[bi[u]] : 0u;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (tb + u * SSC_THREADS >= nal) continue;
+                    const unsigned i = bi[u];
+                    const unsigned ci = bc[u];
                     if (g[ci] != i) continue;
                     const int r = (int)(ci / (unsigned)stride), cc = (int)(ci - (unsigned)r * (unsigned)stride);
                     const int r0 = max(r - reach, 0), r1 = min(r + reach, ncr), c0 = max(cc - reach, 0), c1 = min(cc + reach, ncc);
@@ -459,6 +480,7 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
                             for (int rr = r0; rr <= r1; ++rr)
                                 for (int c2 = c0; c2 <= c1; ++c2) { const unsigned cj = (unsigned)(rr * stride + c2); atomicOr(&s_cov[cj >> 5], 1u << (cj & 31)); }
                     }
+                  }
                 }
                 __syncthreads();
                 // C: survivors = live keypoints not within reach of a keypoint selected this round
@@ -494,9 +516,14 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
                 }
                 __syncthreads();
                 // D: leave the grid empty again
-                for (int t = tid; t < nal; t += SSC_THREADS) {
-                    const unsigned i = first ? (unsigned)t : src[t];
-                    g[cell[i]] = CELL_EMPTY;
+                for (int t0 = tid; t0 < nal; t0 += 4 * SSC_THREADS) {
+                    unsigned ii[4], cc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int t = t0 + u * SSC_THREADS; ii[u] = t < nal ? (first ? (unsigned)t : src[t]) : 0u; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cc[u] = (t0 + u * SSC_THREADS < nal) ? cell[ii[u]] : 0u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (t0 + u * SSC_THREADS < nal) g[cc[u]] = CELL_EMPTY;
                 }
                 nal = s_next;
                 __syncthreads();
