@@ -485,18 +485,29 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
                 __syncthreads();
                 // C: survivors = live keypoints not within reach of a keypoint selected this round
                 // (uniform trip count: every lane of a warp takes part in the ballot)
-                for (int t0 = 0; t0 < nal; t0 += SSC_THREADS) {
+                for (int tq = 0; tq < nal; tq += 4 * SSC_THREADS) {
+                  // the four elements' index / cell loads are issued together (uniform trip count: every lane of a warp
+                  // takes part in the ballots below)
+                  unsigned qi[4], qc[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) { const int t = tq + u * SSC_THREADS + tid; qi[u] = t < nal ? (first ? (unsigned)t : src[t]) : 0u; }
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) qc[u] = (tq + u * SSC_THREADS + tid < nal) ? cell[qi[u]] : 0u;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const int t0 = tq + u * SSC_THREADS;
+                    if (t0 >= nal) break;
                     const int t = t0 + tid;
                     unsigned i = 0;
                     bool keep = false;
                     if (t < nal) {
-                        i = first ? (unsigned)t : src[t];
+                        i = qi[u];
                         keep = !((mask[i >> 5] >> (i & 31)) & 1u);
                         if (keep && use_cov) {
-                            const unsigned ci = cell[i];
+                            const unsigned ci = qc[u];
                             keep = !((s_cov[ci >> 5] >> (ci & 31)) & 1u);
                         } else if (keep) {
-                            const unsigned ci = cell[i];
+                            const unsigned ci = qc[u];
                             const int r = (int)(ci / (unsigned)stride), cc = (int)(ci - (unsigned)r * (unsigned)stride);
                             const int r0 = max(r - reach, 0), r1 = min(r + reach, ncr), c0 = max(cc - reach, 0), c1 = min(cc + reach, ncc);
                             for (int rr = r0; rr <= r1 && keep; ++rr)
@@ -513,6 +524,7 @@ __global__ void __launch_bounds__(SSC_THREADS) k_ssc_bisect(const SscArgs a) {
                     if (bm && lane == 0) basei = atomicAdd(&s_next, __popc(bm));
                     basei = __shfl_sync(FULLM, basei, 0);
                     if (keep) dst[basei + __popc(bm & ((1u << lane) - 1u))] = i;
+                  }
                 }
                 __syncthreads();
                 // D: leave the grid empty again
